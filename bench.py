@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""Headline benchmark: CFG-DDPM solutions/s on the 80-channel MSR configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one full pass of the hot path over one batch: `DDPM.sample` for `--rows`
+synthetic condition rows (default 1 Mi per GPU; BASELINE.json configs[1]) = T=20 reverse
+steps x 2 UNet passes + guidance + posterior update + 4 batch re-normalisations.
+Rank 0 prints ONE JSON line (see the task contract): `value` = device-resident throughput,
+`e2e` = the same through the public API with pinned-host inputs/outputs copied inside the
+timed region, `roofline` = algorithmic FLOP/s of the sampler kernels against the measured
+bf16 tensor peak, `cpu_baseline` = the reference algorithm (oracle port, torch CPU, all host
+threads) on a bounded sample in the same run.
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port
+in oracle/ddpm_oracle.py, bit-identical to the reference under make_golden.py) on the box's
+host cores; under torchrun only rank 0 runs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T = 20
+OMEGA = 500.0
+NET = dict(input_dim=80, proj_dim=128, cond_dim=80, dims=(64, 32, 16, 8), is_attn=(False,) * 4,
+           middle_attn=False, n_blocks=2)   # 80c = the 3c script with M=80 (ASSUMED)
+METRIC = "CFG-DDPM solutions/sec (80c MSR, T=20, omega=500)"
+FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
+
+
+def build_model(device):
+    import diffsg_b200 as D
+    torch.manual_seed(0)
+    model = D.UNet1D(**NET)          # no 80c checkpoint exists: reference init, seed 0
+    alphas = 1.0 - D.generate_cosine_schedule(T)
+    ddpm = D.msr.DDPM(T, model, NET["input_dim"], 20.0, alphas, device, (1, NET["input_dim"]),
+                      {"scaler_min": 0.5, "scaler_max": 2.5, "W": 20.0}, 0.1, 0.9999, 10, 5, False)
+    ddpm.apply(D.init_weights)       # the reference's own init (diffusion.py:82-84); finite at omega=500
+    return ddpm.to(device)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks + throttle reasons via NVML every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.reasons.update(n for bit, n in names.items() if mask & bit)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_run(sd, rows, reps, warmup):
+    """Reference algorithm on the host cores: oracle port of DDPM.sample (torch CPU ops)."""
+    from oracle import ddpm_oracle as O   # the one sanctioned use of oracle/ outside tests
+    g = torch.Generator().manual_seed(0)
+    cond = torch.rand(rows, NET["cond_dim"], generator=g)
+    times = []
+    with torch.no_grad():
+        for r in range(warmup + reps):
+            y_T, steps = O.draw_noise(rows, (1, NET["input_dim"]), T, 1000 + r)
+            t0 = time.perf_counter()
+            O.sample(sd, T, cond, OMEGA, y_T, steps)
+            if r >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ddpm = build_model("cpu")
+    sd = {k: v.detach().clone() for k, v in ddpm.state_dict().items()}
+    rows = args.ref_rows
+    times = cpu_reference_run(sd, rows, args.steps, args.warmup)
+    dt = sum(times) / len(times)
+    val = rows / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solutions/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"MSR 80c (assumed UNet1D 80/128/80/(64,32,16,8)/2) CFG sampling, {rows} rows/step on host CPU",
+                       "T": T, "omega": OMEGA, "rows_per_step": rows},
+            "cpu_baseline": {"value": val, "unit": "solutions/s", "cores": cores, "kind": "port",
+                             "sample": f"{rows} rows x {args.steps} steps, torch CPU, reference algorithm (oracle port, bit-identical to reference DDPM.sample)"},
+            "e2e": {"value": val, "unit": "solutions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1 << 20, help="condition rows per GPU per step")
+    ap.add_argument("--ref-rows", type=int, default=2048, help="rows per step of the CPU reference arm")
+    ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of the in-run cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+
+    import torch.distributed as dist
+    from diffsg_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ddpm = build_model(dev)
+    ddpm.noise_mode = "philox"          # in-kernel noise: no host traffic on the device-resident path
+    B, M, Cd = args.rows, NET["input_dim"], NET["cond_dim"]
+    ddpm.philox_offset = rank * B        # disjoint noise streams per shard
+    g = torch.Generator().manual_seed(rank)
+    cond_host = torch.rand(B, Cd, generator=g).pin_memory()     # U(0,1) = min-max scaled gains
+    cond = cond_host.to(dev, non_blocking=True)
+    out_host = torch.empty(B, M).pin_memory()
+    prog = ddpm.model.engine().program
+    x_macs, c_macs = prog.gemm_macs()
+    f_alg = T * 2 * 2 * x_macs + 2 * c_macs                     # 45.51 MFLOP for 80c
+
+    def step_resident():
+        return ddpm.sample(cond, OMEGA)
+
+    def step_e2e():
+        c = cond_host.to(dev, non_blocking=True)
+        y = ddpm.sample(c, OMEGA)
+        out_host.copy_(y.reshape(B, M), non_blocking=True)
+        return y
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    _lib.launch_count(reset=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(local_rank) as clk:
+        ev[0].record()
+        for _ in range(args.steps):
+            step_resident()
+        ev[1].record()
+        barrier()
+    launches = _lib.launch_count()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
+    # end to end through the public API, host buffers in and out
+    step_e2e()
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev2[1].record()
+    barrier()
+    ms2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms, ms2 = float(ms), float(ms2)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        total = B * world * args.steps
+        value = total / (ms * 1e-3)
+        e2e = total / (ms2 * 1e-3)
+        peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        ach_tf = (B * args.steps * f_alg) / (ms * 1e-3) / 1e12     # per GPU (rank 0's kernels)
+        line = {"metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: MSR 80c CFG-DDPM sampling (assumed UNet1D 80/128/80/(64,32,16,8)/2, "
+                                       "init_weights N(0,0.01) seed 0), synthetic rand(B,80) conditions, rows sharded per GPU, no collective",
+                           "rows_per_gpu": B, "T": T, "omega": OMEGA, "noise": "in-kernel Philox4x32-10",
+                           "batch_stats": "per shard (reference per-call semantics)",
+                           "l2": f"inputs+state per step {2 * B * M * 4 / 2**20:.0f} MiB > 126 MB L2; no explicit flush",
+                           "engine": "simt-fp32"},
+                "clocks": clk.summary(),
+                "e2e": {"value": e2e, "unit": "solutions/s", "h2d_bytes_per_step": B * Cd * 4 * world,
+                        "d2h_bytes_per_step": B * M * 4 * world, "ms_per_step": ms2 / args.steps},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": ach_tf / peak_tf, "traffic": None,
+                             "kernel": "sample_*_kernel (all launches of one sample() call)",
+                             "flop_per_solution": f_alg, "peak_source": f"{pk_kind} bf16 sustained"}}
+        if world == 1 and not args.no_cpu_baseline:
+            sd = {k: v.detach().cpu().clone() for k, v in ddpm.state_dict().items()}
+            times = cpu_reference_run(sd, args.cpu_rows, 2, 1)
+            v = args.cpu_rows / (sum(times) / len(times))
+            line["cpu_baseline"] = {"value": v, "unit": "solutions/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{args.cpu_rows} rows x 2 repetitions after 1 warm-up, same net/T/omega, torch CPU"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""ctypes binding of `libdiffsg_b200.so` (the C-ABI declared in include/diffsg_b200.h).
+
+The library is built in-tree by `build_library()` (nvcc, sm_100a) and loaded lazily.
+There is no fallback: if the shared object is missing or a call fails, a
+`DiffsgError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libdiffsg_b200.so"
+INCLUDE_DIR = PKG_DIR.parent / "include"
+SOURCES = ("diffsg.cu", "side_kernels.cu", "unet_tc.cu")
+NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared")
+
+ABI_VERSION = 1
+OP_GEMM, OP_LNSW, OP_PUSH, OP_POP = 1, 2, 3, 4
+F_ACC, F_TIME, F_NOBIAS = 1, 2, 4
+BUF_COND, N_BUF = 4, 4
+
+
+class DiffsgError(RuntimeError):
+    pass
+
+
+class Op(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("kind", "src", "dst", "K", "N", "flags", "w_off", "b_off", "t_off", "dcol", "ldw", "pad_")]
+
+
+class Cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("abi_version", "input_dim", "cond_dim", "max_width", "n_skip", "skip_floats", "tt_stride",
+                 "tt_rows", "in_buf", "out_buf", "device")] + [("reserved", C.c_int32 * 5)]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [("cond_dev", C.c_void_p), ("y_dev", C.c_void_p), ("noise_dev", C.c_void_p),
+                ("rec_y_dev", C.c_void_p), ("rec_eps_dev", C.c_void_p), ("stat_ws_dev", C.c_void_p),
+                ("coef_host", C.c_void_p), ("B", C.c_int64), ("T", C.c_int32), ("norm_steps", C.c_int32),
+                ("omega", C.c_float), ("pad_", C.c_uint32), ("philox_seed", C.c_uint64),
+                ("philox_offset", C.c_uint64)]
+
+
+# name -> (restype, argtypes); every symbol include/diffsg_b200.h declares
+_P, _I32, _I64, _F, _D, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
+SYMBOLS = {
+    "diffsg_last_error": (C.c_char_p, []),
+    "diffsg_abi_version": (C.c_int, []),
+    "diffsg_plan_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(Op), _I32, C.POINTER(_I32), C.POINTER(_P)]),
+    "diffsg_plan_destroy": (C.c_int, [_P]),
+    "diffsg_plan_set_weights": (C.c_int, [_P, _P, C.c_size_t, _P, _I32]),
+    "diffsg_unet_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P]),
+    "diffsg_sample": (C.c_int, [_P, C.POINTER(SampleArgs), _P]),
+    "diffsg_launch_count": (C.c_int64, [C.c_int]),
+    "diffsg_philox_normal": (C.c_int, [_P, _I64, _I32, _I32, _U64, _U64, _P]),
+    "diffsg_ema_update": (C.c_int, [_P, _P, _I64, _D, _I32, _P]),
+    "diffsg_ema_update_multi": (C.c_int, [_P, _P, _P, _I32, _I64, _D, _I32, _P]),
+    "diffsg_minmax": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
+    "diffsg_objective_msr": (C.c_int, [_P, _P, _P, _F, _P, _P, _I64, _I32, _P]),
+    "diffsg_rate_msr": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "diffsg_decode_nu": (C.c_int, [_P, _P, _F, _F, _F, _P, _I64, _I32, _P]),
+    "diffsg_rate_nu": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "diffsg_decode_co": (C.c_int, [_P, _P, _I64, _I32, _P]),
+    "diffsg_cost_co": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+}
+
+_lib = None
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise DiffsgError("nvcc not found; cannot build libdiffsg_b200.so")
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [INCLUDE_DIR / "diffsg_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a into diffsg_b200/libdiffsg_b200.so (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(INCLUDE_DIR), *srcs, "-o", str(LIB_PATH)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise DiffsgError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (building it if sources are newer) and bind all symbols."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        try:
+            build_library()
+        except DiffsgError as e:
+            raise DiffsgError(f"{LIB_PATH} is missing and could not be built: {e}") from e
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype, fn.argtypes = res, args
+    got = lib.diffsg_abi_version()
+    if got != ABI_VERSION:
+        raise DiffsgError(f"libdiffsg_b200.so ABI {got} != binding ABI {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().diffsg_last_error()
+        raise DiffsgError(f"{what or 'diffsg call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().diffsg_launch_count(1 if reset else 0))

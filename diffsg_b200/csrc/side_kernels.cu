@@ -1,0 +1,297 @@
+// HBM-bound side kernels: EMA update, decoder statistics, per-problem decode + objective.
+// Reference semantics (reference repo paths):
+//   EMA            ddpm_opt/ema.py:3-14
+//   MSR decode/obj ddpm_opt/classifier_free_MSR.py:239-245, 284-288
+//   NU decode/rate ddpm_opt/classifier_free_NU.py:267-303
+//   CO decode/cost ddpm_opt/classifier_free_CO.py:255-290
+#include <cfloat>
+#include "common.cuh"
+
+namespace diffsg {
+
+static inline int blocks_for(int64_t n, int per_block, int cap = 148 * 16) {
+    int64_t b = (n + per_block - 1) / per_block;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// ---------------------------------------------------------------------------------- EMA
+__global__ void ema_flat_kernel(float* __restrict__ avg, const float* __restrict__ p, int64_t n, float d,
+                                float omd, int copy_first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n4 = (((uintptr_t)avg | (uintptr_t)p) & 15) == 0 ? n / 4 : 0;
+    for (int64_t j = i; j < n4; j += stride) {
+        const float4 pv = reinterpret_cast<const float4*>(p)[j];
+        float4 av = pv;
+        if (!copy_first) {
+            av = reinterpret_cast<float4*>(avg)[j];
+            av.x = d * av.x + omd * pv.x; av.y = d * av.y + omd * pv.y;
+            av.z = d * av.z + omd * pv.z; av.w = d * av.w + omd * pv.w;
+        }
+        reinterpret_cast<float4*>(avg)[j] = av;
+    }
+    for (int64_t j = n4 * 4 + i; j < n; j += stride) avg[j] = copy_first ? p[j] : d * avg[j] + omd * p[j];
+}
+
+__global__ void ema_multi_kernel(float* const* __restrict__ avgs, const float* const* __restrict__ ps,
+                                 const int64_t* __restrict__ sizes, float d, float omd, int copy_first) {
+    const int t = blockIdx.y;
+    float* avg = avgs[t];
+    const float* p = ps[t];
+    const int64_t n = sizes[t];
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        avg[j] = copy_first ? p[j] : d * avg[j] + omd * p[j];
+}
+
+// ------------------------------------------------------------------------------ min/max
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__global__ void minmax_init_kernel(float* mm) { mm[0] = FLT_MAX; mm[1] = -FLT_MAX; }
+__global__ void minmax_kernel(const float* __restrict__ y, int64_t B, int ld, int col0, int width, float* mm) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    const int64_t total = B * width;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / width;
+        const int c = (int)(t - r * width);
+        const float v = y[r * ld + col0 + c];
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    __shared__ float slo[32], shi[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { slo[w] = lo; shi[w] = hi; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        lo = lane < nw ? slo[lane] : FLT_MAX;
+        hi = lane < nw ? shi[lane] : -FLT_MAX;
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (lane == 0) { atomic_min_f(mm, lo); atomic_max_f(mm + 1, hi); }
+    }
+}
+
+// ------------------------------------------------------------------------------ softmax
+// Row softmax over a sub-warp group of G lanes (G = 2^k <= 32); values strided by G.
+template <typename F>
+__device__ __forceinline__ float group_reduce(float v, int G, F f) {
+    for (int o = G >> 1; o > 0; o >>= 1) v = f(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+static inline int group_size(int M) {
+    int g = 1;
+    while (g < M && g < 32) g <<= 1;
+    return g;
+}
+
+// MSR: p = W * softmax((y - mn) / (mx - mn)); rate = sum log2(1 + p * g)
+__global__ void objective_msr_kernel(const float* __restrict__ y, const float* __restrict__ g,
+                                     const float* __restrict__ mm, float W, float* __restrict__ p_out,
+                                     float* __restrict__ rate, int64_t B, int M, int G, int decode) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, gl = lane % G, per_warp = 32 / G;
+    const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float mn = decode ? mm[0] : 0.f, range = decode ? (mm[1] - mm[0]) : 1.f;
+    for (int64_t base = warp_global * per_warp; base < B; base += n_warps * per_warp) {
+        const int64_t row = base + sub;
+        const bool ok = row < B;
+        float r = 0.f;
+        if (decode) {
+            float vmax = -FLT_MAX;
+            if (ok) for (int c = gl; c < M; c += G) vmax = fmaxf(vmax, (y[row * M + c] - mn) / range);
+            vmax = group_reduce(vmax, G, [](float a, float b) { return fmaxf(a, b); });
+            float s = 0.f;
+            if (ok) for (int c = gl; c < M; c += G) s += expf((y[row * M + c] - mn) / range - vmax);
+            s = group_reduce(s, G, [](float a, float b) { return a + b; });
+            if (ok) for (int c = gl; c < M; c += G) {
+                const float p = W * (expf((y[row * M + c] - mn) / range - vmax) / s);
+                if (p_out) p_out[row * M + c] = p;
+                r += log2f(1.0f + p * g[row * M + c]);
+            }
+        } else if (ok) {
+            for (int c = gl; c < M; c += G) r += log2f(1.0f + y[row * M + c] * g[row * M + c]);
+        }
+        r = group_reduce(r, G, [](float a, float b) { return a + b; });
+        if (ok && gl == 0) rate[row] = r;
+    }
+}
+
+// NU decode: uav = (y[:, :2] - mn) / (mx - mn) * (width, height); p = P_sum * softmax(y[:, 2:])
+constexpr int kMaxUsers = 32;
+__global__ void decode_nu_kernel(const float* __restrict__ y, const float* __restrict__ mm, float width,
+                                 float height, float P_sum, float* __restrict__ dec, int64_t B, int K) {
+    const float mn = mm[0], range = mm[1] - mm[0];
+    const int ld = K + 2;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < B; row += (int64_t)gridDim.x * blockDim.x) {
+        const float* yr = y + row * ld;
+        float* d = dec + row * ld;
+        d[0] = (yr[0] - mn) / range * width;
+        d[1] = (yr[1] - mn) / range * height;
+        float vmax = -FLT_MAX;
+        for (int j = 0; j < K; ++j) vmax = fmaxf(vmax, yr[2 + j]);
+        float s = 0.f;
+        for (int j = 0; j < K; ++j) s += expf(yr[2 + j] - vmax);
+        for (int j = 0; j < K; ++j) d[2 + j] = expf(yr[2 + j] - vmax) / s * P_sum;
+    }
+}
+
+// NOMA-UAV sum rate with SIC ordered by channel gain (descending; ties by index).
+__global__ void rate_nu_kernel(const float* __restrict__ dec, const float* __restrict__ xy,
+                               float* __restrict__ rate, int64_t B, int K) {
+    const float sigma_sq = 110.f, rou_0 = 60.f, H2 = 150.f * 150.f;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < B; row += (int64_t)gridDim.x * blockDim.x) {
+        const float* d = dec + row * (K + 2);
+        const float* x = xy + row * 2 * K;
+        float h[kMaxUsers];
+        for (int j = 0; j < K; ++j) {
+            const float dx = x[2 * j] - d[0], dy = x[2 * j + 1] - d[1];
+            h[j] = sqrtf(rou_0 / (H2 + dx * dx + dy * dy));
+        }
+        float r = 0.f;
+        for (int j = 0; j < K; ++j) {
+            float stronger = 0.f;
+            int rank = 0;
+            for (int i = 0; i < K; ++i)
+                if (h[i] > h[j] || (h[i] == h[j] && i < j)) { stronger += d[2 + i]; ++rank; }
+            const float h2 = h[j] * h[j];
+            const float sinr = rank == 0 ? d[2 + j] * h2 / sigma_sq : d[2 + j] / (stronger + sigma_sq / h2);
+            r += log2f(1.0f + sinr);
+        }
+        rate[row] = r;
+    }
+}
+
+// CO decode: softmax(y), zeroed when every logit < -10
+constexpr int kMaxNodes = 32;
+__global__ void decode_co_kernel(const float* __restrict__ y, float* __restrict__ dec, int64_t B, int n) {
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < B; row += (int64_t)gridDim.x * blockDim.x) {
+        const float* yr = y + row * n;
+        float vmax = -FLT_MAX;
+        bool all_low = true;
+        for (int j = 0; j < n; ++j) { vmax = fmaxf(vmax, yr[j]); all_low = all_low && (yr[j] < -10.f); }
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) s += expf(yr[j] - vmax);
+        for (int j = 0; j < n; ++j) dec[row * n + j] = all_low ? 0.f : expf(yr[j] - vmax) / s;
+    }
+}
+
+// CO cost: threshold decisions at 0.1, renormalise the offloaded shares, local vs offload cost
+__global__ void cost_co_kernel(const float* __restrict__ x, const float* __restrict__ alloc,
+                               float* __restrict__ cost, int64_t B, int n) {
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < B; row += (int64_t)gridDim.x * blockDim.x) {
+        const float* xr = x + row * 3 * n;
+        const float* a = alloc + row * n;
+        float ysum = 0.f;
+        int dsum = 0;
+        for (int j = 0; j < n; ++j)
+            if (a[j] > 0.1f) { ysum += a[j]; ++dsum; }
+        const float dden = dsum == 0 ? 0.00001f : (float)dsum;
+        const float diff = (1.0f - ysum) / dden;
+        float c = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (a[j] > 0.1f) c += xr[3 * j + 1] + xr[3 * j + 2] / (a[j] + diff);
+            else c += xr[3 * j];
+        }
+        cost[row] = c;
+    }
+}
+
+}  // namespace diffsg
+
+using namespace diffsg;
+
+extern "C" {
+
+int diffsg_ema_update(float* avg, const float* p, int64_t n, double decay, int32_t copy_first, void* stream) {
+    if (!avg || !p || n < 0) { set_error("ema_update: bad argument"); return DIFFSG_E_INVALID; }
+    if (n == 0) return DIFFSG_OK;
+    ema_flat_kernel<<<blocks_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(avg, p, n, (float)decay,
+                                                                            (float)(1.0 - decay), copy_first);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_ema_update_multi(float* const* avgs, const float* const* ps, const int64_t* sizes,
+                            int32_t n_tensors, int64_t max_size, double decay, int32_t copy_first,
+                            void* stream) {
+    if (!avgs || !ps || !sizes || n_tensors < 0 || n_tensors > 65535) { set_error("ema_update_multi: bad argument"); return DIFFSG_E_INVALID; }
+    if (n_tensors == 0) return DIFFSG_OK;
+    dim3 grid(blocks_for(max_size, 1024, 64), n_tensors);
+    ema_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(avgs, ps, sizes, (float)decay,
+                                                             (float)(1.0 - decay), copy_first);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_minmax(const float* y, int64_t B, int32_t ld, int32_t col0, int32_t width, float* mm, void* stream) {
+    if (!y || !mm || B <= 0 || width <= 0 || col0 < 0 || col0 + width > ld) { set_error("minmax: bad argument"); return DIFFSG_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    minmax_init_kernel<<<1, 1, 0, st>>>(mm);
+    minmax_kernel<<<blocks_for(B * width, 2048, 148 * 4), 256, 0, st>>>(y, B, ld, col0, width, mm);
+    count_launch(2);
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_objective_msr(const float* y, const float* g, const float* mm, float W, float* p_out, float* rate,
+                         int64_t B, int32_t M, void* stream) {
+    if (!y || !g || !mm || !rate || B <= 0 || M <= 0) { set_error("objective_msr: bad argument"); return DIFFSG_E_INVALID; }
+    const int G = group_size(M);
+    objective_msr_kernel<<<blocks_for(B, 256 / G * 4), 256, 0, (cudaStream_t)stream>>>(y, g, mm, W, p_out, rate, B, M, G, 1);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_rate_msr(const float* p, const float* g, float* rate, int64_t B, int32_t M, void* stream) {
+    if (!p || !g || !rate || B <= 0 || M <= 0) { set_error("rate_msr: bad argument"); return DIFFSG_E_INVALID; }
+    const int G = group_size(M);
+    objective_msr_kernel<<<blocks_for(B, 256 / G * 4), 256, 0, (cudaStream_t)stream>>>(p, g, nullptr, 1.f, nullptr, rate, B, M, G, 0);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_decode_nu(const float* y, const float* mm, float width, float height, float P_sum, float* dec,
+                     int64_t B, int32_t K, void* stream) {
+    if (!y || !mm || !dec || B <= 0 || K <= 0) { set_error("decode_nu: bad argument"); return DIFFSG_E_INVALID; }
+    decode_nu_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(y, mm, width, height, P_sum, dec, B, K);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_rate_nu(const float* dec, const float* xy, float* rate, int64_t B, int32_t K, void* stream) {
+    if (!dec || !xy || !rate || B <= 0 || K <= 0 || K > kMaxUsers) { set_error("rate_nu: bad argument (K <= %d)", kMaxUsers); return DIFFSG_E_INVALID; }
+    rate_nu_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(dec, xy, rate, B, K);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_decode_co(const float* y, float* dec, int64_t B, int32_t n, void* stream) {
+    if (!y || !dec || B <= 0 || n <= 0) { set_error("decode_co: bad argument"); return DIFFSG_E_INVALID; }
+    decode_co_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(y, dec, B, n);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_cost_co(const float* x, const float* alloc, float* cost, int64_t B, int32_t n, void* stream) {
+    if (!x || !alloc || !cost || B <= 0 || n <= 0) { set_error("cost_co: bad argument"); return DIFFSG_E_INVALID; }
+    cost_co_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(x, alloc, cost, B, n);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+}  // extern "C"

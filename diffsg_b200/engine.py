@@ -1,0 +1,169 @@
+"""Kernel plan bound to a `UNet1D` module: owns the C-ABI plan, the packed parameter blob
+and the hoisted time tables, and re-packs when the module's parameters change."""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .packer import lower, pack_params, time_table
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.DiffsgError(
+                "diffsg_b200 runs on CUDA (sm_100a) only: got a tensor on "
+                f"'{t.device}'. There is no CPU implementation; move the module and inputs to a B200.")
+
+
+@contextlib.contextmanager
+def _fp32_matmul():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class UNetEngine:
+    def __init__(self, model):
+        params = list(model.parameters())
+        self.device = params[0].device
+        if self.device.type != "cuda":
+            raise _lib.DiffsgError(f"UNet1D parameters live on '{self.device}'; diffsg_b200 needs a CUDA device")
+        self.model = model
+        self.lib = _lib.load()
+        self.program = lower(model)
+        p = self.program
+        cfg = _lib.Cfg(abi_version=_lib.ABI_VERSION, input_dim=p.input_dim, cond_dim=p.cond_dim,
+                       max_width=p.max_width, n_skip=len(p.skip_widths), skip_floats=sum(p.skip_widths),
+                       tt_stride=max(p.tt_stride, 4), tt_rows=0, in_buf=p.in_buf, out_buf=p.out_buf,
+                       device=self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self._ops = p.op_array()
+        sw = (C.c_int32 * max(len(p.skip_widths), 1))(*p.skip_widths)
+        handle = C.c_void_p()
+        _lib.check(self.lib.diffsg_plan_create(C.byref(cfg), self._ops, len(p.ops), sw, C.byref(handle)),
+                   "diffsg_plan_create")
+        self.handle = handle
+        self._sig = None
+        self._blob = None
+        self._tables = {}       # key -> (t_values tuple / T) -> table tensor
+        self._bound_table = None
+        self._stat_ws = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.diffsg_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # ------------------------------------------------------------------ parameter binding
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def refresh(self):
+        """Re-pack the blob if any parameter changed (optimizer step, load_state_dict, ...)."""
+        sig = self._signature()
+        if sig != self._sig:
+            with _fp32_matmul():
+                self._blob = pack_params(self.program, self.device)
+            self._tables.clear()
+            self._bound_table = None
+            self._sig = sig
+
+    def _bind(self, table: torch.Tensor):
+        if self._bound_table is not table:
+            _lib.check(self.lib.diffsg_plan_set_weights(self.handle, self._blob.data_ptr(), self._blob.numel(),
+                                                        table.data_ptr(), table.shape[0]),
+                       "diffsg_plan_set_weights")
+            self._bound_table = table
+
+    def step_table(self, T: int) -> torch.Tensor:
+        """Time-bias table for the sampler: row i <-> t = i / T (reference MSR.py:126)."""
+        key = ("steps", T)
+        if key not in self._tables:
+            t = torch.arange(T, device=self.device) / T
+            with _fp32_matmul():
+                self._tables[key] = time_table(self.model, self.program, t)
+        return self._tables[key]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, t, cond, cond_mask):
+        _require_cuda(x, t, cond, cond_mask)
+        self.refresh()
+        x2 = _f32c(x).reshape(-1, self.program.input_dim)
+        B = x2.shape[0]
+        cond2 = _f32c(cond).reshape(B, self.program.cond_dim)
+        tv = t.detach().reshape(-1).to(torch.float32)
+        if tv.numel() == 1 and B > 1:
+            tv = tv.expand(B)
+        uniq, inv = torch.unique(tv, return_inverse=True)
+        with _fp32_matmul():
+            table = time_table(self.model, self.program, uniq)
+        self._keep = table  # keep alive while bound
+        self._bind(table)
+        mask = None
+        if cond_mask is not None:
+            mask = _f32c(cond_mask).reshape(-1)
+            if mask.numel() == 1 and B > 1:
+                mask = mask.expand(B).contiguous()
+        t_idx = inv.to(torch.int32).contiguous()
+        eps = torch.empty(B, self.program.input_dim, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.diffsg_unet_forward(self.handle, x2.data_ptr(), t_idx.data_ptr(), cond2.data_ptr(),
+                                                mask.data_ptr() if mask is not None else None, eps.data_ptr(),
+                                                B, _lib.stream_ptr()), "diffsg_unet_forward")
+        return eps
+
+    # ------------------------------------------------------------------ sampler
+    def sample(self, cond, y_init, coef, T, omega, *, noise=None, seed=0, offset=0, norm_steps=4,
+               rec_y=None, rec_eps=None):
+        """In-place reverse diffusion on `y_init` ([B, M] fp32 CUDA); returns it."""
+        _require_cuda(cond, y_init, noise, rec_y, rec_eps)
+        self.refresh()
+        table = self.step_table(T)
+        self._bind(table)
+        B = y_init.shape[0]
+        if self._stat_ws is None or self._stat_ws.numel() < 2 * T:
+            self._stat_ws = torch.zeros(2 * max(T, 64), dtype=torch.float64, device=self.device)
+        coef_arr = (C.c_float * (3 * T))(*[float(v) for v in coef])
+        args = _lib.SampleArgs(cond_dev=cond.data_ptr(), y_dev=y_init.data_ptr(),
+                               noise_dev=noise.data_ptr() if noise is not None else None,
+                               rec_y_dev=rec_y.data_ptr() if rec_y is not None else None,
+                               rec_eps_dev=rec_eps.data_ptr() if rec_eps is not None else None,
+                               stat_ws_dev=self._stat_ws.data_ptr(),
+                               coef_host=C.cast(coef_arr, C.c_void_p), B=B, T=T, norm_steps=norm_steps,
+                               omega=float(omega), pad_=0, philox_seed=int(seed) & (2**64 - 1),
+                               philox_offset=int(offset) & (2**64 - 1))
+        _lib.check(self.lib.diffsg_sample(self.handle, C.byref(args), _lib.stream_ptr()), "diffsg_sample")
+        return y_init
+
+
+def unet_forward(model, x, t, cond, cond_mask):
+    """`UNet1D.forward` entry: inference through the fused kernels; training through
+    `diffsg_b200.train` when gradients are required."""
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    if needs_grad:
+        from .train import unet_forward_train
+        return unet_forward_train(model, x, t, cond, cond_mask)
+    return model.engine().forward(x, t, cond, cond_mask)
+
+
+def philox_normal(B: int, M: int, step: int, seed: int, offset: int, device) -> torch.Tensor:
+    """The sampler's own noise stream for (seed, offset, step) as a [B, M] tensor."""
+    out = torch.empty(B, M, dtype=torch.float32, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.diffsg_philox_normal(out.data_ptr(), B, M, step, int(seed) & (2**64 - 1),
+                                            int(offset) & (2**64 - 1), _lib.stream_ptr()), "diffsg_philox_normal")
+    return out

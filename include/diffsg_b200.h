@@ -1,0 +1,203 @@
+/*
+ * diffsg_b200 — C-ABI of the B200-native CFG-DDPM solver path.
+ *
+ * The reference (qiyu3816/DiffSG) is pure Python/PyTorch and has no FFI; its public
+ * surface for this path is the nn.Module API.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root).  The
+ * Python host side (diffsg_b200/*.py) keeps the reference's constructor arguments,
+ * state_dict layout and sample()/forward() signatures and binds these symbols through
+ * ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DIFFSG_E_* code on failure;
+ *     diffsg_last_error() returns a thread-local, NUL-terminated description.
+ *   - all `*_dev` pointers are device pointers on the plan's device, row-major, fp32
+ *     unless stated.  The caller owns every buffer; the library borrows them for the
+ *     duration of the call (weights: until the next diffsg_plan_set_weights / destroy).
+ *   - all work is enqueued on the caller's stream (`stream` = cudaStream_t cast to
+ *     void*); no call synchronises the device.
+ *   - there is no CPU path: a missing/unsupported GPU is an error, never a fallback.
+ */
+#ifndef DIFFSG_B200_H
+#define DIFFSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIFFSG_ABI_VERSION 1
+
+enum {
+    DIFFSG_OK = 0,
+    DIFFSG_E_INVALID = -1,   /* bad argument / malformed program */
+    DIFFSG_E_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    DIFFSG_E_UNSUPPORTED = -3, /* shape outside the compiled limits, or wrong GPU arch */
+    DIFFSG_E_STATE = -4      /* call order (e.g. forward before set_weights) */
+};
+
+/* ---- network program ---------------------------------------------------------------
+ * The host lowers UNet1D (reference ddpm_opt/UNetCF.py:262-356) to a flat list of ops
+ * over four per-row scratch vectors (buffer ids 0..3), a condition vector (id 4) and a
+ * skip stack.  Parameters live in one fp32 blob; offsets are in floats.
+ */
+enum {
+    DIFFSG_OP_GEMM = 1,  /* dst[dcol:dcol+N] (+)= src[0:K] . W[K,N] + bias[N]  (nn.Linear) */
+    DIFFSG_OP_LNSW = 2,  /* dst[0:N] = swish(layer_norm(src[0:N]; gamma, beta, eps=1e-5)) */
+    DIFFSG_OP_PUSH = 3,  /* skip[slot=dcol] = src[0:N]                                     */
+    DIFFSG_OP_POP = 4    /* dst[dcol:dcol+N] = skip[slot=K]                                */
+};
+enum {
+    DIFFSG_F_ACC = 1,       /* GEMM: accumulate into dst instead of overwriting            */
+    DIFFSG_F_TIME = 2,      /* GEMM: add time_table[t_idx[row]][t_off : t_off+N] to bias   */
+    DIFFSG_F_NOBIAS = 4     /* GEMM: no bias vector (b_off ignored)                        */
+};
+#define DIFFSG_BUF_COND 4   /* src id of the swish(cond * mask) vector                     */
+#define DIFFSG_N_BUF 4
+
+typedef struct diffsg_op {
+    int32_t kind;   /* DIFFSG_OP_*                                                         */
+    int32_t src;    /* source buffer id                                                    */
+    int32_t dst;    /* destination buffer id                                               */
+    int32_t K;      /* GEMM: input width (unpadded).  POP: skip slot.                      */
+    int32_t N;      /* GEMM: output width.  LNSW/PUSH/POP: vector width.                   */
+    int32_t flags;  /* DIFFSG_F_*                                                          */
+    int32_t w_off;  /* GEMM: W, stored [K][ldw] (W^T of nn.Linear.weight).  LNSW: gamma.   */
+    int32_t b_off;  /* GEMM: bias.  LNSW: beta.                                            */
+    int32_t t_off;  /* GEMM+TIME: column offset into a time_table row                      */
+    int32_t dcol;   /* GEMM/POP: first destination column.  PUSH: skip slot.               */
+    int32_t ldw;    /* GEMM: row stride of W in floats (N rounded up to 4)                 */
+    int32_t pad_;
+} diffsg_op;
+
+typedef struct diffsg_cfg {
+    int32_t abi_version;   /* DIFFSG_ABI_VERSION                                           */
+    int32_t input_dim;     /* M: width of y / eps (UNet1D input_dim)                       */
+    int32_t cond_dim;      /* C: width of the condition vector                             */
+    int32_t max_width;     /* widest vector any op touches (<= 256)                        */
+    int32_t n_skip;        /* number of skip slots                                         */
+    int32_t skip_floats;   /* sum of skip widths (floats per row)                          */
+    int32_t tt_stride;     /* floats per time_table row                                    */
+    int32_t tt_rows;       /* rows in the time table (T for sampling; U for forward)       */
+    int32_t in_buf;        /* buffer id that receives x / y_t                              */
+    int32_t out_buf;       /* buffer id holding eps after the last op                      */
+    int32_t device;        /* CUDA device ordinal                                          */
+    int32_t reserved[5];
+} diffsg_cfg;
+
+typedef struct diffsg_plan diffsg_plan;
+
+const char* diffsg_last_error(void);
+int diffsg_abi_version(void);
+
+/* Plan = compiled program + plan-lifetime scratch (skip stack, partial sums).
+ * Replaces: UNet1D.__init__ (ddpm_opt/UNetCF.py:262-316) as the owner of the topology. */
+int diffsg_plan_create(const diffsg_cfg* cfg, const diffsg_op* ops, int32_t n_ops,
+                       const int32_t* skip_widths, diffsg_plan** out);
+int diffsg_plan_destroy(diffsg_plan* plan);
+
+/* Bind parameters.  `params_dev`: fp32 blob addressed by the ops' offsets;
+ * `time_table_dev`: [tt_rows][tt_stride] hoisted per-block time biases
+ * (TimeEmbedding + ResidualBlock.time_emb, ddpm_opt/UNetCF.py:30-46,91).
+ * Replaces: nn.Module.load_state_dict / .to(device) for the denoiser. */
+int diffsg_plan_set_weights(diffsg_plan* plan, const float* params_dev, size_t n_params,
+                            const float* time_table_dev, int32_t tt_rows);
+
+/* eps[B,M] = UNet(x[B,M], time row t_idx[B], cond[B,C] * mask[B]).
+ * mask_dev may be NULL (all ones).  Replaces: UNet1D.forward (ddpm_opt/UNetCF.py:318-356). */
+int diffsg_unet_forward(diffsg_plan* plan, const float* x_dev, const int32_t* t_idx_dev,
+                        const float* cond_dev, const float* mask_dev, float* eps_dev,
+                        int64_t B, void* stream);
+
+/* Reverse-diffusion CFG sampler.  Replaces: DDPM.sample
+ * (ddpm_opt/classifier_free_MSR.py:114-155 == _NU.py:143-180 == _CO.py:117-154).
+ *
+ *   for i = T-1 .. 0:
+ *     eps = (1+omega) * UNet(y, i, cond, 1) - omega * UNet(y, i, cond, 0)
+ *     y   = (y - c_eps[i] * eps) * c_rs[i] + c_noise[i] * z_i        (z_i = 0 for i <= 1)
+ *     if i > T-5: y = (y - mean(y)) / sqrt(var_unbiased(y))          (scalars over [B,M])
+ *
+ * coef_host: 3*T floats on the HOST: c_eps[T] | c_rs[T] | c_noise[T].
+ * y_dev: in = y_T, out = y_0 (in place).  noise_dev: NULL => counter-based Philox4x32-10
+ * normals keyed by (seed, step, row, col); else [(T-2)][B][M] injected draws, plane k used
+ * at step i = T-1-k.  rec_y_dev / rec_eps_dev: NULL or [T][B][M] per-step records
+ * (record_denoise_path).  stat_ws_dev: >= 2*T doubles of zero-initialisable workspace.
+ */
+typedef struct diffsg_sample_args {
+    const float* cond_dev;
+    float* y_dev;
+    const float* noise_dev;
+    float* rec_y_dev;
+    float* rec_eps_dev;
+    double* stat_ws_dev;
+    const float* coef_host;
+    int64_t B;
+    int32_t T;
+    int32_t norm_steps;   /* number of leading steps that re-normalise (reference: 4)      */
+    float omega;
+    uint32_t pad_;
+    uint64_t philox_seed;
+    uint64_t philox_offset;
+} diffsg_sample_args;
+
+#ifdef __cplusplus
+static_assert(sizeof(diffsg_op) == 48 && sizeof(diffsg_cfg) == 64 && sizeof(diffsg_sample_args) == 96,
+              "diffsg_b200 ABI struct layout changed: bump DIFFSG_ABI_VERSION and the bindings");
+#endif
+
+int diffsg_sample(diffsg_plan* plan, const diffsg_sample_args* args, void* stream);
+
+/* Number of kernel launches issued by this library on the calling thread since the last
+ * reset (bench.py's `gpu_launches`). */
+int64_t diffsg_launch_count(int reset);
+
+/* Fill out[n] with the sampler's Philox normals for (seed, offset, step) — the exact
+ * stream diffsg_sample uses when noise_dev == NULL (tests / reproducibility). */
+int diffsg_philox_normal(float* out_dev, int64_t B, int32_t M, int32_t step,
+                         uint64_t seed, uint64_t offset, void* stream);
+
+/* avg = copy_first ? p : decay*avg + (1-decay)*p over one flat fp32 buffer.
+ * Replaces: ExponentialMovingAverage.update_parameters (ddpm_opt/ema.py:3-14). */
+int diffsg_ema_update(float* avg_dev, const float* p_dev, int64_t n, double decay,
+                      int32_t copy_first, void* stream);
+
+/* Multi-tensor form: ptr tables live on the device. */
+int diffsg_ema_update_multi(float* const* avg_ptrs_dev, const float* const* p_ptrs_dev,
+                            const int64_t* sizes_dev, int32_t n_tensors, int64_t max_size,
+                            double decay, int32_t copy_first, void* stream);
+
+/* Global (min, max) of a strided [B, width] slice -> mm_dev[2] (decoder statistics). */
+int diffsg_minmax(const float* y_dev, int64_t B, int32_t ld, int32_t col0, int32_t width,
+                  float* mm_dev, void* stream);
+
+/* MSR decode + objective (ddpm_opt/classifier_free_MSR.py:239-245, 284-288):
+ *   p = W * softmax_row((y - mm[0]) / (mm[1] - mm[0]));  rate = sum_j log2(1 + p_j * g_j)
+ * p_out_dev may be NULL. */
+int diffsg_objective_msr(const float* y_dev, const float* g_dev, const float* mm_dev,
+                         float W, float* p_out_dev, float* rate_dev, int64_t B, int32_t M,
+                         void* stream);
+
+/* MSR rate of a given allocation (labels): rate = sum_j log2(1 + p_j * g_j). */
+int diffsg_rate_msr(const float* p_dev, const float* g_dev, float* rate_dev, int64_t B,
+                    int32_t M, void* stream);
+
+/* NU decode (ddpm_opt/classifier_free_NU.py:267-276) and NOMA rate (:279-303).
+ * y: [B, 2+K]; mm = global (min,max) of y[:, :2]; dec_out: [B, 2+K]. */
+int diffsg_decode_nu(const float* y_dev, const float* mm_dev, float width, float height,
+                     float P_sum, float* dec_out_dev, int64_t B, int32_t K, void* stream);
+int diffsg_rate_nu(const float* dec_dev, const float* xy_dev, float* rate_dev, int64_t B,
+                   int32_t K, void* stream);
+
+/* CO decode (ddpm_opt/classifier_free_CO.py:281-290) and cost (:255-278).
+ * x: [B, 3*n] (local, transition, ideal-exec per node); y: [B, n]. */
+int diffsg_decode_co(const float* y_dev, float* dec_out_dev, int64_t B, int32_t n,
+                     void* stream);
+int diffsg_cost_co(const float* x_dev, const float* alloc_dev, float* cost_dev, int64_t B,
+                   int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSG_B200_H */

@@ -1,0 +1,218 @@
+"""CPU-side tests: oracle vs golden vectors, host logic (schedule, state_dict layout, program
+lowering + packing + hoisting), C-ABI library surface.  No GPU needed."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import diffsg_b200 as D
+from diffsg_b200 import _lib
+from diffsg_b200.packer import lower, pack_params, time_table
+from oracle import ddpm_oracle as O
+from oracle.standin import CONFIGS, make_state_dict
+
+from conftest import ROOT, load_golden, nu_checkpoint_model, rel_l2, standin_model
+from program_interp import run_program
+
+T = 20
+
+
+def test_schedule_matches_golden():
+    g = load_golden("schedule_T20.npz")
+    betas = D.generate_cosine_schedule(T)
+    assert np.array_equal(betas, g["betas64"])
+    assert np.array_equal(O.cosine_betas(T), g["betas64"])
+    assert abs(betas[0] - 0.00799272) < 1e-8 and betas[19] == 0.84
+    ddpm, _ = standin_model("attn")
+    for k in ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+              "reciprocal_sqrt_alphas", "remove_noise_coeff", "sqrt_betas"):
+        assert np.array_equal(getattr(ddpm, k).numpy(), g[k]), k
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_state_dict_layout_matches_reference(name, manifest):
+    ddpm, _ = standin_model(name)
+    sd = ddpm.state_dict()
+    ref = manifest[name]
+    assert list(sd.keys()) == sorted(ref, key=list(ref).index) or set(sd.keys()) == set(ref)
+    assert set(sd.keys()) == set(ref)
+    for k, v in sd.items():
+        assert list(v.shape) == ref[k], k
+    assert sd["ema.n_averaged"].dtype == torch.int64
+
+
+def test_nu_checkpoint_keys(manifest):
+    ddpm = nu_checkpoint_model()
+    ref = manifest["nu_ckpt"]
+    sd = ddpm.state_dict()
+    assert len(ref) == 805 and set(sd.keys()) == set(ref)
+    assert all(list(sd[k].shape) == ref[k] for k in ref)
+    cfg = D.infer_config_from_state_dict(sd)
+    assert cfg == dict(input_dim=5, proj_dim=32, cond_dim=6, dims=(32, 16, 8), is_attn=(False,) * 3,
+                       middle_attn=False, n_blocks=2)
+
+
+def test_infer_config_roundtrip():
+    for name, (_, cfg) in CONFIGS.items():
+        m = D.UNet1D(**cfg)
+        got = D.infer_config_from_state_dict(m.state_dict(), prefix="")
+        assert got == {**cfg, "dims": tuple(cfg["dims"]), "is_attn": tuple(cfg["is_attn"])}, name
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_oracle_reproduces_reference_goldens(name):
+    """The committed eps / sampler outputs came from the unmodified reference; the oracle must
+    reproduce them bit-for-bit on this machine too."""
+    g = load_golden(f"standin_{name}.npz")
+    _, cfg = CONFIGS[name]
+    shapes = {k: v.shape for k, v in D.UNet1D(**cfg).state_dict().items()}
+    sd = {"model." + k: v for k, v in make_state_dict(shapes, 1234).items()}
+    sd.update(O.ddpm_buffers(1.0 - O.cosine_betas(T)))
+    x, cond, ts, mask = (torch.tensor(g[k]) for k in ("x", "cond", "ts", "mask"))
+    eps = O.unet_forward(sd, x, ts / T, cond, mask)
+    assert rel_l2(eps, g["eps"]) < 1e-6
+    if name in ("attn", "nu_like"):
+        M = cfg["input_dim"]
+        B = x.shape[0]
+        steps = [torch.tensor(n).reshape(B, 1, M) for n in g["noise"]]
+        y0 = O.sample(sd, T, cond, 3.0, torch.tensor(g["y_T"]).reshape(B, 1, M), steps)
+        assert rel_l2(y0, g["y0_omega3"]) < 1e-5
+
+
+def test_oracle_nu_checkpoint_trace():
+    g = load_golden("nu_trace.npz")
+    ck = {k: torch.tensor(v) for k, v in load_golden("nu_ckpt.npz").items()}
+    B = 64
+    cond = torch.tensor(g["cond"][:B])
+    for step in (0, 7, 19):
+        i = T - 1 - step
+        t = torch.full((1, B), i) / T
+        y = torch.tensor(g["y_in"][step][:B])
+        e1 = O.unet_forward(ck, y, t, cond, torch.ones(B, 1))
+        e0 = O.unet_forward(ck, y, t, cond, torch.zeros(B, 1))
+        assert rel_l2(e1, g["eps_1"][step][:B]) < 1e-6 and rel_l2(e0, g["eps_0"][step][:B]) < 1e-6
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_lowered_program_matches_oracle(name):
+    """packer: topology -> ops, weight transposition/padding, cond-bias folding, time hoisting."""
+    g = load_golden(f"standin_{name}.npz")
+    ddpm, cfg = standin_model(name)
+    prog = lower(ddpm.model)
+    blob = pack_params(prog, "cpu")
+    ts = torch.tensor(g["ts"]).reshape(-1)
+    table = time_table(ddpm.model, prog, torch.arange(T) / T)
+    x, cond, mask = (torch.tensor(g[k]) for k in ("x", "cond", "mask"))
+    eps = run_program(prog, blob, table, x, ts, cond, mask)
+    assert rel_l2(eps, g["eps"]) < 2e-6
+    x_macs, c_macs = prog.gemm_macs()
+    expect = {"msr3c": (546688, 3768), "msr80c": (566400, 100480), "co": (329024, 11736), "nu_like": (60864, 2736)}
+    if name in expect:
+        assert (x_macs, c_macs) == expect[name]
+
+
+def test_program_buffers_never_alias():
+    for name, (_, cfg) in CONFIGS.items():
+        prog = lower(D.UNet1D(**cfg))
+        for o in prog.ops:
+            if o["kind"] in (_lib.OP_GEMM, _lib.OP_LNSW):
+                assert o["src"] != o["dst"], (name, o)
+            if o["kind"] == _lib.OP_GEMM:
+                assert o["w_off"] % 4 == 0 and o["ldw"] % 4 == 0 and o["ldw"] >= o["N"]
+        assert prog.max_width <= 256
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(v) for v in got) == want
+    z = O.philox_normal(4096, 80, 7, seed=42)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+
+
+def test_objective_oracles_match_goldens():
+    g = load_golden("msr_data.npz")
+    dec = O.msr_decode(torch.tensor(g["y_rand"]))
+    assert torch.equal(dec, torch.tensor(g["dec_rand"]))
+    lo, hi, W = g["scaler"]
+    gains = torch.tensor(g["X_test"]) * (hi - lo) + lo
+    assert abs(float(O.msr_rate(torch.tensor(g["Y_test"]), gains.float()).mean()) - 7.533) < 5e-3
+    c = load_golden("co_data.npz")
+    lo, hi = c["scaler"]
+    Xs = (torch.tensor(c["X_test"]) * (hi - lo) + lo).float()
+    cost = O.co_cost(Xs, torch.tensor(c["Y_test"]))
+    assert rel_l2(cost, c["true_cost"]) < 1e-6 and abs(float(cost.mean()) - 2.0587) < 5e-3
+    assert rel_l2(O.co_cost(Xs, O.co_decode(torch.tensor(c["y_rand"]))), c["pred_cost_rand"]) < 1e-6
+    n = load_golden("nu_objective.npz")
+    d = load_golden("nu_data.npz")
+    dec = O.nu_decode(torch.tensor(n["y0_test"]), 400, 400, 18.0)
+    rate = O.nu_rate(dec, torch.tensor(d["X_test"]) * 400.0)
+    assert rel_l2(rate, n["pred_rate_test"]) < 1e-6
+    assert rel_l2(rate[:200], n["rate_calc_ref_first200"]) < 1e-6  # reference rate_calc itself
+    assert 0.88 < float(n["less_ratio_test"]) < 0.93 and 0.89 < float(n["less_ratio_ood"]) < 0.94
+
+
+def test_loaders_handle_reference_names(tmp_path):
+    assert D.msr.parse_scalar_from_name("../datasets/3c_10w_10000samples.csv", "w") == 10.0
+    assert D.msr.parse_scalar_from_name("3c_20w_2000samples_ood.csv", "w") == 20.0
+    assert D.msr.parse_scalar_from_name("x/3u_18mW_10000samples.csv", "mw") == 18.0
+    assert D.msr.parse_scalar_from_name("3u_30mW_1000samples_ood.csv", "mw") == 30.0
+    rng = np.random.default_rng(0)
+    rows = np.concatenate([rng.uniform(0.5, 2.5, (50, 3)), rng.uniform(5, 8, (50, 1)), rng.uniform(0, 10, (50, 3))], 1)
+    p = tmp_path / "3c_10w_50samples.csv"
+    np.savetxt(p, rows, delimiter=",")
+    Xtr, Ytr, Xte, Yte, cfg = D.msr.msr_data_load(str(p))
+    assert Xtr.shape == (35, 3) and Xte.shape == (15, 3) and cfg["W"] == 10.0 and cfg["M"] == 3
+    assert Xtr.min() >= 0 and Xtr.max() <= 1
+
+
+def test_no_cpu_fallback():
+    ddpm, cfg = standin_model("attn")
+    with pytest.raises(_lib.DiffsgError):
+        ddpm.sample(torch.rand(4, cfg["cond_dim"]), 1.0)
+    with pytest.raises(_lib.DiffsgError):
+        with torch.no_grad():
+            ddpm.model(torch.rand(4, cfg["input_dim"]), torch.zeros(1, 4), torch.rand(4, cfg["cond_dim"]), torch.ones(4, 1))
+    with pytest.raises(_lib.DiffsgError):
+        D.objectives.co_cost(torch.rand(4, 9), torch.rand(4, 3))
+
+
+def test_reference_aliases():
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "ddpm_opt" or k.startswith("ddpm_opt.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        D.install_reference_aliases()
+        from ddpm_opt.UNetCF import UNet1D
+        from ddpm_opt.classifier_free_NU import DDPM, custom_decoder, nu_data_load, rate_calc  # noqa: F401
+        from ddpm_opt.classifier_free_MSR import DDPM as M2, msr_data_load  # noqa: F401
+        from ddpm_opt.classifier_free_CO import DDPM as C2, co_data_load, cost_calc  # noqa: F401
+        from ddpm_opt.diffusion import generate_cosine_schedule, init_weights  # noqa: F401
+        from ddpm_opt.ema import ExponentialMovingAverage  # noqa: F401
+        assert UNet1D is D.UNet1D and DDPM is D.nu.DDPM
+    finally:
+        for k in [k for k in sys.modules if k == "ddpm_opt" or k.startswith("ddpm_opt.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports exactly what include/diffsg_b200.h declares."""
+    header = (ROOT / "include" / "diffsg_b200.h").read_text()
+    declared = set(re.findall(r"\b(diffsg_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    _lib.build_library()
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().diffsg_abi_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.Op) == 48 and ctypes.sizeof(_lib.Cfg) == 64 and ctypes.sizeof(_lib.SampleArgs) == 96
