@@ -70,6 +70,7 @@ SYMBOLS = {
     "diffsg_rate_nu": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "diffsg_decode_co": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "diffsg_cost_co": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "diffsg_debug_tc_gemm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, C.c_uint32, C.c_uint32, _I32, _P]),
 }
 
 _lib = None

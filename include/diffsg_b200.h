@@ -197,6 +197,13 @@ int diffsg_decode_co(const float* y_dev, float* dec_out_dev, int64_t B, int32_t 
 int diffsg_cost_co(const float* x_dev, const float* alloc_dev, float* cost_dev, int64_t B,
                    int32_t n, void* stream);
 
+/* ---- test hooks (not part of the product surface) ------------------------------------
+ * One 128-row tcgen05 GEMM tile: C[128,N] = A[128,K] . W[N,K]^T with A split into fp16
+ * (hi, lo) in-kernel and W given as pre-packed fp16 core-matrix images. */
+int diffsg_debug_tc_gemm(const float* A_dev, const void* W_hi_dev, const void* W_lo_dev,
+                         float* C_dev, int32_t K, int32_t N, int32_t nterms, uint32_t layout,
+                         uint32_t lbo, int32_t swap_lbo_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
