@@ -24,6 +24,7 @@ ABI_VERSION = 1
 OP_GEMM, OP_LNSW, OP_PUSH, OP_POP = 1, 2, 3, 4
 F_ACC, F_TIME, F_NOBIAS = 1, 2, 4
 BUF_COND, N_BUF = 4, 4
+ENGINE_SIMT, ENGINE_TC = 0, 1
 
 
 class DiffsgError(RuntimeError):
@@ -39,6 +40,12 @@ class Cfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("abi_version", "input_dim", "cond_dim", "max_width", "n_skip", "skip_floats", "tt_stride",
                  "tt_rows", "in_buf", "out_buf", "device")] + [("reserved", C.c_int32 * 5)]
+
+
+class TcProgramC(C.Structure):
+    _fields_ = [("stages", C.c_void_p), ("chunks", C.c_void_p), ("epis", C.c_void_p), ("skip_widths", C.c_void_p),
+                ("n_stages", C.c_int32), ("n_chunks", C.c_int32), ("n_epi", C.c_int32), ("n_skip", C.c_int32),
+                ("nterms", C.c_int32), ("tt_stride", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class SampleArgs(C.Structure):
@@ -70,6 +77,9 @@ SYMBOLS = {
     "diffsg_rate_nu": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "diffsg_decode_co": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "diffsg_cost_co": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "diffsg_plan_attach_tc": (C.c_int, [_P, C.POINTER(TcProgramC)]),
+    "diffsg_plan_set_tc_weights": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _I32]),
+    "diffsg_plan_set_engine": (C.c_int, [_P, _I32]),
     "diffsg_debug_tc_gemm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, C.c_uint32, C.c_uint32, _I32, _P]),
 }
 

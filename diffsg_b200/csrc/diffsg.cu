@@ -332,6 +332,7 @@ int diffsg_plan_create(const diffsg_cfg* cfg, const diffsg_op* ops, int32_t n_op
 
 int diffsg_plan_destroy(diffsg_plan* p) {
     if (!p) return DIFFSG_OK;
+    tc::tc_destroy(p);
     if (p->d_ops) cudaFree(p->d_ops);
     if (p->d_scratch) cudaFree(p->d_scratch);
     delete p;
@@ -372,9 +373,10 @@ static int grid_for(const diffsg_plan* p, int64_t B) {
 int diffsg_unet_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond,
                         const float* mask, float* eps, int64_t B, void* stream) {
     if (!p || !x || !t_idx || !cond || !eps) { set_error("unet_forward: null argument"); return DIFFSG_E_INVALID; }
-    if (!p->have_weights) { set_error("unet_forward before set_weights"); return DIFFSG_E_STATE; }
+    if (p->engine != DIFFSG_ENGINE_TC && !p->have_weights) { set_error("unet_forward before set_weights"); return DIFFSG_E_STATE; }
     if (B <= 0) return DIFFSG_OK;
     DIFFSG_CUDA_OK(cudaSetDevice(p->cfg.device));
+    if (p->engine == DIFFSG_ENGINE_TC) return tc::tc_forward(p, x, t_idx, cond, mask, eps, B, (cudaStream_t)stream);
     unet_forward_simt_kernel<<<grid_for(p, B), p->warps * 32, p->smem_bytes, (cudaStream_t)stream>>>(
         p->dev, x, t_idx, cond, mask, eps, B);
     count_launch();
@@ -384,13 +386,14 @@ int diffsg_unet_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, co
 
 int diffsg_sample(diffsg_plan* p, const diffsg_sample_args* a, void* stream) {
     if (!p || !a || !a->cond_dev || !a->y_dev || !a->coef_host || !a->stat_ws_dev) { set_error("sample: null argument"); return DIFFSG_E_INVALID; }
-    if (!p->have_weights) { set_error("sample before set_weights"); return DIFFSG_E_STATE; }
+    if (p->engine != DIFFSG_ENGINE_TC && !p->have_weights) { set_error("sample before set_weights"); return DIFFSG_E_STATE; }
     if (a->T <= 0 || a->T > 64) { set_error("T=%d outside [1,64]", a->T); return DIFFSG_E_UNSUPPORTED; }
-    if (a->T > p->tt_rows) { set_error("time table has %d rows, T=%d", p->tt_rows, a->T); return DIFFSG_E_INVALID; }
     if (a->norm_steps < 0) { set_error("norm_steps < 0"); return DIFFSG_E_INVALID; }
     if (a->B <= 0) return DIFFSG_OK;
     DIFFSG_CUDA_OK(cudaSetDevice(p->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->engine == DIFFSG_ENGINE_TC) return tc::tc_sample(p, a, st);
+    if (a->T > p->tt_rows) { set_error("time table has %d rows, T=%d", p->tt_rows, a->T); return DIFFSG_E_INVALID; }
     const int T = a->T;
     const int norm_steps = a->norm_steps > T ? T : a->norm_steps;
     SampleDev S;
@@ -426,6 +429,20 @@ int diffsg_sample(diffsg_plan* p, const diffsg_sample_args* a, void* stream) {
         count_launch();
     }
     DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_plan_attach_tc(diffsg_plan* p, const diffsg_tc_program* prog) { return tc::tc_attach(p, prog); }
+
+int diffsg_plan_set_tc_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_bytes, const float* params,
+                               size_t n_params, const float* tt, int32_t tt_rows) {
+    return tc::tc_set_weights(p, w_hi, w_lo, w_bytes, params, n_params, tt, tt_rows);
+}
+
+int diffsg_plan_set_engine(diffsg_plan* p, int32_t engine) {
+    if (!p || (engine != DIFFSG_ENGINE_SIMT && engine != DIFFSG_ENGINE_TC)) { set_error("set_engine: bad argument"); return DIFFSG_E_INVALID; }
+    if (engine == DIFFSG_ENGINE_TC && !p->tc) { set_error("set_engine: no tensor-core program attached"); return DIFFSG_E_STATE; }
+    p->engine = engine;
     return DIFFSG_OK;
 }
 

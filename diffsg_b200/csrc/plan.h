@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "unet_simt.cuh"
 
+namespace diffsg { namespace tc { struct TcHost; } }
+
 struct diffsg_plan {
     diffsg_cfg cfg{};
     diffsg::PlanDev dev{};
@@ -15,4 +17,19 @@ struct diffsg_plan {
     size_t smem_bytes = 0;
     int tt_rows = 0;
     bool have_weights = false;
+    int engine = DIFFSG_ENGINE_SIMT;
+    diffsg::tc::TcHost* tc = nullptr;   // tensor-core program + scratch (unet_tc.cu)
 };
+
+namespace diffsg {
+namespace tc {
+// implemented in unet_tc.cu
+int tc_attach(diffsg_plan* p, const diffsg_tc_program* prog);
+int tc_set_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_bytes, const float* params,
+                   size_t n_params, const float* tt, int tt_rows);
+int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond, const float* mask,
+               float* eps, int64_t B, cudaStream_t st);
+int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st);
+void tc_destroy(diffsg_plan* p);
+}  // namespace tc
+}  // namespace diffsg

@@ -6,19 +6,19 @@
 //   images and streamed with 1-D bulk TMA, fp32 accumulation in TMEM.
 #include <cstdio>
 
+#include <cstring>
+#include <new>
+
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "unet_tc.cuh"
+#include "plan.h"
 
 namespace diffsg {
 namespace tc {
 
-constexpr int kTileRows = 128;      // rows per CTA tile == UMMA M == TMEM lanes
-constexpr int kChunkK = 64;         // K elements per operand chunk (A slot / W stage)
-constexpr int kSlotBytes = kTileRows * kChunkK * 2;   // one fp16 A chunk (16 KB)
-constexpr int kASlots = 2;
-constexpr int kWStages = 2;
 constexpr int kMaxN = 128;
-constexpr int kStageBytes = kMaxN * kChunkK * 2;      // one fp16 W chunk (16 KB)
+constexpr int kStageBytes = kWStageBytes;
 
 struct GemmTestArgs {
     const float* A;        // [128][K] fp32
@@ -138,6 +138,177 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(GemmTestArgs g) {
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace tc
+}  // namespace diffsg
+
+// ---------------------------------------------------------------------------- host side
+namespace diffsg {
+namespace tc {
+
+struct TcHost {
+    TcDev dev{};
+    Stage* d_stages = nullptr;
+    Chunk* d_chunks = nullptr;
+    Epi* d_epis = nullptr;
+    float* d_scratch = nullptr;
+    int grid_max = 0;
+    size_t smem_bytes = 0;
+    int tt_rows = 0;
+    bool have_weights = false;
+};
+
+void tc_destroy(diffsg_plan* p) {
+    if (!p || !p->tc) return;
+    TcHost* h = p->tc;
+    if (h->d_stages) cudaFree(h->d_stages);
+    if (h->d_chunks) cudaFree(h->d_chunks);
+    if (h->d_epis) cudaFree(h->d_epis);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    delete h;
+    p->tc = nullptr;
+}
+
+int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
+    if (!p || !g || !g->stages || !g->chunks || !g->epis) { set_error("attach_tc: null argument"); return DIFFSG_E_INVALID; }
+    if (g->n_stages <= 0 || g->n_stages > kMaxStages || g->n_chunks <= 0 || g->n_chunks > kMaxChunks || g->n_epi <= 0 ||
+        g->n_epi > kMaxEpi || g->n_skip < 0 || g->n_skip > kMaxSkip) {
+        set_error("attach_tc: program too large (%d stages, %d chunks, %d epilogue ops, %d skips)", g->n_stages, g->n_chunks, g->n_epi, g->n_skip);
+        return DIFFSG_E_UNSUPPORTED;
+    }
+    if (g->nterms < 1 || g->nterms > 3) { set_error("attach_tc: nterms must be 1..3"); return DIFFSG_E_INVALID; }
+    const int M = p->cfg.input_dim, C = p->cfg.cond_dim;
+    if (M > 128 || C > 128) { set_error("attach_tc: input_dim / cond_dim > 128"); return DIFFSG_E_UNSUPPORTED; }
+    // validate records
+    const Stage* st = (const Stage*)g->stages;
+    const Chunk* ch = (const Chunk*)g->chunks;
+    const Epi* ep = (const Epi*)g->epis;
+    for (int i = 0; i < g->n_stages; ++i) {
+        if (st[i].chunk_begin + st[i].n_chunks > g->n_chunks || st[i].epi_begin + st[i].n_epi > g->n_epi ||
+            st[i].region > 1 || st[i].n16 < 1 || st[i].n16 > 8) { set_error("attach_tc: stage %d malformed", i); return DIFFSG_E_INVALID; }
+    }
+    for (int i = 0; i < g->n_chunks; ++i)
+        if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16) { set_error("attach_tc: chunk %d kw=%d", i, ch[i].kw); return DIFFSG_E_INVALID; }
+    for (int i = 0; i < g->n_epi; ++i)
+        if (ep[i].kind < TE_LOAD_TMEM || ep[i].kind > TE_EMIT_COND || ep[i].dp16 > 8 || ep[i].region > 1 ||
+            ((ep[i].kind == TE_LOAD_SKIP || ep[i].kind == TE_STORE_SKIP) && ep[i].slot >= g->n_skip)) {
+            set_error("attach_tc: epilogue op %d malformed", i); return DIFFSG_E_INVALID;
+        }
+    tc_destroy(p);
+    TcHost* h = new (std::nothrow) TcHost();
+    if (!h) { set_error("out of host memory"); return DIFFSG_E_INVALID; }
+    p->tc = h;
+    DIFFSG_CUDA_OK(cudaSetDevice(p->cfg.device));
+    TcDev& D = h->dev;
+    memset(&D, 0, sizeof(D));
+    D.n_stages = g->n_stages; D.n_chunks = g->n_chunks; D.n_epi = g->n_epi;
+    D.nterms = g->nterms; D.tt_stride = g->tt_stride;
+    D.M = M; D.Mp = ((M + 15) / 16) * 16; D.C = C; D.Cp = ((C + 15) / 16) * 16;
+    size_t off = 0;
+    for (int s = 0; s < g->n_skip; ++s) {
+        if (g->skip_widths[s] <= 0 || g->skip_widths[s] > 128 || g->skip_widths[s] % 16) { set_error("attach_tc: skip width"); return DIFFSG_E_INVALID; }
+        D.skip_off[s] = (int)off;
+        off += (size_t)g->skip_widths[s] * kRows;
+    }
+    D.stash_off = (int)off; off += (size_t)D.Mp * kRows;
+    D.cond_off = (int)off;  off += (size_t)D.Cp * kRows;      // 2 images x Cp x 128 fp16 = Cp*128 floats
+    D.scratch_floats = (off + 31) & ~size_t(31);
+    h->grid_max = p->sm_count;                                  // one CTA per SM
+    const int w_terms = g->nterms == 3 ? 2 : 1;
+    h->smem_bytes = 1024 + ((sizeof(SmemLayout) + 1023) & ~size_t(1023)) + (size_t)kWStages * w_terms * kWStageBytes;
+    if ((int)h->smem_bytes > p->max_smem) { set_error("attach_tc: needs %zu B shared memory", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }
+    if (cudaMalloc(&h->d_stages, sizeof(Stage) * g->n_stages) != cudaSuccess ||
+        cudaMalloc(&h->d_chunks, sizeof(Chunk) * g->n_chunks) != cudaSuccess ||
+        cudaMalloc(&h->d_epis, sizeof(Epi) * g->n_epi) != cudaSuccess ||
+        cudaMalloc(&h->d_scratch, sizeof(float) * D.scratch_floats * h->grid_max) != cudaSuccess) {
+        set_error("attach_tc: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        tc_destroy(p);
+        return DIFFSG_E_CUDA;
+    }
+    DIFFSG_CUDA_OK(cudaMemcpy(h->d_stages, st, sizeof(Stage) * g->n_stages, cudaMemcpyHostToDevice));
+    DIFFSG_CUDA_OK(cudaMemcpy(h->d_chunks, ch, sizeof(Chunk) * g->n_chunks, cudaMemcpyHostToDevice));
+    DIFFSG_CUDA_OK(cudaMemcpy(h->d_epis, ep, sizeof(Epi) * g->n_epi, cudaMemcpyHostToDevice));
+    DIFFSG_CUDA_OK(cudaMemset(h->d_scratch, 0, sizeof(float) * D.scratch_floats * h->grid_max));
+    D.stages = h->d_stages; D.chunks = h->d_chunks; D.epis = h->d_epis; D.scratch = h->d_scratch;
+    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    return DIFFSG_OK;
+}
+
+int tc_set_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_bytes, const float* params,
+                   size_t n_params, const float* tt, int tt_rows) {
+    if (!p || !p->tc) { set_error("set_tc_weights: no tensor-core program attached"); return DIFFSG_E_STATE; }
+    if (!w_hi || !params || !tt || tt_rows <= 0 || (p->tc->dev.nterms == 3 && !w_lo)) { set_error("set_tc_weights: null argument"); return DIFFSG_E_INVALID; }
+    if (((uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)params | (uintptr_t)tt) & 15) { set_error("set_tc_weights: blobs must be 16-byte aligned"); return DIFFSG_E_INVALID; }
+    (void)w_bytes; (void)n_params;
+    TcDev& D = p->tc->dev;
+    D.w_hi = (const uint8_t*)w_hi; D.w_lo = (const uint8_t*)w_lo; D.params = params; D.tt = tt;
+    p->tc->tt_rows = tt_rows;
+    p->tc->have_weights = true;
+    return DIFFSG_OK;
+}
+
+static int tc_grid(const diffsg_plan* p, int64_t B) {
+    const int64_t tiles = (B + kRows - 1) / kRows;
+    return (int)(tiles < p->tc->grid_max ? tiles : p->tc->grid_max);
+}
+
+int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond, const float* mask,
+               float* eps, int64_t B, cudaStream_t st) {
+    if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
+    RunArgs R;
+    memset(&R, 0, sizeof(R));
+    R.x = x; R.t_idx = t_idx; R.cond = cond; R.mask = mask; R.eps = eps; R.B = B;
+    tc_unet_kernel<false><<<tc_grid(p, B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+__global__ void tc_renorm_kernel(float* __restrict__ y, float* __restrict__ rec, const double* __restrict__ stt, int64_t n) {
+    const double s = stt[0], q = stt[1];
+    const double mean = s / (double)n;
+    const double var = (q - s * mean) / (double)(n - 1);
+    const float mf = (float)mean, sd = sqrtf((float)var);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = (y[i] - mf) / sd;
+        y[i] = v;
+        if (rec) rec[i] = v;
+    }
+}
+
+int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
+    if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
+    const int T = a->T;
+    if (T > p->tc->tt_rows) { set_error("tensor-core time table has %d rows, T=%d", p->tc->tt_rows, T); return DIFFSG_E_INVALID; }
+    const int norm_steps = a->norm_steps > T ? T : a->norm_steps;
+    RunArgs R;
+    memset(&R, 0, sizeof(R));
+    R.cond = a->cond_dev; R.y = a->y_dev; R.noise = a->noise_dev; R.rec_y = a->rec_y_dev; R.rec_eps = a->rec_eps_dev;
+    R.stats = a->stat_ws_dev; R.B = a->B; R.T = T; R.norm_steps = norm_steps; R.omega = a->omega;
+    R.seed = a->philox_seed; R.offset = a->philox_offset;
+    for (int i = 0; i < T; ++i) { R.c_eps[i] = a->coef_host[i]; R.c_rs[i] = a->coef_host[T + i]; R.c_noise[i] = a->coef_host[2 * T + i]; }
+    DIFFSG_CUDA_OK(cudaMemsetAsync(a->stat_ws_dev, 0, sizeof(double) * 2 * T, st));
+    const int grid = tc_grid(p, a->B);
+    const int64_t n = a->B * (int64_t)p->cfg.input_dim;
+    int i = T - 1;
+    for (int k = 0; k < norm_steps; ++k, --i) {
+        R.step_hi = R.step_lo = i;
+        tc_unet_kernel<true><<<grid, kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+        int rb = (int)((n + 1023) / 1024);
+        if (rb > p->sm_count * 8) rb = p->sm_count * 8;
+        tc_renorm_kernel<<<rb, 256, 0, st>>>(a->y_dev, a->rec_y_dev ? a->rec_y_dev + (int64_t)(T - 1 - i) * n : nullptr,
+                                            a->stat_ws_dev + 2 * i, n);
+        count_launch(2);
+    }
+    if (i >= 0) {
+        R.step_hi = i; R.step_lo = 0;
+        tc_unet_kernel<true><<<grid, kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+        count_launch();
+    }
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
 }
 
 }  // namespace tc

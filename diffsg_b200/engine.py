@@ -7,8 +7,10 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, tc_packer
 from .packer import lower, pack_params, time_table
+
+PRECISIONS = ("auto", "fp32", "fp16x2", "fp16x3")
 
 
 def _require_cuda(*tensors):
@@ -34,7 +36,16 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 class UNetEngine:
-    def __init__(self, model):
+    """precision:
+         "fp32"   exact-fp32 warp-row engine (CUDA cores; any topology)
+         "fp16x2" tcgen05 engine, activations split into fp16 (hi, lo), weights fp16
+         "fp16x3" tcgen05 engine, additionally the fp16 residual of the weights (~fp32 accuracy)
+         "auto"   "fp16x2" when the topology fits the tensor-core engine, else "fp32"
+    """
+
+    def __init__(self, model, precision="auto"):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
         params = list(model.parameters())
         self.device = params[0].device
         if self.device.type != "cuda":
@@ -53,8 +64,26 @@ class UNetEngine:
         _lib.check(self.lib.diffsg_plan_create(C.byref(cfg), self._ops, len(p.ops), sw, C.byref(handle)),
                    "diffsg_plan_create")
         self.handle = handle
+        why = tc_packer.supported(model)
+        if precision == "auto":
+            precision = "fp32" if why else "fp16x2"
+        if precision != "fp32" and why:
+            raise _lib.DiffsgError(f"precision {precision!r} needs the tensor-core engine, which does not support: {why}")
+        self.precision = precision
+        self.tc = None
+        if precision != "fp32":
+            self.tc = tc_packer.lower_tc(model, nterms=3 if precision == "fp16x3" else 2)
+            st, ch, ep = self.tc.arrays()
+            self._tc_arrays = (st, ch, ep, (C.c_int32 * max(len(self.tc.skip_widths), 1))(*self.tc.skip_widths))
+            prog = _lib.TcProgramC(stages=st.ctypes.data, chunks=ch.ctypes.data, epis=ep.ctypes.data,
+                                   skip_widths=C.cast(self._tc_arrays[3], C.c_void_p), n_stages=len(st),
+                                   n_chunks=len(ch), n_epi=len(ep), n_skip=len(self.tc.skip_widths),
+                                   nterms=self.tc.nterms, tt_stride=max(self.tc.tt_stride, 4))
+            _lib.check(self.lib.diffsg_plan_attach_tc(self.handle, C.byref(prog)), "diffsg_plan_attach_tc")
+            _lib.check(self.lib.diffsg_plan_set_engine(self.handle, _lib.ENGINE_TC), "diffsg_plan_set_engine")
         self._sig = None
         self._blob = None
+        self._tc_blobs = None
         self._tables = {}       # key -> (t_values tuple / T) -> table tensor
         self._bound_table = None
         self._stat_ws = None
@@ -77,25 +106,39 @@ class UNetEngine:
         sig = self._signature()
         if sig != self._sig:
             with _fp32_matmul():
-                self._blob = pack_params(self.program, self.device)
+                if self.tc is None:
+                    self._blob = pack_params(self.program, self.device)
+                else:
+                    self._tc_blobs = tc_packer.pack_tc_weights(self.tc, self.device)
             self._tables.clear()
             self._bound_table = None
             self._sig = sig
 
     def _bind(self, table: torch.Tensor):
         if self._bound_table is not table:
-            _lib.check(self.lib.diffsg_plan_set_weights(self.handle, self._blob.data_ptr(), self._blob.numel(),
-                                                        table.data_ptr(), table.shape[0]),
-                       "diffsg_plan_set_weights")
+            if self.tc is None:
+                _lib.check(self.lib.diffsg_plan_set_weights(self.handle, self._blob.data_ptr(), self._blob.numel(),
+                                                            table.data_ptr(), table.shape[0]),
+                           "diffsg_plan_set_weights")
+            else:
+                hi, lo, params = self._tc_blobs
+                _lib.check(self.lib.diffsg_plan_set_tc_weights(
+                    self.handle, hi.data_ptr(), lo.data_ptr() if lo is not None else None, hi.numel() * 2,
+                    params.data_ptr(), params.numel(), table.data_ptr(), table.shape[0]), "diffsg_plan_set_tc_weights")
             self._bound_table = table
+
+    def _time_table(self, t_values):
+        with _fp32_matmul():
+            if self.tc is None:
+                return time_table(self.model, self.program, t_values)
+            return tc_packer.time_table_tc(self.model, self.tc, t_values)
 
     def step_table(self, T: int) -> torch.Tensor:
         """Time-bias table for the sampler: row i <-> t = i / T (reference MSR.py:126)."""
         key = ("steps", T)
         if key not in self._tables:
             t = torch.arange(T, device=self.device) / T
-            with _fp32_matmul():
-                self._tables[key] = time_table(self.model, self.program, t)
+            self._tables[key] = self._time_table(t)
         return self._tables[key]
 
     # ------------------------------------------------------------------ forward
@@ -109,8 +152,7 @@ class UNetEngine:
         if tv.numel() == 1 and B > 1:
             tv = tv.expand(B)
         uniq, inv = torch.unique(tv, return_inverse=True)
-        with _fp32_matmul():
-            table = time_table(self.model, self.program, uniq)
+        table = self._time_table(uniq)
         self._keep = table  # keep alive while bound
         self._bind(table)
         mask = None

@@ -1,0 +1,374 @@
+"""Lower a `UNet1D` to the tensor-core engine's stage program (include/diffsg_b200.h,
+"tensor-core program").
+
+One CTA carries a 128-row tile; thread == row == TMEM lane.  The network becomes a list of
+STAGES.  A stage is one GEMM group (every MMA accumulates into one 128-column TMEM region)
+followed by an EPILOGUE: a short list of micro-ops over one per-thread register vector
+v[<=128] that loads the accumulator (+ bias / hoisted time bias), optionally spills it to the
+skip stack, computes LayerNorm statistics, and EMITS the next stage's A operand as fp16
+(hi, lo) K-chunks into the shared-memory operand ring.
+
+Layout decisions made here:
+  * activations x live in TMEM as x = acc[region] + xb, with xb a host-precomputed cumulative
+    bias vector, so the residual add `h + x` is the MMA accumulating into x's own region;
+  * `cat(x, skip)` is never materialised: its K-chunks are emitted skip-part first, x-part
+    second, and the weight rows are permuted to match;
+  * an UpBlock's `lin3(a3) + shortcut(cat(x, skip))` is ONE GEMM group of K = D + 2D;
+  * weights are fp16 core-matrix images ([n/8][k/8][n%8][8], one image per <=64-wide K-chunk)
+    streamed by 1-D bulk TMA; with nterms == 3 a second image holds the fp16 residual of W;
+  * widths are padded to multiples of 16 (UMMA K / N granularity); pad rows/cols are zero.
+Reference semantics: ddpm_opt/UNetCF.py:83-95, :318-356.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .unet import AttentionBlock, DownBlock, Downsample, ResidualBlock, UNet1D, UpBlock, Upsample
+
+CHUNK_K = 64
+MAX_W = 128
+
+# epilogue micro-op kinds (mirror include/diffsg_b200.h)
+TE_LOAD_TMEM, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT = 1, 2, 3, 4, 5
+TE_STATS, TE_EMIT_LN, TE_EMIT_RAW, TE_EMIT_COND = 6, 7, 8, 9
+STATS_RESET, STATS_FINISH = 1, 2
+
+EPI_DT = np.dtype([("kind", "u1"), ("region", "u1"), ("dp16", "u1"), ("flags", "u1"), ("dt", "u2"), ("slot", "u2"),
+                   ("off0", "i4"), ("off1", "i4")])
+CHUNK_DT = np.dtype([("kw", "u2"), ("flags", "u2"), ("w_off16", "u4")])          # w_off16: offset / 16 bytes
+STAGE_DT = np.dtype([("chunk_begin", "u2"), ("n_chunks", "u2"), ("epi_begin", "u2"), ("n_epi", "u2"),
+                     ("n16", "u1"), ("region", "u1"), ("accumulate", "u1"), ("has_gemm", "u1"), ("pad", "u4")])
+CHUNK_COND = 1
+
+
+def pad16(n: int) -> int:
+    return max(16, (n + 15) & ~15)
+
+
+def supported(model: UNet1D) -> str | None:
+    """None if the tensor-core engine can run this topology, else the reason it cannot."""
+    widths = [model.proj_dim, *model.dims]
+    if any(w > MAX_W for w in widths):
+        return f"width > {MAX_W}"
+    if model.input_dim > MAX_W or model.cond_dim > MAX_W:
+        return f"input_dim / cond_dim > {MAX_W}"
+    if any(model.is_attn) or model.middle_attn:
+        return "attention blocks"
+    return None
+
+
+@dataclass
+class TcProgram:
+    stages: list = field(default_factory=list)
+    chunks: list = field(default_factory=list)
+    epis: list = field(default_factory=list)
+    wpieces: list = field(default_factory=list)     # (byte offset, n_pad, kw, fn -> [n, kw] fp32 weight slice)
+    ppieces: list = field(default_factory=list)     # (float offset, n, fn -> flat fp32)
+    w_bytes: int = 0
+    n_params: int = 0
+    skip_widths: list = field(default_factory=list)  # padded widths
+    time_blocks: list = field(default_factory=list)
+    tt_stride: int = 0
+    input_dim: int = 0
+    cond_dim: int = 0
+    nterms: int = 2
+    _open: dict | None = None
+
+    # ---- blobs
+    def vec(self, fn, n: int, npad: int) -> int:
+        off = self.n_params
+        self.ppieces.append((off, n, fn))
+        self.n_params += (npad + 3) & ~3
+        return off
+
+    def weight_chunk(self, fn, n: int, npad: int, k: int, kw: int) -> int:
+        """fn() -> [n, k] fp32 (rows = output features, cols = this chunk's K slice)."""
+        off = self.w_bytes
+        self.wpieces.append((off, n, npad, k, kw, fn))
+        self.w_bytes += npad * kw * 2
+        return off
+
+    # ---- stage construction
+    def begin_stage(self, n_out: int, region: int, accumulate: bool, has_gemm: bool = True):
+        assert self._open is None
+        self._open = dict(chunk_begin=len(self.chunks), n16=pad16(n_out) // 16, region=region,
+                          accumulate=int(accumulate), has_gemm=int(has_gemm), epi_begin=None)
+
+    def add_k_segment(self, weight_fn, n_out: int, k: int, cond: bool = False):
+        """Append the K-chunks of one operand segment of width k (weight_fn() -> [n_out, k])."""
+        npad, kp = pad16(n_out), pad16(k)
+        for k0 in range(0, kp, CHUNK_K):
+            kw = min(CHUNK_K, kp - k0)
+            kreal = max(0, min(k - k0, kw))
+            off = self.weight_chunk(lambda k0=k0, kreal=kreal: weight_fn()[:, k0:k0 + kreal], n_out, npad, kreal, kw)
+            self.chunks.append(dict(kw=kw, flags=CHUNK_COND if cond else 0, w_off16=off // 16))
+
+    def epi(self, kind, region=0, dp=16, flags=0, dt=0, slot=0, off0=-1, off1=-1):
+        st = self._open
+        if st["epi_begin"] is None:
+            st["epi_begin"] = len(self.epis)
+        self.epis.append(dict(kind=kind, region=region, dp16=dp // 16, flags=flags, dt=dt, slot=slot, off0=off0, off1=off1))
+
+    def end_stage(self):
+        st = self._open
+        st["n_chunks"] = len(self.chunks) - st["chunk_begin"]
+        if st["epi_begin"] is None:
+            st["epi_begin"] = len(self.epis)
+        st["n_epi"] = len(self.epis) - st["epi_begin"]
+        self.stages.append(st)
+        self._open = None
+
+    # ---- arrays for the C-ABI
+    def arrays(self):
+        s = np.zeros(len(self.stages), STAGE_DT)
+        for i, d in enumerate(self.stages):
+            for k in ("chunk_begin", "n_chunks", "epi_begin", "n_epi", "n16", "region", "accumulate", "has_gemm"):
+                s[i][k] = d[k]
+        c = np.zeros(len(self.chunks), CHUNK_DT)
+        for i, d in enumerate(self.chunks):
+            c[i] = (d["kw"], d["flags"], d["w_off16"])
+        e = np.zeros(len(self.epis), EPI_DT)
+        for i, d in enumerate(self.epis):
+            e[i] = (d["kind"], d["region"], d["dp16"], d["flags"], d["dt"], d["slot"], d["off0"], d["off1"])
+        return s, c, e
+
+    def gemm_macs(self):
+        """(x-path, cond) algorithmic MACs per row-forward from the un-padded shapes."""
+        x = c = 0
+        for (_, n, _, k, _, _), ch in zip(self.wpieces, self.chunks):
+            if ch["flags"] & CHUNK_COND:
+                c += n * k
+            else:
+                x += n * k
+        return x, c
+
+
+def _emit_next(p: TcProgram, plan, xr, xb_off, width):
+    """Epilogue tail shared by every stage that ends with a finished activation x (in region xr,
+    bias xb): what it must EMIT depends on the module that consumes x next (`plan`)."""
+    dp = pad16(width)
+    kind = plan[0]
+    if kind == "res":            # identity-shortcut ResidualBlock: LN1 -> Swish
+        blk = plan[1]
+        p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=width)
+        g = p.vec(lambda: blk.norm1.weight, width, dp)
+        b = p.vec(lambda: blk.norm1.bias, width, dp)
+        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g, off1=b)
+    elif kind == "raw":          # Down/Upsample Linear consumes x itself
+        p.epi(TE_EMIT_RAW, dp=dp, dt=width)
+    elif kind == "up":           # UpBlock: LN1 over cat(x, skip); chunks: skip part, then x part
+        blk, slot = plan[1], plan[2]
+        g_x = p.vec(lambda: blk.norm1.weight[:width], width, dp)
+        b_x = p.vec(lambda: blk.norm1.bias[:width], width, dp)
+        g_s = p.vec(lambda: blk.norm1.weight[width:], width, dp)
+        b_s = p.vec(lambda: blk.norm1.bias[width:], width, dp)
+        p.epi(TE_STATS, flags=STATS_RESET, dp=dp, dt=width)
+        p.epi(TE_LOAD_SKIP, dp=dp, dt=width, slot=slot)
+        p.epi(TE_STATS, flags=STATS_FINISH, dp=dp, dt=width)
+        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g_s, off1=b_s)
+        p.epi(TE_LOAD_TMEM, region=xr, dp=dp, dt=width, off0=xb_off)
+        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g_x, off1=b_x)
+    elif kind == "final":
+        norm = plan[1]
+        p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=width)
+        g = p.vec(lambda: norm.weight, width, dp)
+        b = p.vec(lambda: norm.bias, width, dp)
+        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g, off1=b)
+    else:
+        raise ValueError(kind)
+
+
+def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
+    why = supported(model)
+    if why:
+        raise ValueError(f"tensor-core engine does not support this UNet1D: {why}")
+    p = TcProgram(input_dim=model.input_dim, cond_dim=model.cond_dim, nterms=nterms)
+    M, C = model.input_dim, model.cond_dim
+
+    # flat module sequence with look-ahead ("what consumes x next?")
+    seq = []
+    for m in model.down:
+        seq.append(("down_res", m.res) if isinstance(m, DownBlock) else ("lin", m.lin))
+    seq += [("mid_res", model.middle.res1), ("mid_res", model.middle.res2)]
+    for m in model.up:
+        seq.append(("up_res", m.res) if isinstance(m, UpBlock) else ("lin", m.lin))
+    seq.append(("final", None))
+
+    # skip slots are pushed after feature_proj and after every `down` module, popped LIFO by UpBlocks
+    n_push = 1 + len(model.down)
+    pops = [i for i, (k, _) in enumerate(seq) if k == "up_res"]
+    assert len(pops) == n_push
+    pop_slot = {idx: n_push - 1 - j for j, idx in enumerate(pops)}
+
+    def consumer_plan(i):
+        k, mod = seq[i]
+        if k in ("down_res", "mid_res"):
+            return ("res", mod)
+        if k == "lin":
+            return ("raw",)
+        if k == "up_res":
+            return ("up", mod, pop_slot[i])
+        return ("final", model.norm)
+
+    # ---- stage 0: operand of feature_proj = the raw input row
+    p.begin_stage(16, 0, False, has_gemm=False)
+    p.epi(TE_LOAD_INPUT, dp=pad16(M), dt=M)
+    p.epi(TE_EMIT_RAW, dp=pad16(M), dt=M)
+    p.end_stage()
+
+    # ---- feature_proj
+    fp = model.feature_proj
+    width = model.proj_dim
+    xr = 0
+    p.begin_stage(width, xr, False)
+    p.add_k_segment(lambda: fp.weight, width, M)
+    xb = [lambda: fp.bias]                 # list of bias terms summed into the cumulative vector
+    xb_off = p.vec(lambda xb=tuple(xb): sum(f() for f in xb), width, pad16(width))
+    p.epi(TE_LOAD_TMEM, region=xr, dp=pad16(width), dt=width, off0=xb_off)
+    slot = 0
+    p.skip_widths.append(pad16(width))
+    p.epi(TE_STORE_SKIP, dp=pad16(width), dt=width, slot=slot)
+    _emit_next(p, consumer_plan(0), xr, xb_off, width)
+    p.end_stage()
+    slot += 1
+    n_down = len(model.down)
+
+    def res_inner(blk: ResidualBlock, din, dout, hr):
+        """G1 and G2 of a ResidualBlock (operands of G1 already emitted); leaves A3 emitted."""
+        t_off = p.tt_stride
+        p.time_blocks.append((t_off, blk.time_emb))
+        p.tt_stride += pad16(dout)
+        dp = pad16(dout)
+        return t_off, dp
+
+    for i, (kind, mod) in enumerate(seq):
+        nxt = consumer_plan(i + 1) if i + 1 < len(seq) else None
+        if kind == "lin":
+            lin = mod
+            hr = 1 - xr
+            p.begin_stage(lin.out_features, hr, False)
+            p.add_k_segment(lambda lin=lin: lin.weight, lin.out_features, lin.in_features)
+            width = lin.out_features
+            xr = hr
+            xb = [lambda lin=lin: lin.bias]
+            xb_off = p.vec(lambda xb=tuple(xb): sum(f() for f in xb), width, pad16(width))
+            p.epi(TE_LOAD_TMEM, region=xr, dp=pad16(width), dt=width, off0=xb_off)
+            if i < n_down:
+                p.skip_widths.append(pad16(width))
+                p.epi(TE_STORE_SKIP, dp=pad16(width), dt=width, slot=slot)
+                slot += 1
+            _emit_next(p, nxt, xr, xb_off, width)
+            p.end_stage()
+        elif kind in ("down_res", "mid_res", "up_res"):
+            blk: ResidualBlock = mod
+            dout = blk.out_dim
+            dp = pad16(dout)
+            hr = 1 - xr
+            is_up = kind == "up_res"
+            t_off = p.tt_stride
+            p.time_blocks.append((t_off, blk.time_emb))
+            p.tt_stride += dp
+            # ---- G1: h = lin1(a1) + b1 + time
+            p.begin_stage(dout, hr, False)
+            if is_up:   # K order: skip part (cat columns [width:]) then x part (cat columns [:width])
+                p.add_k_segment(lambda blk=blk, w=width: blk.lin1.weight[:, w:], dout, blk.in_dim - width)
+                p.add_k_segment(lambda blk=blk, w=width: blk.lin1.weight[:, :w], dout, width)
+            else:
+                p.add_k_segment(lambda blk=blk: blk.lin1.weight, dout, blk.in_dim)
+            b1 = p.vec(lambda blk=blk: blk.lin1.bias, dout, dp)
+            p.epi(TE_LOAD_TMEM, region=hr, dp=dp, dt=dout, off0=b1, off1=t_off)
+            p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=dout)
+            g = p.vec(lambda blk=blk: blk.norm2.weight, dout, dp)
+            b = p.vec(lambda blk=blk: blk.norm2.bias, dout, dp)
+            p.epi(TE_EMIT_LN, dp=dp, dt=dout, off0=g, off1=b)
+            p.epi(TE_EMIT_COND)
+            p.end_stage()
+            # ---- G2: h = lin2(a2) + b2 + cond_emb(swish(cond))
+            p.begin_stage(dout, hr, False)
+            p.add_k_segment(lambda blk=blk: blk.lin2.weight, dout, dout)
+            p.add_k_segment(lambda blk=blk: blk.cond_emb.weight, dout, C, cond=True)
+            b2 = p.vec(lambda blk=blk: blk.lin2.bias + blk.cond_emb.bias, dout, dp)
+            p.epi(TE_LOAD_TMEM, region=hr, dp=dp, dt=dout, off0=b2)
+            p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=dout)
+            g = p.vec(lambda blk=blk: blk.norm3.weight, dout, dp)
+            b = p.vec(lambda blk=blk: blk.norm3.bias, dout, dp)
+            p.epi(TE_EMIT_LN, dp=dp, dt=dout, off0=g, off1=b)
+            if is_up:   # raw operands of the shortcut Linear: x part, then skip part
+                sw = blk.in_dim - width
+                p.epi(TE_LOAD_TMEM, region=xr, dp=pad16(width), dt=width, off0=xb_off)
+                p.epi(TE_EMIT_RAW, dp=pad16(width), dt=width)
+                p.epi(TE_LOAD_SKIP, dp=pad16(sw), dt=sw, slot=pop_slot[i])
+                p.epi(TE_EMIT_RAW, dp=pad16(sw), dt=sw)
+            p.end_stage()
+            # ---- G3: x' = lin3(a3) + b3 + shortcut(x)
+            if is_up:
+                p.begin_stage(dout, hr, False)
+                p.add_k_segment(lambda blk=blk: blk.lin3.weight, dout, dout)
+                p.add_k_segment(lambda blk=blk, w=width: blk.shortcut.weight[:, :w], dout, width)
+                p.add_k_segment(lambda blk=blk, w=width: blk.shortcut.weight[:, w:], dout, blk.in_dim - width)
+                xr = hr
+                xb = [lambda blk=blk: blk.lin3.bias, lambda blk=blk: blk.shortcut.bias]
+            else:
+                assert isinstance(blk.shortcut, nn.Identity) and blk.in_dim == dout
+                p.begin_stage(dout, xr, True)
+                p.add_k_segment(lambda blk=blk: blk.lin3.weight, dout, dout)
+                xb = xb + [lambda blk=blk: blk.lin3.bias]
+            width = dout
+            xb_off = p.vec(lambda xb=tuple(xb): sum(f() for f in xb), width, dp)
+            p.epi(TE_LOAD_TMEM, region=xr, dp=dp, dt=width, off0=xb_off)
+            if kind == "down_res" and i < n_down:
+                p.skip_widths.append(dp)
+                p.epi(TE_STORE_SKIP, dp=dp, dt=width, slot=slot)
+                slot += 1
+            _emit_next(p, nxt, xr, xb_off, width)
+            p.end_stage()
+        elif kind == "final":
+            fin = model.final
+            hr = 1 - xr
+            p.begin_stage(M, hr, False)
+            p.add_k_segment(lambda: fin.weight, M, fin.in_features)
+            bf = p.vec(lambda: fin.bias, M, pad16(M))
+            p.epi(TE_LOAD_TMEM, region=hr, dp=pad16(M), dt=M, off0=bf)
+            p.epi(TE_STORE_OUT, dp=pad16(M), dt=M)
+            p.end_stage()
+    assert slot == n_push, (slot, n_push)
+    return p
+
+
+def pack_tc_weights(p: TcProgram, device):
+    """-> (w_hi uint8 blob, w_lo uint8 blob or None, params fp32 blob) on `device`."""
+    with torch.no_grad():
+        hi = torch.zeros(max(p.w_bytes // 2, 8), dtype=torch.float16, device=device)
+        lo = torch.zeros_like(hi) if p.nterms >= 3 else None
+        for off, n, npad, k, kw, fn in p.wpieces:
+            w = torch.zeros(npad, kw, dtype=torch.float32, device=device)
+            if k > 0:
+                w[:n, :k] = fn().detach().to(device=device, dtype=torch.float32)
+            wh = w.to(torch.float16)
+            img = lambda t: t.reshape(npad // 8, 8, kw // 8, 8).permute(0, 2, 1, 3).reshape(-1)
+            hi[off // 2:off // 2 + npad * kw] = img(wh)
+            if lo is not None:
+                lo[off // 2:off // 2 + npad * kw] = img((w - wh.to(torch.float32)).to(torch.float16))
+        params = torch.zeros(max(p.n_params, 4), dtype=torch.float32, device=device)
+        for off, n, fn in p.ppieces:
+            params[off:off + n] = fn().detach().to(device=device, dtype=torch.float32).reshape(-1)
+    return hi, lo, params
+
+
+def time_table_tc(model: UNet1D, p: TcProgram, t_values: torch.Tensor) -> torch.Tensor:
+    """Same hoisted time path as packer.time_table, laid out for this program's t_off."""
+    from .packer import _swish, sinusoid
+    te = model.time_emb
+    F = torch.nn.functional
+    with torch.no_grad():
+        e = sinusoid(t_values, model.proj_dim)
+        e = F.linear(_swish(F.linear(e, te.lin1.weight, te.lin1.bias)), te.lin2.weight, te.lin2.bias)
+        a = _swish(e)
+        tab = torch.zeros(a.shape[0], max(p.tt_stride, 4), dtype=torch.float32, device=a.device)
+        for t_off, lin in p.time_blocks:
+            tab[:, t_off:t_off + lin.out_features] = F.linear(a, lin.weight, lin.bias)
+    return tab.contiguous()

@@ -150,13 +150,15 @@ class UNet1D(nn.Module):
         self.final = nn.Linear(width, input_dim)
 
         self._engine = None  # lazily-built kernel plan (diffsg_b200.engine.UNetEngine)
+        self.precision = "auto"  # "auto" | "fp32" | "fp16x2" | "fp16x3" (see engine.UNetEngine)
 
     # ------------------------------------------------------------------ kernel glue
     def engine(self):
         """The kernel plan bound to this module's current parameters (built on demand)."""
         from .engine import UNetEngine
-        if self._engine is None:
-            self._engine = UNetEngine(self)
+        if self._engine is None or self._engine.precision_request != self.precision:
+            self._engine = UNetEngine(self, self.precision)
+            self._engine.precision_request = self.precision
         return self._engine
 
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.float(): packed weights are stale

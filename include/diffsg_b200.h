@@ -149,6 +149,34 @@ static_assert(sizeof(diffsg_op) == 48 && sizeof(diffsg_cfg) == 64 && sizeof(diff
 
 int diffsg_sample(diffsg_plan* plan, const diffsg_sample_args* args, void* stream);
 
+/* ---- tensor-core program (engine DIFFSG_ENGINE_TC) ------------------------------------
+ * Second lowering of the same network for the tcgen05 engine (diffsg_b200/tc_packer.py):
+ * stages = GEMM groups accumulating in TMEM, each followed by an epilogue micro-program.
+ * Records are packed little-endian structs; see diffsg_b200/csrc/unet_tc.cuh. */
+enum { DIFFSG_ENGINE_SIMT = 0, DIFFSG_ENGINE_TC = 1 };
+
+typedef struct diffsg_tc_program {
+    const void* stages;        /* n_stages x 16-byte records                                  */
+    const void* chunks;        /* n_chunks x  8-byte records                                  */
+    const void* epis;          /* n_epi    x 16-byte records                                  */
+    const int32_t* skip_widths;/* n_skip padded widths (multiples of 16)                      */
+    int32_t n_stages, n_chunks, n_epi, n_skip;
+    int32_t nterms;            /* 2: (A_hi + A_lo) . W_fp16;  3: + A_hi . W_lo                */
+    int32_t tt_stride;         /* floats per row of the tensor-core time table                */
+    int32_t reserved[2];
+} diffsg_tc_program;
+
+/* Attach the tensor-core program to a plan (fails with DIFFSG_E_UNSUPPORTED if the topology is
+ * outside the engine's limits; the plan then keeps running on the fp32 engine). */
+int diffsg_plan_attach_tc(diffsg_plan* plan, const diffsg_tc_program* prog);
+/* fp16 weight images (w_lo_dev may be NULL when nterms == 2), fp32 side parameters and the
+ * hoisted time table of the tensor-core program. */
+int diffsg_plan_set_tc_weights(diffsg_plan* plan, const void* w_hi_dev, const void* w_lo_dev,
+                               size_t w_bytes, const float* params_dev, size_t n_params,
+                               const float* time_table_dev, int32_t tt_rows);
+/* Select the engine used by diffsg_unet_forward / diffsg_sample. */
+int diffsg_plan_set_engine(diffsg_plan* plan, int32_t engine);
+
 /* Number of kernel launches issued by this library on the calling thread since the last
  * reset (bench.py's `gpu_launches`). */
 int64_t diffsg_launch_count(int reset);

@@ -1,0 +1,90 @@
+"""Test-only CPU interpreter of the tensor-core stage program (diffsg_b200.tc_packer): same
+dataflow as diffsg_b200/csrc/unet_tc.cuh (TMEM regions, register vector, operand chunk queue),
+evaluated in fp32 (optionally with the fp16 operand rounding of the real engine)."""
+import torch
+
+from diffsg_b200 import tc_packer as T
+
+
+def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_fp16=False):
+    B = x.shape[0]
+    regions = [torch.zeros(B, 128), torch.zeros(B, 128)]
+    skips = {}
+    c = cond * mask
+    cpad = torch.zeros(B, T.pad16(p.cond_dim))
+    cpad[:, :p.cond_dim] = c * torch.sigmoid(c)
+    queue = []                       # emitted A chunks, FIFO
+    v = torch.zeros(B, 128)
+    stats = dict(cnt=0.0, mean=torch.zeros(B), m2=torch.zeros(B), rstd=torch.ones(B))
+    out = None
+    w16 = w_hi.view(torch.float16) if w_hi.dtype != torch.float16 else w_hi
+    w16lo = None if w_lo is None else w_lo
+
+    def split(a):
+        if not emulate_fp16:
+            return a
+        hi = a.half().float()
+        return hi + (a - hi).half().float()
+
+    def emit(vec, dp):
+        for k0 in range(0, dp, 64):
+            queue.append(split(vec[:, k0:min(dp, k0 + 64)].clone()))
+
+    for st in p.stages:
+        if st["has_gemm"]:
+            N = st["n16"] * 16
+            acc = regions[st["region"]][:, :N].clone() if st["accumulate"] else torch.zeros(B, N)
+            for ch in p.chunks[st["chunk_begin"]:st["chunk_begin"] + st["n_chunks"]]:
+                kw = ch["kw"]
+                a = queue.pop(0)
+                assert a.shape[1] == kw, (a.shape, kw)
+                off = ch["w_off16"] * 8
+                img = w16[off:off + N * kw].float()
+                if p.nterms >= 3:
+                    img = img + w16lo[off:off + N * kw].float()
+                W = img.reshape(N // 8, kw // 8, 8, 8).permute(0, 2, 1, 3).reshape(N, kw)
+                acc = acc + a @ W.t()
+            regions[st["region"]][:, :N] = acc
+        for op in p.epis[st["epi_begin"]:st["epi_begin"] + st["n_epi"]]:
+            k, dp, dt = op["kind"], op["dp16"] * 16, op["dt"]
+            if k == T.TE_LOAD_TMEM:
+                v[:, :dp] = regions[op["region"]][:, :dp] + params[op["off0"]:op["off0"] + dp]
+                if op["off1"] >= 0:
+                    v[:, :dp] += table[t_idx][:, op["off1"]:op["off1"] + dp]
+            elif k == T.TE_LOAD_SKIP:
+                v[:, :dp] = skips[op["slot"]][:, :dp]
+            elif k == T.TE_STORE_SKIP:
+                skips[op["slot"]] = v[:, :dp].clone()
+            elif k == T.TE_LOAD_INPUT:
+                v[:, :dp] = 0
+                v[:, :dt] = x
+            elif k == T.TE_STATS:
+                if op["flags"] & T.STATS_RESET:
+                    stats.update(cnt=0.0, mean=torch.zeros(B), m2=torch.zeros(B))
+                m = v[:, :dt].mean(dim=1)
+                q = ((v[:, :dt] - m[:, None]) ** 2).sum(dim=1)
+                tot = stats["cnt"] + dt
+                delta = m - stats["mean"]
+                stats["mean"] = stats["mean"] + delta * (dt / tot)
+                stats["m2"] = stats["m2"] + q + delta * delta * (stats["cnt"] * dt / tot)
+                stats["cnt"] = tot
+                if op["flags"] & T.STATS_FINISH:
+                    stats["rstd"] = 1.0 / torch.sqrt(stats["m2"] / tot + 1e-5)
+            elif k == T.TE_EMIT_LN:
+                g, b = params[op["off0"]:op["off0"] + dp], params[op["off1"]:op["off1"] + dp]
+                t = (v[:, :dp] - stats["mean"][:, None]) * stats["rstd"][:, None] * g + b
+                t = t * torch.sigmoid(t)
+                t[:, dt:] = 0
+                emit(t, dp)
+            elif k == T.TE_EMIT_RAW:
+                t = v[:, :dp].clone()
+                t[:, dt:] = 0
+                emit(t, dp)
+            elif k == T.TE_EMIT_COND:
+                emit(cpad, cpad.shape[1])
+            elif k == T.TE_STORE_OUT:
+                out = v[:, :dt].clone()
+            else:
+                raise ValueError(k)
+    assert not queue, f"{len(queue)} operand chunks were emitted but never consumed"
+    return out

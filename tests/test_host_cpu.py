@@ -216,3 +216,41 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert _lib.load().diffsg_abi_version() == _lib.ABI_VERSION
     assert ctypes.sizeof(_lib.Op) == 48 and ctypes.sizeof(_lib.Cfg) == 64 and ctypes.sizeof(_lib.SampleArgs) == 96
+
+
+@pytest.mark.parametrize("name", ["nu_like", "msr3c", "msr80c", "co"])
+def test_tc_program_matches_oracle(name):
+    """tc_packer: stage/chunk/epilogue lowering, fp16 weight images (x3 -> ~fp32), cumulative biases,
+    cat-free UpBlocks, merged lin3+shortcut GEMM groups — interpreted on the CPU."""
+    from diffsg_b200 import tc_packer
+    from tc_interp import run_tc_program
+    g = load_golden(f"standin_{name}.npz")
+    ddpm, cfg = standin_model(name)
+    prog = tc_packer.lower_tc(ddpm.model, nterms=3)
+    hi, lo, params = tc_packer.pack_tc_weights(prog, "cpu")
+    table = tc_packer.time_table_tc(ddpm.model, prog, torch.arange(T) / T)
+    x, cond, mask = (torch.tensor(g[k]) for k in ("x", "cond", "mask"))
+    ts = torch.tensor(g["ts"]).reshape(-1)
+    eps = run_tc_program(prog, hi, lo, params, table, x, ts, cond, mask)
+    assert rel_l2(eps, g["eps"]) < 5e-6
+    st, ch, ep = prog.arrays()
+    assert st.dtype.itemsize == 16 and ch.dtype.itemsize == 8 and ep.dtype.itemsize == 16
+    assert len(st) <= 160 and len(ch) <= 512 and len(ep) <= 768
+    expect = {"msr3c": (546688, 3768), "msr80c": (566400, 100480), "co": (329024, 11736), "nu_like": (60864, 2736)}
+    assert prog.gemm_macs() == expect[name]
+    # fp16x2 mode: same program, weights rounded to fp16 once
+    prog2 = tc_packer.lower_tc(ddpm.model, nterms=2)
+    hi2, lo2, params2 = tc_packer.pack_tc_weights(prog2, "cpu")
+    assert lo2 is None
+    eps2 = run_tc_program(prog2, hi2, None, params2, table, x, ts, cond, mask, emulate_fp16=True)
+    assert rel_l2(eps2, g["eps"]) < 1e-3
+
+
+def test_tc_engine_rejects_unsupported_topologies():
+    from diffsg_b200 import tc_packer
+    ddpm, _ = standin_model("attn")
+    assert tc_packer.supported(ddpm.model) == "attention blocks"
+    with pytest.raises(ValueError):
+        tc_packer.lower_tc(ddpm.model)
+    wide = D.UNet1D(input_dim=4, proj_dim=256, cond_dim=4, dims=(64, 32), is_attn=(False, False), n_blocks=1)
+    assert tc_packer.supported(wide) is not None
