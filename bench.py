@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=2048, help="rows per step of the CPU reference arm")
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of the in-run cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16x2", "fp16x3"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +178,7 @@ def main():
         torch.cuda.synchronize()
 
     ddpm = build_model(dev)
+    ddpm.model.precision = args.precision
     ddpm.noise_mode = "philox"          # in-kernel noise: no host traffic on the device-resident path
     B, M, Cd = args.rows, NET["input_dim"], NET["cond_dim"]
     ddpm.philox_offset = rank * B        # disjoint noise streams per shard
@@ -184,8 +186,10 @@ def main():
     cond_host = torch.rand(B, Cd, generator=g).pin_memory()     # U(0,1) = min-max scaled gains
     cond = cond_host.to(dev, non_blocking=True)
     out_host = torch.empty(B, M).pin_memory()
-    prog = ddpm.model.engine().program
-    x_macs, c_macs = prog.gemm_macs()
+    engine = ddpm.model.engine()
+    x_macs, c_macs = engine.program.gemm_macs()
+    engine_name = {"fp32": "simt-fp32 (CUDA cores)", "fp16x2": "tcgen05 fp16x2 (A hi+lo, W fp16, fp32 accum)",
+                   "fp16x3": "tcgen05 fp16x3 (A hi+lo, W hi+lo, fp32 accum)"}[engine.precision]
     f_alg = T * 2 * 2 * x_macs + 2 * c_macs                     # 45.51 MFLOP for 80c
 
     def step_resident():
@@ -234,13 +238,13 @@ def main():
         ach_tf = (B * args.steps * f_alg) / (ms * 1e-3) / 1e12     # per GPU (rank 0's kernels)
         line = {"metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32" if engine.precision == "fp32" else "f16", "data": "synthetic",
                 "config": {"workload": "BASELINE configs[1]: MSR 80c CFG-DDPM sampling (assumed UNet1D 80/128/80/(64,32,16,8)/2, "
                                        "init_weights N(0,0.01) seed 0), synthetic rand(B,80) conditions, rows sharded per GPU, no collective",
                            "rows_per_gpu": B, "T": T, "omega": OMEGA, "noise": "in-kernel Philox4x32-10",
                            "batch_stats": "per shard (reference per-call semantics)",
                            "l2": f"inputs+state per step {2 * B * M * 4 / 2**20:.0f} MiB > 126 MB L2; no explicit flush",
-                           "engine": "simt-fp32"},
+                           "engine": engine_name},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e, "unit": "solutions/s", "h2d_bytes_per_step": B * Cd * 4 * world,
                         "d2h_bytes_per_step": B * M * 4 * world, "ms_per_step": ms2 / args.steps},

@@ -24,32 +24,57 @@ def cuda(a):
     return torch.as_tensor(a).to(DEV)
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
-def test_unet_forward_matches_reference(name):
+# engine -> (per-pass eps tolerance, tolerance on a well-conditioned final y)
+PRECISIONS = {"fp32": (2e-5, 5e-4), "fp16x3": (2e-5, 5e-4), "fp16x2": (1e-3, 5e-3)}
+ENGINE_CASES = [(n, p) for n in CONFIGS for p in PRECISIONS if not (n == "attn" and p != "fp32")]
+
+
+def with_precision(ddpm, precision):
+    ddpm.model.precision = precision
+    assert ddpm.model.engine().precision == precision
+    return ddpm
+
+
+@pytest.mark.parametrize("name,precision", ENGINE_CASES)
+def test_unet_forward_matches_reference(name, precision):
     g = load_golden(f"standin_{name}.npz")
     ddpm, cfg = standin_model(name, DEV)
+    with_precision(ddpm, precision)
     with torch.no_grad():
         eps = ddpm.model(cuda(g["x"]), cuda(g["ts"]) / T, cuda(g["cond"]), cuda(g["mask"]))
     assert eps.shape == g["eps"].shape
-    assert rel_l2(eps.cpu(), g["eps"]) < 2e-5
+    assert rel_l2(eps.cpu(), g["eps"]) < PRECISIONS[precision][0]
 
 
-@pytest.mark.parametrize("B", [1, 7, 8, 9, 200])
-def test_unet_forward_ragged_batches(B):
-    """Row-group tails (B not a multiple of 8) and scalar time / mask broadcasting."""
+def test_auto_precision_picks_tensor_cores_when_supported():
+    ddpm, _ = standin_model("msr80c", DEV)
+    assert ddpm.model.engine().precision == "fp16x2" and ddpm.model.engine().tc is not None
+    ddpm, _ = standin_model("attn", DEV)
+    assert ddpm.model.engine().precision == "fp32"
+    ddpm.model.precision = "fp16x3"
+    with pytest.raises(_lib.DiffsgError):
+        ddpm.model.engine()
+
+
+@pytest.mark.parametrize("precision", list(PRECISIONS))
+@pytest.mark.parametrize("B", [1, 7, 8, 9, 127, 129, 200])
+def test_unet_forward_ragged_batches(B, precision):
+    """Row-group / tile tails (B not a multiple of 8 or 128) and per-row time indices + masks."""
     g = load_golden("standin_nu_like.npz")
     ddpm, cfg = standin_model("nu_like", DEV)
+    with_precision(ddpm, precision)
     idx = np.arange(B) % g["x"].shape[0]
     x, cond, ts, mask = g["x"][idx], g["cond"][idx], g["ts"][:, idx], g["mask"][idx]
     with torch.no_grad():
         eps = ddpm.model(cuda(x), cuda(ts) / T, cuda(cond), cuda(mask))
-    assert rel_l2(eps.cpu(), g["eps"][idx]) < 2e-5
+    assert rel_l2(eps.cpu(), g["eps"][idx]) < PRECISIONS[precision][0]
 
 
-def test_nu_checkpoint_teacher_forced_eps():
+@pytest.mark.parametrize("precision", list(PRECISIONS))
+def test_nu_checkpoint_teacher_forced_eps(precision):
     """eps_0 / eps_1 of ddpm_nu_3u.pt at every step, on the reference trajectory."""
     g = load_golden("nu_trace.npz")
-    ddpm = nu_checkpoint_model(DEV)
+    ddpm = with_precision(nu_checkpoint_model(DEV), precision)
     B = g["cond"].shape[0]
     cond = cuda(g["cond"])
     worst = 0.0
@@ -61,23 +86,27 @@ def test_nu_checkpoint_teacher_forced_eps():
             e1 = ddpm.model(y, t, cond, torch.ones(B, 1, device=DEV))
             e0 = ddpm.model(y, t, cond, torch.zeros(B, 1, device=DEV))
             worst = max(worst, rel_l2(e1.cpu(), g["eps_1"][step]), rel_l2(e0.cpu(), g["eps_0"][step]))
-    assert worst < 1e-3, worst          # the gate
-    assert worst < 2e-5, worst          # what the exact-fp32 engine actually delivers
+    assert worst < 1e-3, worst                         # the gate (BASELINE.json north_star)
+    assert worst < PRECISIONS[precision][0], worst     # what this engine is expected to deliver
+    print(f"[{precision}] worst per-pass eps rel-L2 over 20 steps: {worst:.2e}")
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
-def test_sampler_injected_noise_low_guidance(name):
+@pytest.mark.parametrize("name,precision", ENGINE_CASES)
+def test_sampler_injected_noise_low_guidance(name, precision):
     """Full reverse process with the reference's own draws injected; omega = 3 keeps the
     trajectory well conditioned so the final y itself can be compared."""
     g = load_golden(f"standin_{name}.npz")
     ddpm, cfg = standin_model(name, DEV)
+    with_precision(ddpm, precision)
     y0 = ddpm.sample(cuda(g["cond"]), 3.0, y_init=cuda(g["y_T"]), noise=cuda(g["noise"]))
-    assert rel_l2(y0.cpu(), g["y0_omega3"]) < 5e-4
+    assert rel_l2(y0.cpu(), g["y0_omega3"]) < PRECISIONS[precision][1]
 
 
-def test_sampler_records_match_reference():
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_sampler_records_match_reference(precision):
     g = load_golden("standin_nu_like.npz")
     ddpm, cfg = standin_model("nu_like", DEV)
+    with_precision(ddpm, precision)
     B, M = g["cond"].shape[0], cfg["input_dim"]
     rec_y = torch.empty(T, B, M, device=DEV)
     rec_e = torch.empty(T, B, M, device=DEV)
@@ -89,17 +118,19 @@ def test_sampler_records_match_reference():
     assert rel_l2(y.cpu(), g["y0_omega3"]) < 5e-4
 
 
-def test_nu_sampler_omega_sweep_reference_stream():
+@pytest.mark.parametrize("precision", list(PRECISIONS))
+def test_nu_sampler_omega_sweep_reference_stream(precision):
     """ddpm_nu_3u.pt, noise drawn from torch's CPU generator under the same seed
     as the reference run.  Low guidance: compare y0; omega = 500 is chaotic so it is
     judged on the objective below."""
     g = load_golden("nu_trace.npz")
-    ddpm = nu_checkpoint_model(DEV)
+    ddpm = with_precision(nu_checkpoint_model(DEV), precision)
     cond = cuda(g["cond"])
+    loose = 10.0 if precision == "fp16x2" else 1.0
     for om, tol in ((0, 2e-4), (1, 2e-4), (10, 1e-3)):
         torch.manual_seed(123)
         y0 = ddpm.sample(cond, float(om))
-        assert rel_l2(y0.cpu(), g[f"y0_omega{om}"]) < tol, om
+        assert rel_l2(y0.cpu(), g[f"y0_omega{om}"]) < tol * loose, om
 
 
 def _nu_eval(ddpm, X, Y, P_sum, seed):
@@ -109,13 +140,15 @@ def _nu_eval(ddpm, X, Y, P_sum, seed):
     return D.nu.evaluate(ddpm, X, Y, ddpm.custom_config, omega=500, batch_size=512)
 
 
-def test_nu_objective_parity_test_split_and_ood():
+@pytest.mark.parametrize("precision", list(PRECISIONS))
+def test_nu_objective_parity_test_split_and_ood(precision):
     """BASELINE config 3: NU 18 mW test split + 30 mW OOD, omega 500, bs 512, same CPU noise
     stream as the reference run: sum-rate ratio within 0.5 % of the reference's."""
     ref = load_golden("nu_objective.npz")
     d = load_golden("nu_data.npz")
-    ddpm = nu_checkpoint_model(DEV)
+    ddpm = with_precision(nu_checkpoint_model(DEV), precision)
     out = _nu_eval(ddpm, d["X_test"], d["Y_test"], 18.0, 123)
+    print(f"[{precision}] NU less ratio {out['less_ratio']:.5f} (reference {float(ref['less_ratio_test']):.5f})")
     assert abs(out["less_ratio"] / float(ref["less_ratio_test"]) - 1) < 5e-3
     assert rel_l2(out["true_rate"].cpu(), ref["true_rate_test"]) < 1e-5
     assert abs(float(out["pred_rate"].mean()) / float(ref["pred_rate_test"].mean()) - 1) < 5e-3
@@ -125,7 +158,7 @@ def test_nu_objective_parity_test_split_and_ood():
 
 def test_nu_record_denoise_path():
     g = load_golden("nu_record.npz")
-    ddpm = nu_checkpoint_model(DEV)
+    ddpm = with_precision(nu_checkpoint_model(DEV), "fp16x3")
     ddpm.record_denoise_path = True
     torch.manual_seed(7)
     y0 = ddpm.sample(cuda(g["cond"]), 500)
@@ -156,19 +189,21 @@ def test_philox_stream_matches_oracle_and_sampler_uses_it():
     assert rel_l2(y_a.cpu(), y_b.cpu()) < 1e-5
 
 
-def test_sampler_is_independent_of_sharding_in_phase_b():
+@pytest.mark.parametrize("precision", list(PRECISIONS))
+def test_sampler_is_independent_of_sharding_in_phase_b(precision):
     """Rows are independent once the 4 batch-normalised steps are over: sampling two halves
     with the statistics disabled equals sampling the whole (the multi-GPU sharding argument)."""
     ddpm, cfg = standin_model("nu_like", DEV)
-    B, M = 96, cfg["input_dim"]
+    with_precision(ddpm, precision)
+    B, M = 300, cfg["input_dim"]
     g = torch.Generator().manual_seed(0)
     cond = torch.rand(B, cfg["cond_dim"], generator=g).to(DEV)
     y_T = torch.randn(B, M, generator=g).to(DEV)
     noise = torch.randn(T - 2, B, M, generator=g).to(DEV)
     eng, coef = ddpm.model.engine(), ddpm.step_coefficients()
     whole = eng.sample(cond, y_T.clone(), coef, T, 3.0, noise=noise, norm_steps=0)
-    a = eng.sample(cond[:40].contiguous(), y_T[:40].clone(), coef, T, 3.0, noise=noise[:, :40].contiguous(), norm_steps=0)
-    b = eng.sample(cond[40:].contiguous(), y_T[40:].clone(), coef, T, 3.0, noise=noise[:, 40:].contiguous(), norm_steps=0)
+    a = eng.sample(cond[:140].contiguous(), y_T[:140].clone(), coef, T, 3.0, noise=noise[:, :140].contiguous(), norm_steps=0)
+    b = eng.sample(cond[140:].contiguous(), y_T[140:].clone(), coef, T, 3.0, noise=noise[:, 140:].contiguous(), norm_steps=0)
     assert torch.equal(whole, torch.cat((a, b)))
 
 
@@ -218,15 +253,16 @@ def test_objective_kernels_match_reference():
     assert rel_l2(D.objectives.msr_decode_rate(y80.to(DEV), g80.to(DEV), 20.0).cpu(), want) < 1e-6
 
 
-def test_repack_after_parameter_update():
-    ddpm, cfg = standin_model("attn", DEV)
-    g = load_golden("standin_attn.npz")
+@pytest.mark.parametrize("name", ["attn", "nu_like"])
+def test_repack_after_parameter_update(name):
+    ddpm, cfg = standin_model(name, DEV)
+    g = load_golden(f"standin_{name}.npz")
     args = (cuda(g["x"]), cuda(g["ts"]) / T, cuda(g["cond"]), cuda(g["mask"]))
     with torch.no_grad():
         a = ddpm.model(*args)
         ddpm.model.final.bias.add_(1.0)
         b = ddpm.model(*args)
-    assert torch.allclose(b, a + 1.0, atol=1e-5)
+    assert torch.allclose(b, a + 1.0, atol=1e-4)
 
 
 def test_errors_are_loud():
