@@ -192,6 +192,7 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
         if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16) { set_error("attach_tc: chunk %d kw=%d", i, ch[i].kw); return DIFFSG_E_INVALID; }
     for (int i = 0; i < g->n_epi; ++i)
         if (ep[i].kind < TE_LOAD_TMEM || ep[i].kind > TE_EMIT_COND || ep[i].dp16 > 8 || ep[i].region > 1 ||
+            (ep[i].dt != ep[i].dp16 * 16 && ep[i].dp16 != 1 && (ep[i].kind == TE_STATS || ep[i].kind == TE_EMIT_LN)) ||
             ((ep[i].kind == TE_LOAD_SKIP || ep[i].kind == TE_STORE_SKIP) && ep[i].slot >= g->n_skip)) {
             set_error("attach_tc: epilogue op %d malformed", i); return DIFFSG_E_INVALID;
         }
@@ -214,9 +215,10 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     D.stash_off = (int)off; off += (size_t)D.Mp * kRows;
     D.cond_off = (int)off;  off += (size_t)D.Cp * kRows;      // 2 images x Cp x 128 fp16 = Cp*128 floats
     D.scratch_floats = (off + 31) & ~size_t(31);
-    h->grid_max = p->sm_count;                                  // one CTA per SM
     const int w_terms = g->nterms == 3 ? 2 : 1;
     h->smem_bytes = 1024 + ((sizeof(SmemLayout) + 1023) & ~size_t(1023)) + (size_t)kWStages * w_terms * kWStageBytes;
+    // fp16x2 fits two CTAs (tiles) per SM: 2 x (<= 113 KB smem, 256 TMEM columns, 32 K registers)
+    h->grid_max = p->sm_count * ((h->smem_bytes <= 113 * 1024) ? kCtasPerSm : 1);
     if ((int)h->smem_bytes > p->max_smem) { set_error("attach_tc: needs %zu B shared memory", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }
     if (cudaMalloc(&h->d_stages, sizeof(Stage) * g->n_stages) != cudaSuccess ||
         cudaMalloc(&h->d_chunks, sizeof(Chunk) * g->n_chunks) != cudaSuccess ||

@@ -20,12 +20,14 @@ constexpr int kRows = 128;
 constexpr int kChunkK = 64;
 constexpr int kSlotBytes = kRows * kChunkK * 2;      // 16 KB: one fp16 A chunk
 constexpr int kASlots = 2;
-constexpr int kWStages = 3;
+constexpr int kWStages = 2;
 constexpr int kWStageBytes = 128 * kChunkK * 2;      // 16 KB: one fp16 W chunk (N <= 128)
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;                         // epilogue warps 4..7 (one aligned warpgroup)
 constexpr int kTmemCols = 256;                       // two 128-column regions
-constexpr int kMaxStages = 160, kMaxChunks = 512, kMaxEpi = 768;
+constexpr int kMaxStages = 128, kMaxChunks = 256, kMaxEpi = 640;
+constexpr int kCtasPerSm = 2;                        // fp16x2: two co-resident tiles per SM
+constexpr int kRegsProducer = 32, kRegsEpilogue = 224;  // setmaxnreg split of the 128-per-thread launch budget
 
 enum : int { TE_LOAD_TMEM = 1, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT, TE_STATS, TE_EMIT_LN,
              TE_EMIT_RAW, TE_EMIT_COND };
@@ -80,7 +82,13 @@ struct EpiCtx {
     uint32_t aseq;          // A-ring sequence number (chunks produced so far)
 };
 
-__device__ __forceinline__ float swish_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU ex2 + rcp (relative error ~3e-7; exact limits at +-inf)
+__device__ __forceinline__ float swish_f(float x) {
+    const float e = exp2f(-1.4426950408889634f * x);
+    return __fdividef(x, 1.0f + e);
+}
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer)); }
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue)); }
 
 // producer side of one A chunk: wait for the slot, return its base offset for this row
 __device__ __forceinline__ void a_slot_acquire(SmemLayout& S, uint32_t aseq) {
@@ -93,82 +101,133 @@ __device__ __forceinline__ void a_slot_publish(SmemLayout& S, uint32_t aseq) {
     mbar_arrive(&S.a_full[aseq % kASlots]);
 }
 
-// Emit v[0:dp) as K-chunks.  MODE 0: raw, 1: swish(LN(v) * gamma + beta)
-template <int MODE>
-__device__ __forceinline__ void emit_vec(SmemLayout& S, EpiCtx& E, const TcDev& P, int row, int dp16, int dt,
+// Emit v[0:16*DP16) as K-chunks of <= 64.  MODE 0: raw, 1: swish(LN(v) * gamma + beta).
+// FULL: every column is real (dt == 16*DP16) -> no per-element predicates.
+template <int MODE, int DP16, bool FULL>
+__device__ __forceinline__ void emit_vec(SmemLayout& S, EpiCtx& E, const TcDev& P, int row, int dt,
                                          int off_g, int off_b) {
     const float4* g4 = reinterpret_cast<const float4*>(P.params + (MODE ? off_g : 0));
     const float4* b4 = reinterpret_cast<const float4*>(P.params + (MODE ? off_b : 0));
+    const float a_scale = E.rstd, a_shift = -E.mean * E.rstd;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (c * 4 < dp16) {
-            const int ngr = min(4, dp16 - c * 4);
-            const uint32_t sbo = (uint32_t)ngr * 256;                 // kw * 16
-            const uint32_t sl = E.aseq % kASlots;
-            a_slot_acquire(S, E.aseq);
-            uint8_t* hi_base = S.a_hi[sl] + (row >> 3) * sbo + (row & 7) * 16;
-            uint8_t* lo_base = S.a_lo[sl] + (row >> 3) * sbo + (row & 7) * 16;
+    for (int c = 0; c * 4 < DP16; ++c) {
+        constexpr int kDummy = 0; (void)kDummy;
+        const int ngr = (DP16 - c * 4) < 4 ? (DP16 - c * 4) : 4;
+        const uint32_t sbo = (uint32_t)ngr * 256;                 // kw * 16
+        const uint32_t sl = E.aseq % kASlots;
+        a_slot_acquire(S, E.aseq);
+        uint8_t* hi_base = S.a_hi[sl] + (row >> 3) * sbo + (row & 7) * 16;
+        uint8_t* lo_base = S.a_lo[sl] + (row >> 3) * sbo + (row & 7) * 16;
 #pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-                if (gg < ngr) {
+        for (int gg = 0; gg < 4; ++gg) {
+            if (gg < ngr) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int j0 = (c * 4 + gg) * 16 + h * 8;
-                        float x[8];
-                        if (MODE) {
-                            const float4 ga = __ldg(g4 + j0 / 4), gb = __ldg(g4 + j0 / 4 + 1);
-                            const float4 ba = __ldg(b4 + j0 / 4), bb = __ldg(b4 + j0 / 4 + 1);
-                            const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                            const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                for (int h = 0; h < 2; ++h) {
+                    const int j0 = (c * 4 + gg) * 16 + h * 8;
+                    float x[8];
+                    if (MODE) {
+                        const float4 ga = __ldg(g4 + j0 / 4), gb = __ldg(g4 + j0 / 4 + 1);
+                        const float4 ba = __ldg(b4 + j0 / 4), bb = __ldg(b4 + j0 / 4 + 1);
+                        const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                        const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float t = (E.v[j0 + j] - E.mean) * E.rstd * gam[j] + bet[j];
-                                x[j] = (j0 + j < dt) ? swish_f(t) : 0.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = (j0 + j < dt) ? E.v[j0 + j] : 0.f;
+                        for (int j = 0; j < 8; ++j) {
+                            const float t = fmaf(fmaf(E.v[j0 + j], a_scale, a_shift), gam[j], bet[j]);
+                            x[j] = (FULL || j0 + j < dt) ? swish_f(t) : 0.f;
                         }
-                        uint4 hi, lo;
-                        split_pack8(x, hi, lo);
-                        *reinterpret_cast<uint4*>(hi_base + (gg * 2 + h) * 128) = hi;
-                        *reinterpret_cast<uint4*>(lo_base + (gg * 2 + h) * 128) = lo;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = (FULL || j0 + j < dt) ? E.v[j0 + j] : 0.f;
                     }
+                    uint4 hi, lo;
+                    split_pack8(x, hi, lo);
+                    *reinterpret_cast<uint4*>(hi_base + (gg * 2 + h) * 128) = hi;
+                    *reinterpret_cast<uint4*>(lo_base + (gg * 2 + h) * 128) = lo;
                 }
             }
-            a_slot_publish(S, E.aseq);
-            ++E.aseq;
         }
+        a_slot_publish(S, E.aseq);
+        ++E.aseq;
     }
 }
 
 // Per-row LayerNorm statistics of v[0:dt), merged into the running (cnt, mean, m2) (Chan et al.)
-__device__ __forceinline__ void stats_vec(EpiCtx& E, int dp16, int dt, int flags) {
+template <int DP16, bool FULL>
+__device__ __forceinline__ void stats_vec(EpiCtx& E, int dt, int flags) {
     if (flags & kStatsReset) { E.cnt = 0.f; E.mean = 0.f; E.m2 = 0.f; }
-    float s = 0.f;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-        if (g < dp16) {
+    for (int j = 0; j < DP16 * 16; ++j) s4[j & 3] += (FULL || j < dt) ? E.v[j] : 0.f;
+    const float n = FULL ? (float)(DP16 * 16) : (float)dt;
+    const float m = ((s4[0] + s4[1]) + (s4[2] + s4[3])) / n;
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s += (g * 16 + j < dt) ? E.v[g * 16 + j] : 0.f;
-        }
-    const float n = (float)dt, m = s / n;
-    float q = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g)
-        if (g < dp16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float d = (g * 16 + j < dt) ? E.v[g * 16 + j] - m : 0.f;
-                q = fmaf(d, d, q);
-            }
-        }
+    for (int j = 0; j < DP16 * 16; ++j) {
+        const float d = (FULL || j < dt) ? E.v[j] - m : 0.f;
+        q4[j & 3] = fmaf(d, d, q4[j & 3]);
+    }
+    const float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     const float tot = E.cnt + n, delta = m - E.mean;
     E.mean += delta * (n / tot);
     E.m2 += q + delta * delta * (E.cnt * n / tot);
     E.cnt = tot;
-    if (flags & kStatsFinish) E.rstd = 1.0f / sqrtf(E.m2 / E.cnt + kLnEps);
+    if (flags & kStatsFinish) E.rstd = rsqrtf(E.m2 / E.cnt + kLnEps);
 }
+
+template <int DP16>
+__device__ __forceinline__ void load_tmem_vec(EpiCtx& E, const TcDev& P, uint32_t ta, int off0, int off1, int trow) {
+#pragma unroll
+    for (int g = 0; g < DP16; ++g) tmem_ld16(ta + g * 16, *reinterpret_cast<float(*)[16]>(&E.v[g * 16]));
+    const float4* b4 = reinterpret_cast<const float4*>(P.params + off0);
+    const float4* t4 = reinterpret_cast<const float4*>(P.tt + (size_t)trow * P.tt_stride + (off1 >= 0 ? off1 : 0));
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < DP16; ++g) {           // one 16-column group (4 x float4) of bias in flight at a time
+        float4 b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b[q] = __ldg(b4 + g * 4 + q);
+        if (off1 >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldg(t4 + g * 4 + q);
+                b[q].x += t.x; b[q].y += t.y; b[q].z += t.z; b[q].w += t.w;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            E.v[g * 16 + q * 4 + 0] += b[q].x; E.v[g * 16 + q * 4 + 1] += b[q].y;
+            E.v[g * 16 + q * 4 + 2] += b[q].z; E.v[g * 16 + q * 4 + 3] += b[q].w;
+        }
+    }
+}
+template <int DP16>
+__device__ __forceinline__ void load_skip_vec(EpiCtx& E, const float4* sk) {
+#pragma unroll
+    for (int q = 0; q < DP16 * 4; ++q) {
+        const float4 t = sk[q * kRows];
+        E.v[q * 4 + 0] = t.x; E.v[q * 4 + 1] = t.y; E.v[q * 4 + 2] = t.z; E.v[q * 4 + 3] = t.w;
+    }
+}
+template <int DP16>
+__device__ __forceinline__ void store_skip_vec(const EpiCtx& E, float4* sk) {
+#pragma unroll
+    for (int q = 0; q < DP16 * 4; ++q)
+        sk[q * kRows] = make_float4(E.v[q * 4], E.v[q * 4 + 1], E.v[q * 4 + 2], E.v[q * 4 + 3]);
+}
+
+// widths the tensor-core engine accepts: 16, 32, 64, 80, 96, 112, 128 columns (dp16 = 1,2,4,5,6,7,8;
+// 3 is folded into 4 by the packer never emitting it -> treated as invalid at attach time)
+#define DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)     \
+    switch (dp16) {                            \
+        case 1: CALL(1); break;                \
+        case 2: CALL(2); break;                \
+        case 3: CALL(3); break;                \
+        case 4: CALL(4); break;                \
+        case 5: CALL(5); break;                \
+        case 6: CALL(6); break;                \
+        case 7: CALL(7); break;                \
+        default: CALL(8); break;               \
+    }
 
 template <bool kSampler>
 __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, const RunArgs& R, EpiCtx& E,
@@ -190,52 +249,23 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             switch (op.kind) {
                 case TE_LOAD_TMEM: {
                     const uint32_t ta = tmem_row + op.region * 128;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (g < dp16) tmem_ld16(ta + g * 16, *reinterpret_cast<float(*)[16]>(&E.v[g * 16]));
-                    tmem_ld_wait();
-                    const float4* b4 = reinterpret_cast<const float4*>(P.params + op.off0);
-                    const float4* t4 = reinterpret_cast<const float4*>(P.tt + (size_t)trow * P.tt_stride + (op.off1 >= 0 ? op.off1 : 0));
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (g < dp16) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                float4 b = __ldg(b4 + g * 4 + q);
-                                if (op.off1 >= 0) {
-                                    const float4 t = __ldg(t4 + g * 4 + q);
-                                    b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w;
-                                }
-                                E.v[g * 16 + q * 4 + 0] += b.x; E.v[g * 16 + q * 4 + 1] += b.y;
-                                E.v[g * 16 + q * 4 + 2] += b.z; E.v[g * 16 + q * 4 + 3] += b.w;
-                            }
-                        }
+#define CALL(W) load_tmem_vec<W>(E, P, ta, op.off0, op.off1, trow)
+                    DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
                     break;
                 }
                 case TE_LOAD_SKIP: {
                     const float4* sk = reinterpret_cast<const float4*>(scr + P.skip_off[op.slot]) + row;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (g < dp16) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 t = sk[(g * 4 + q) * kRows];
-                                E.v[g * 16 + q * 4 + 0] = t.x; E.v[g * 16 + q * 4 + 1] = t.y;
-                                E.v[g * 16 + q * 4 + 2] = t.z; E.v[g * 16 + q * 4 + 3] = t.w;
-                            }
-                        }
+#define CALL(W) load_skip_vec<W>(E, sk)
+                    DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
                     break;
                 }
                 case TE_STORE_SKIP: {
                     float4* sk = reinterpret_cast<float4*>(scr + P.skip_off[op.slot]) + row;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (g < dp16) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                sk[(g * 4 + q) * kRows] = make_float4(E.v[g * 16 + q * 4], E.v[g * 16 + q * 4 + 1],
-                                                                      E.v[g * 16 + q * 4 + 2], E.v[g * 16 + q * 4 + 3]);
-                        }
+#define CALL(W) store_skip_vec<W>(E, sk)
+                    DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
                     break;
                 }
                 case TE_LOAD_INPUT: {
@@ -250,13 +280,35 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     break;
                 }
                 case TE_STATS:
-                    stats_vec(E, dp16, dt, op.flags);
+                    if (dt == dp16 * 16) {
+#define CALL(W) stats_vec<W, true>(E, dt, op.flags)
+                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
+                    } else {
+                        stats_vec<1, false>(E, dt, op.flags);      // only 16-wide vectors may be partial
+                    }
                     break;
                 case TE_EMIT_LN:
-                    emit_vec<1>(S, E, P, row, dp16, dt, op.off0, op.off1);
+                    if (dt == dp16 * 16) {
+#define CALL(W) emit_vec<1, W, true>(S, E, P, row, dt, op.off0, op.off1)
+                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
+                    } else {
+                        emit_vec<1, 1, false>(S, E, P, row, dt, op.off0, op.off1);
+                    }
                     break;
                 case TE_EMIT_RAW:
-                    emit_vec<0>(S, E, P, row, dp16, dt, 0, 0);
+                    if (dt == dp16 * 16) {
+#define CALL(W) emit_vec<0, W, true>(S, E, P, row, dt, 0, 0)
+                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
+                    } else if (dp16 == 1) {
+                        emit_vec<0, 1, false>(S, E, P, row, dt, 0, 0);
+                    } else {
+#define CALL(W) emit_vec<0, W, false>(S, E, P, row, dt, 0, 0)
+                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+#undef CALL
+                    }
                     break;
                 case TE_EMIT_COND: {
                     if (!use_cond) break;
@@ -347,7 +399,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
 }
 
 template <bool kSampler>
-__global__ void __launch_bounds__(kThreads, 1) tc_unet_kernel(TcDev P, RunArgs R) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, RunArgs R) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(sm);
@@ -374,7 +426,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_unet_kernel(TcDev P, RunArgs R
     const int n_pass = kSampler ? 2 : 1;
     const int step_hi = kSampler ? R.step_hi : 0, step_lo = kSampler ? R.step_lo : 0;
 
-    if (warp == 0) {
+    if (warp < kEpiWarp0) {
+      setmaxnreg_dec();
+      if (warp == 0) {
         // =========================== weight producer
         if (lane == 0) {
             uint32_t wseq = 0;
@@ -444,8 +498,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_unet_kernel(TcDev P, RunArgs R
                         }
                     }
         }
-    } else if (warp >= kEpiWarp0) {
+      }
+    } else {
         // =========================== epilogue / operand producers (thread == row)
+        setmaxnreg_inc();
         const int row = 32 * (warp & 3) + lane;
         EpiCtx E;
         E.aseq = 0; E.mean = 0.f; E.rstd = 1.f; E.m2 = 0.f; E.cnt = 0.f;
