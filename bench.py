@@ -244,7 +244,7 @@ def main():
                            "rows_per_gpu": B, "T": T, "omega": OMEGA, "noise": "in-kernel Philox4x32-10",
                            "batch_stats": "per shard (reference per-call semantics)",
                            "l2": f"inputs+state per step {2 * B * M * 4 / 2**20:.0f} MiB > 126 MB L2; no explicit flush",
-                           "engine": engine_name},
+                           "engine": engine_name, "engine_info": engine.info()},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e, "unit": "solutions/s", "h2d_bytes_per_step": B * Cd * 4 * world,
                         "d2h_bytes_per_step": B * M * 4 * world, "ms_per_step": ms2 / args.steps},

@@ -446,6 +446,13 @@ int diffsg_plan_set_engine(diffsg_plan* p, int32_t engine) {
     return DIFFSG_OK;
 }
 
+int diffsg_plan_query(const diffsg_plan* p, int32_t what) {
+    if (!p) return -1;
+    if (what == 0) return p->engine;
+    if (what == 5) return p->warps;
+    return tc::tc_query(p, what);
+}
+
 int diffsg_philox_normal(float* out, int64_t B, int32_t M, int32_t step, uint64_t seed, uint64_t offset,
                          void* stream) {
     if (!out || B < 0 || M <= 0) { set_error("philox_normal: bad argument"); return DIFFSG_E_INVALID; }

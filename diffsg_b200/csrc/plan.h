@@ -31,5 +31,6 @@ int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float
                float* eps, int64_t B, cudaStream_t st);
 int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st);
 void tc_destroy(diffsg_plan* p);
+int tc_query(const diffsg_plan* p, int what);
 }  // namespace tc
 }  // namespace diffsg

@@ -6,8 +6,12 @@
 //   images and streamed with 1-D bulk TMA, fp32 accumulation in TMEM.
 #include <cstdio>
 
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -147,13 +151,18 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(GemmTestArgs g) {
 namespace diffsg {
 namespace tc {
 
+static std::mutex g_prog_mutex;
+static uint64_t g_resident[64] = {0};
+
 struct TcHost {
     TcDev dev{};
-    Stage* d_stages = nullptr;
-    Chunk* d_chunks = nullptr;
-    Epi* d_epis = nullptr;
+    std::vector<Stage> stages;
+    std::vector<Chunk> chunks;
+    std::vector<Epi> epis;
+    uint64_t serial = 0;
     float* d_scratch = nullptr;
     int grid_max = 0;
+    int occupancy = 0;
     size_t smem_bytes = 0;
     int tt_rows = 0;
     bool have_weights = false;
@@ -162,9 +171,10 @@ struct TcHost {
 void tc_destroy(diffsg_plan* p) {
     if (!p || !p->tc) return;
     TcHost* h = p->tc;
-    if (h->d_stages) cudaFree(h->d_stages);
-    if (h->d_chunks) cudaFree(h->d_chunks);
-    if (h->d_epis) cudaFree(h->d_epis);
+    {
+        std::lock_guard<std::mutex> lock(g_prog_mutex);
+        if (g_resident[p->cfg.device & 63] == h->serial) g_resident[p->cfg.device & 63] = 0;
+    }
     if (h->d_scratch) cudaFree(h->d_scratch);
     delete h;
     p->tc = nullptr;
@@ -186,16 +196,23 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     const Epi* ep = (const Epi*)g->epis;
     for (int i = 0; i < g->n_stages; ++i) {
         if (st[i].chunk_begin + st[i].n_chunks > g->n_chunks || st[i].epi_begin + st[i].n_epi > g->n_epi ||
-            st[i].region > 1 || st[i].n16 < 1 || st[i].n16 > 8) { set_error("attach_tc: stage %d malformed", i); return DIFFSG_E_INVALID; }
+            st[i].n16 < 1 || st[i].n16 > 8 || (st[i].pkg_f4 + st[i].tt_f4) * 4 > kPkgFloats) {
+            set_error("attach_tc: stage %d malformed", i); return DIFFSG_E_INVALID;
+        }
     }
     for (int i = 0; i < g->n_chunks; ++i)
         if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16) { set_error("attach_tc: chunk %d kw=%d", i, ch[i].kw); return DIFFSG_E_INVALID; }
-    for (int i = 0; i < g->n_epi; ++i)
-        if (ep[i].kind < TE_LOAD_TMEM || ep[i].kind > TE_EMIT_COND || ep[i].dp16 > 8 || ep[i].region > 1 ||
-            (ep[i].dt != ep[i].dp16 * 16 && ep[i].dp16 != 1 && (ep[i].kind == TE_STATS || ep[i].kind == TE_EMIT_LN)) ||
-            ((ep[i].kind == TE_LOAD_SKIP || ep[i].kind == TE_STORE_SKIP) && ep[i].slot >= g->n_skip)) {
+    for (int i = 0; i < g->n_epi; ++i) {
+        const Epi& e = ep[i];
+        const bool ln = e.kind == TE_STATS || e.kind == TE_EMIT_LN || e.kind == TE_LN_BLOCK || e.kind == TE_LOAD_SKIP || e.kind == TE_STORE_SKIP;
+        const int npc = e.np / 2;
+        if (e.kind < TE_LOAD || e.kind > TE_LN_BLOCK || e.np > 16 || (e.np & 1) || e.dt > e.np * 8 ||
+            (ln && npc != 1 && npc != 2 && npc != 4 && npc != 8) ||
+            (ln && e.dt != e.np * 8 && e.np != 2) ||
+            ((e.kind == TE_LOAD_SKIP || e.kind == TE_STORE_SKIP || (e.kind == TE_LN_BLOCK && ((e.misc >> 1) & kFPush))) && e.slot >= g->n_skip)) {
             set_error("attach_tc: epilogue op %d malformed", i); return DIFFSG_E_INVALID;
         }
+    }
     tc_destroy(p);
     TcHost* h = new (std::nothrow) TcHost();
     if (!h) { set_error("out of host memory"); return DIFFSG_E_INVALID; }
@@ -216,25 +233,55 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     D.cond_off = (int)off;  off += (size_t)D.Cp * kRows;      // 2 images x Cp x 128 fp16 = Cp*128 floats
     D.scratch_floats = (off + 31) & ~size_t(31);
     const int w_terms = g->nterms == 3 ? 2 : 1;
-    h->smem_bytes = 1024 + ((sizeof(SmemLayout) + 1023) & ~size_t(1023)) + (size_t)kWStages * w_terms * kWStageBytes;
-    // fp16x2 fits two CTAs (tiles) per SM: 2 x (<= 113 KB smem, 256 TMEM columns, 32 K registers)
-    h->grid_max = p->sm_count * ((h->smem_bytes <= 113 * 1024) ? kCtasPerSm : 1);
+    h->smem_bytes = 128 + ((sizeof(SmemLayout) + 127) & ~size_t(127)) + (size_t)kWStages * w_terms * kWStageBytes;
+    // fp16x2 fits two CTAs (tiles) per SM: 2 x (<= 113 KB smem, 256 TMEM columns, 30 K registers)
+    h->grid_max = p->sm_count;
     if ((int)h->smem_bytes > p->max_smem) { set_error("attach_tc: needs %zu B shared memory", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }
-    if (cudaMalloc(&h->d_stages, sizeof(Stage) * g->n_stages) != cudaSuccess ||
-        cudaMalloc(&h->d_chunks, sizeof(Chunk) * g->n_chunks) != cudaSuccess ||
-        cudaMalloc(&h->d_epis, sizeof(Epi) * g->n_epi) != cudaSuccess ||
-        cudaMalloc(&h->d_scratch, sizeof(float) * D.scratch_floats * h->grid_max) != cudaSuccess) {
+    static std::atomic<uint64_t> next_serial{1};
+    h->serial = next_serial.fetch_add(1);
+    h->stages.assign(st, st + g->n_stages);
+    h->chunks.assign(ch, ch + g->n_chunks);
+    h->epis.assign(ep, ep + g->n_epi);
+    if (cudaMalloc(&h->d_scratch, sizeof(float) * D.scratch_floats * p->sm_count * kCtasPerSm) != cudaSuccess) {
         set_error("attach_tc: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         tc_destroy(p);
         return DIFFSG_E_CUDA;
     }
-    DIFFSG_CUDA_OK(cudaMemcpy(h->d_stages, st, sizeof(Stage) * g->n_stages, cudaMemcpyHostToDevice));
-    DIFFSG_CUDA_OK(cudaMemcpy(h->d_chunks, ch, sizeof(Chunk) * g->n_chunks, cudaMemcpyHostToDevice));
-    DIFFSG_CUDA_OK(cudaMemcpy(h->d_epis, ep, sizeof(Epi) * g->n_epi, cudaMemcpyHostToDevice));
-    DIFFSG_CUDA_OK(cudaMemset(h->d_scratch, 0, sizeof(float) * D.scratch_floats * h->grid_max));
-    D.stages = h->d_stages; D.chunks = h->d_chunks; D.epis = h->d_epis; D.scratch = h->d_scratch;
+    DIFFSG_CUDA_OK(cudaMemset(h->d_scratch, 0, sizeof(float) * D.scratch_floats * p->sm_count * kCtasPerSm));
+    D.scratch = h->d_scratch;
     DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int occ = 0;
+    DIFFSG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_unet_kernel<true>, kThreads, h->smem_bytes));
+    h->occupancy = occ;
+    if (getenv("DIFFSG_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, tc_unet_kernel<true>);
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, p->cfg.device);
+        fprintf(stderr, "[diffsg] tc kernel: regs %d, static smem %zu, dyn smem %zu (max %d), maxThreads %d, occ %d | SM: regs %d, smem %zu, "
+                "reserved/block %zu, max blocks %d, max threads %d\n", fa.numRegs, fa.sharedSizeBytes, h->smem_bytes,
+                fa.maxDynamicSharedSizeBytes, fa.maxThreadsPerBlock, occ, prop.regsPerMultiprocessor, prop.sharedMemPerMultiprocessor,
+                prop.reservedSharedMemPerBlock, prop.maxBlocksPerMultiProcessor, prop.maxThreadsPerMultiProcessor);
+        for (int thr = 128; thr <= 512; thr += 64) {
+            int o = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tc_unet_kernel<true>, thr, h->smem_bytes);
+            fprintf(stderr, "[diffsg]   occupancy at %d threads: %d\n", thr, o);
+        }
+        for (size_t sm = 32768; sm <= 131072; sm += 16384) {
+            int o = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tc_unet_kernel<true>, kThreads, sm);
+            fprintf(stderr, "[diffsg]   occupancy at %zu B smem: %d\n", sm, o);
+        }
+    }
+    if (occ < 1) { set_error("attach_tc: kernel does not fit on an SM (smem %zu B)", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }
+    // The occupancy API reports 1 for every kernel that contains tcgen05.alloc (it cannot see how many
+    // TMEM columns are requested); two CTAs x (256 columns, <= 113 KB smem, 30 K registers) do fit.
+    const bool two = 2 * (h->smem_bytes + 1024) <= 233472;
+    h->occupancy = two ? kCtasPerSm : 1;
+    h->grid_max = p->sm_count * h->occupancy;
     return DIFFSG_OK;
 }
 
@@ -251,6 +298,31 @@ int tc_set_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_
     return DIFFSG_OK;
 }
 
+int tc_query(const diffsg_plan* p, int what) {
+    if (!p->tc) return -1;
+    switch (what) {
+        case 1: return p->tc->occupancy;
+        case 2: return (int)p->tc->smem_bytes;
+        case 3: return p->tc->grid_max;
+        case 4: return p->tc->dev.nterms;
+        default: return -1;
+    }
+}
+
+// The stage program is read from __constant__ memory: upload it (stream-ordered) whenever another
+// plan's program is resident on this device.  One tensor-core program is active per device at a time.
+static int tc_activate(diffsg_plan* p, cudaStream_t st) {
+    TcHost* h = p->tc;
+    std::lock_guard<std::mutex> lock(g_prog_mutex);
+    const int dev = p->cfg.device & 63;
+    if (g_resident[dev] == h->serial) return DIFFSG_OK;
+    DIFFSG_CUDA_OK(cudaMemcpyToSymbolAsync(c_stages, h->stages.data(), sizeof(Stage) * h->stages.size(), 0, cudaMemcpyHostToDevice, st));
+    DIFFSG_CUDA_OK(cudaMemcpyToSymbolAsync(c_chunks, h->chunks.data(), sizeof(Chunk) * h->chunks.size(), 0, cudaMemcpyHostToDevice, st));
+    DIFFSG_CUDA_OK(cudaMemcpyToSymbolAsync(c_epis, h->epis.data(), sizeof(Epi) * h->epis.size(), 0, cudaMemcpyHostToDevice, st));
+    g_resident[dev] = h->serial;
+    return DIFFSG_OK;
+}
+
 static int tc_grid(const diffsg_plan* p, int64_t B) {
     const int64_t tiles = (B + kRows - 1) / kRows;
     return (int)(tiles < p->tc->grid_max ? tiles : p->tc->grid_max);
@@ -259,6 +331,7 @@ static int tc_grid(const diffsg_plan* p, int64_t B) {
 int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond, const float* mask,
                float* eps, int64_t B, cudaStream_t st) {
     if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
+    if (int rc = tc_activate(p, st)) return rc;
     RunArgs R;
     memset(&R, 0, sizeof(R));
     R.x = x; R.t_idx = t_idx; R.cond = cond; R.mask = mask; R.eps = eps; R.B = B;
@@ -285,6 +358,7 @@ int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
     const int T = a->T;
     if (T > p->tc->tt_rows) { set_error("tensor-core time table has %d rows, T=%d", p->tc->tt_rows, T); return DIFFSG_E_INVALID; }
     const int norm_steps = a->norm_steps > T ? T : a->norm_steps;
+    if (int rc = tc_activate(p, st)) return rc;
     RunArgs R;
     memset(&R, 0, sizeof(R));
     R.cond = a->cond_dev; R.y = a->y_dev; R.noise = a->noise_dev; R.rec_y = a->rec_y_dev; R.rec_eps = a->rec_eps_dev;

@@ -1,11 +1,17 @@
-// Tensor-core engine: one CTA carries a 128-row tile through the whole UNet1D stage program.
+// Tensor-core engine: one CTA carries a 128-row tile through the whole UNet1D stage program;
+// two CTAs are co-resident per SM (fp16x2) so one tile's MMAs overlap the other's epilogue.
 //
-//   warp 0      bulk-TMA producer: streams fp16 weight K-chunk images into the W ring
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (A, W from shared memory, fp32
-//               accumulators in TMEM), commits completion to mbarriers
-//   warps 4-7   epilogue / operand producers: thread == row == TMEM lane.  Load the accumulator
-//               row into registers, add biases, LayerNorm + Swish in fp32, split into fp16
-//               (hi, lo) and write the next GEMM's A operand as core-matrix K-chunks
+//   warp 0        bulk-TMA producer: streams fp16 weight K-chunk images into the W ring and the
+//                 per-stage fp32 parameter package (bias / LayerNorm gamma, beta / time-bias slice)
+//                 into the package ring
+//   warp 1        MMA issuer: one thread issues tcgen05.mma (A, W from shared memory, fp32
+//                 accumulators in TMEM) and commits completion to mbarriers
+//   warps 4-11    epilogue / operand producers.  TMEM lane == row; the row's vector is split across
+//                 TWO threads (warps 4-7: low half of the columns, warps 8-11: high half), so eight
+//                 warps hide each other's latencies.  They load the accumulator into registers, add
+//                 the bias, LayerNorm (statistics exchanged between the two halves through shared
+//                 memory) + Swish in fp32, split into fp16 (hi, lo) and write the next GEMM's A
+//                 operand as core-matrix K-chunks.
 //
 // Program format: diffsg_b200/tc_packer.py.  Reference semantics: ddpm_opt/UNetCF.py:83-95,
 // :318-356; sampler: ddpm_opt/classifier_free_MSR.py:124-137.
@@ -22,24 +28,37 @@ constexpr int kSlotBytes = kRows * kChunkK * 2;      // 16 KB: one fp16 A chunk
 constexpr int kASlots = 2;
 constexpr int kWStages = 2;
 constexpr int kWStageBytes = 128 * kChunkK * 2;      // 16 KB: one fp16 W chunk (N <= 128)
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;                         // epilogue warps 4..7 (one aligned warpgroup)
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kEpiWarp0 = 4;                         // epilogue warps 4..11 (two aligned warpgroups)
 constexpr int kTmemCols = 256;                       // two 128-column regions
-constexpr int kMaxStages = 128, kMaxChunks = 256, kMaxEpi = 640;
-constexpr int kCtasPerSm = 2;                        // fp16x2: two co-resident tiles per SM
-constexpr int kRegsProducer = 32, kRegsEpilogue = 224;  // setmaxnreg split of the 128-per-thread launch budget
+constexpr int kMaxStages = 256, kMaxChunks = 512, kMaxEpi = 1024;   // program lives in __constant__ memory (16 KB)
+constexpr int kPkgFloats = 640, kPSlots = 2;
+constexpr int kCtasPerSm = 2;
+constexpr int kRegsProducer = 24, kRegsEpilogue = 104;   // setmaxnreg split of the 80-per-thread launch budget
 
-enum : int { TE_LOAD_TMEM = 1, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT, TE_STATS, TE_EMIT_LN,
-             TE_EMIT_RAW, TE_EMIT_COND };
+enum : int { TE_LOAD = 1, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT, TE_STATS, TE_EMIT_LN,
+             TE_EMIT_RAW, TE_EMIT_COND, TE_LN_BLOCK };
 constexpr int kStatsReset = 1, kStatsFinish = 2, kChunkCond = 1;
+constexpr int kFTime = 1, kFCond = 2, kFPush = 4;
 
-struct __align__(16) Epi { uint8_t kind, region, dp16, flags; uint16_t dt, slot; int32_t off0, off1; };
+struct __align__(8) Epi { uint8_t kind, np, dt, misc, slot, off0, off1, off2; };   // misc: region | flags << 1
 struct __align__(8) Chunk { uint16_t kw, flags; uint32_t w_off16; };
-struct __align__(16) Stage { uint16_t chunk_begin, n_chunks, epi_begin, n_epi; uint8_t n16, region, accumulate, has_gemm; uint32_t pad; };
-static_assert(sizeof(Epi) == 16 && sizeof(Chunk) == 8 && sizeof(Stage) == 16, "program record layout");
+struct __align__(16) Stage {
+    uint16_t chunk_begin, epi_begin;
+    uint8_t n_chunks, n_epi, n16, bits;          // bits: region | accumulate << 1 | has_gemm << 2 | has_time << 3
+    uint32_t pkg_off4;
+    uint16_t tt_src4;
+    uint8_t pkg_f4, tt_f4;
+};
+static_assert(sizeof(Epi) == 8 && sizeof(Chunk) == 8 && sizeof(Stage) == 16, "program record layout");
+
+// The active stage program (uploaded by the host before a launch whenever the plan changes).
+__constant__ Stage c_stages[kMaxStages];
+__constant__ Chunk c_chunks[kMaxChunks];
+__constant__ Epi c_epis[kMaxEpi];
 
 struct TcDev {
-    const Stage* stages; const Chunk* chunks; const Epi* epis;
     int n_stages, n_chunks, n_epi;
     const uint8_t* w_hi; const uint8_t* w_lo;     // fp16 weight images (lo: nterms == 3 only)
     const float* params; const float* tt;
@@ -54,20 +73,19 @@ struct TcDev {
 struct SmemLayout {
     uint8_t a_hi[kASlots][kSlotBytes];
     uint8_t a_lo[kASlots][kSlotBytes];
-    uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], acc_full;
+    float pkg[kPSlots][kPkgFloats];
+    float2 xchg[2][kEpiThreads];
+    uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], p_full[kPSlots],
+        p_empty[kPSlots], acc_full;
     uint32_t tmem_base, pad_;
-    Stage stages[kMaxStages];
-    Chunk chunks[kMaxChunks];
-    Epi epis[kMaxEpi];
     // followed by the W ring: kWStages * (nterms == 3 ? 2 : 1) * kWStageBytes (dynamic)
 };
+static_assert(((sizeof(SmemLayout) + 127) & ~size_t(127)) + kWStages * kWStageBytes + 128 <= 114688, "two CTAs per SM: measured limit 112 KB each");
 
 // What one launch does: kSampler -> steps step_hi..step_lo, two passes each; else one forward.
 struct RunArgs {
-    // forward
-    const float* x; const int32_t* t_idx; const float* cond; const float* mask; float* eps;
-    // sampler
-    float* y; const float* noise; float* rec_y; float* rec_eps; double* stats;
+    const float* x; const int32_t* t_idx; const float* cond; const float* mask; float* eps;      // forward
+    float* y; const float* noise; float* rec_y; float* rec_eps; double* stats;                  // sampler
     int64_t B;
     int T, step_hi, step_lo, norm_steps;
     float omega;
@@ -76,149 +94,180 @@ struct RunArgs {
 };
 
 // ------------------------------------------------------------------------------------------
-struct EpiCtx {
-    float v[128];
-    float mean, rstd, m2, cnt;
-    uint32_t aseq;          // A-ring sequence number (chunks produced so far)
-};
-
-// x * sigmoid(x) with MUFU ex2 + rcp (relative error ~3e-7; exact limits at +-inf)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (relative error ~3e-7; correct limits at +-inf)
 __device__ __forceinline__ float swish_f(float x) {
-    const float e = exp2f(-1.4426950408889634f * x);
-    return __fdividef(x, 1.0f + e);
+    return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer)); }
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue)); }
-
-// producer side of one A chunk: wait for the slot, return its base offset for this row
-__device__ __forceinline__ void a_slot_acquire(SmemLayout& S, uint32_t aseq) {
-    const uint32_t sl = aseq % kASlots, ph = (aseq / kASlots) & 1;
-    mbar_wait(&S.a_empty[sl], ph ^ 1);
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
-__device__ __forceinline__ void a_slot_publish(SmemLayout& S, uint32_t aseq) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Per-thread epilogue state.  A vector of `np` 8-column pieces is split between the two threads of
+// a row: half 0 owns pieces [0, np/2), half 1 owns [np/2, np); each thread keeps its pieces in v[].
+struct EpiCtx {
+    float v[64];
+    float mean, rstd, m2, cnt, cnt_all;
+    uint32_t aseq;          // A-ring sequence number (chunks published so far by the whole tile)
+    uint32_t xpar;          // parity of the statistics exchange buffer
+    int half, row, et;
+};
+
+// ---- A-operand ring (producer side) --------------------------------------------------------
+// Write this thread's NPC pieces of an np-piece vector into the chunk slots aseq, aseq+1 and publish.
+// `piece(i, hi, lo)` yields the packed fp16 (hi, lo) of local piece i.
+template <int NPC, typename F>
+__device__ __forceinline__ void emit_pieces(SmemLayout& S, EpiCtx& E, int np, F piece) {
+    const int pbeg = E.half * NPC;
+    const int nch = (np + 7) >> 3;
+    // chunks touched by this thread: first = pbeg >> 3, last = (pbeg + NPC - 1) >> 3  (at most two)
+    const int c_first = pbeg >> 3, c_last = (pbeg + NPC - 1) >> 3;
+    for (int c = c_first; c <= c_last; ++c) {
+        const uint32_t sq = E.aseq + c;
+        mbar_wait(&S.a_empty[sq % kASlots], ((sq / kASlots) & 1) ^ 1);
+    }
+#pragma unroll
+    for (int i = 0; i < NPC; ++i) {
+        const int p = pbeg + i, c = p >> 3, kc = p & 7;
+        const int cnt = min(8, np - 8 * c);                     // pieces in chunk c
+        const uint32_t sl = (E.aseq + c) % kASlots;
+        const uint32_t off = (uint32_t)(E.row >> 3) * (cnt * 128) + kc * 128 + (E.row & 7) * 16;
+        uint4 hi, lo;
+        piece(i, hi, lo);
+        *reinterpret_cast<uint4*>(S.a_hi[sl] + off) = hi;
+        *reinterpret_cast<uint4*>(S.a_lo[sl] + off) = lo;
+    }
     fence_proxy_async_smem();
     tcgen05_fence_before();
-    mbar_arrive(&S.a_full[aseq % kASlots]);
+    const int n0 = np >> 1;
+    for (int c = c_first; c <= c_last; ++c) {
+        // both halves contribute to chunk c iff it straddles the split point n0
+        const bool both = (8 * c < n0) && (min(8 * c + 8, np) > n0);
+        mbar_arrive_n(&S.a_full[(E.aseq + c) % kASlots], both ? 1u : 2u);
+    }
+    E.aseq += nch;
 }
 
-// Emit v[0:16*DP16) as K-chunks of <= 64.  MODE 0: raw, 1: swish(LN(v) * gamma + beta).
-// FULL: every column is real (dt == 16*DP16) -> no per-element predicates.
-template <int MODE, int DP16, bool FULL>
-__device__ __forceinline__ void emit_vec(SmemLayout& S, EpiCtx& E, const TcDev& P, int row, int dt,
-                                         int off_g, int off_b) {
-    const float4* g4 = reinterpret_cast<const float4*>(P.params + (MODE ? off_g : 0));
-    const float4* b4 = reinterpret_cast<const float4*>(P.params + (MODE ? off_b : 0));
+template <int MODE, int NPC, bool FULL>   // MODE 0: raw, 1: swish(LN(v) * gamma + beta)
+__device__ __forceinline__ void emit_vec(SmemLayout& S, EpiCtx& E, int np, int nv, const float* pk_g, const float* pk_b) {
     const float a_scale = E.rstd, a_shift = -E.mean * E.rstd;
+    const int cb = E.half * NPC * 8;
+    emit_pieces<NPC>(S, E, np, [&](int i, uint4& hi, uint4& lo) {
+        float x[8];
+        if (MODE) {
+            const float4 ga = *reinterpret_cast<const float4*>(pk_g + cb + i * 8), gb = *reinterpret_cast<const float4*>(pk_g + cb + i * 8 + 4);
+            const float4 ba = *reinterpret_cast<const float4*>(pk_b + cb + i * 8), bb = *reinterpret_cast<const float4*>(pk_b + cb + i * 8 + 4);
+            const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-    for (int c = 0; c * 4 < DP16; ++c) {
-        constexpr int kDummy = 0; (void)kDummy;
-        const int ngr = (DP16 - c * 4) < 4 ? (DP16 - c * 4) : 4;
-        const uint32_t sbo = (uint32_t)ngr * 256;                 // kw * 16
-        const uint32_t sl = E.aseq % kASlots;
-        a_slot_acquire(S, E.aseq);
-        uint8_t* hi_base = S.a_hi[sl] + (row >> 3) * sbo + (row & 7) * 16;
-        uint8_t* lo_base = S.a_lo[sl] + (row >> 3) * sbo + (row & 7) * 16;
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-            if (gg < ngr) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j0 = (c * 4 + gg) * 16 + h * 8;
-                    float x[8];
-                    if (MODE) {
-                        const float4 ga = __ldg(g4 + j0 / 4), gb = __ldg(g4 + j0 / 4 + 1);
-                        const float4 ba = __ldg(b4 + j0 / 4), bb = __ldg(b4 + j0 / 4 + 1);
-                        const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                        const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float t = fmaf(fmaf(E.v[j0 + j], a_scale, a_shift), gam[j], bet[j]);
-                            x[j] = (FULL || j0 + j < dt) ? swish_f(t) : 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) x[j] = (FULL || j0 + j < dt) ? E.v[j0 + j] : 0.f;
-                    }
-                    uint4 hi, lo;
-                    split_pack8(x, hi, lo);
-                    *reinterpret_cast<uint4*>(hi_base + (gg * 2 + h) * 128) = hi;
-                    *reinterpret_cast<uint4*>(lo_base + (gg * 2 + h) * 128) = lo;
-                }
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(fmaf(E.v[i * 8 + j], a_scale, a_shift), gam[j], bet[j]);
+                x[j] = (FULL || i * 8 + j < nv) ? swish_f(t) : 0.f;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (FULL || i * 8 + j < nv) ? E.v[i * 8 + j] : 0.f;
         }
-        a_slot_publish(S, E.aseq);
-        ++E.aseq;
+        split_pack8(x, hi, lo);
+    });
+}
+
+// LayerNorm statistics of this thread's valid columns merged into the running (cnt, mean, m2);
+// on `finish` the two halves of the row exchange their partial results (Chan et al. merge).
+template <int NPC, bool FULL>
+__device__ __forceinline__ void stats_vec(SmemLayout& S, EpiCtx& E, int nv, int dt, int flags) {
+    if (flags & kStatsReset) { E.cnt = 0.f; E.mean = 0.f; E.m2 = 0.f; E.cnt_all = 0.f; }
+    constexpr int W = NPC * 8;
+    if (FULL || nv > 0) {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < W; ++j) s4[j & 3] += (FULL || j < nv) ? E.v[j] : 0.f;
+        const float n = FULL ? (float)W : (float)nv;
+        const float m = ((s4[0] + s4[1]) + (s4[2] + s4[3])) / n;
+        float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const float d = (FULL || j < nv) ? E.v[j] - m : 0.f;
+            q4[j & 3] = fmaf(d, d, q4[j & 3]);
+        }
+        const float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        const float tot = E.cnt + n, delta = m - E.mean;
+        E.mean += delta * (n / tot);
+        E.m2 += q + delta * delta * (E.cnt * n / tot);
+        E.cnt = tot;
+    }
+    E.cnt_all += (float)dt;
+    if (flags & kStatsFinish) {
+        S.xchg[E.xpar][E.et] = make_float2(E.mean, E.m2);
+        epi_bar_sync();
+        const float2 o = S.xchg[E.xpar][E.et ^ 128];
+        E.xpar ^= 1;
+        const float on = E.cnt_all - E.cnt;                    // the partner's column count
+        if (on > 0.f) {
+            const float delta = o.x - E.mean;
+            E.mean += delta * (on / E.cnt_all);
+            E.m2 += o.y + delta * delta * (E.cnt * on / E.cnt_all);
+        }
+        E.rstd = rsqrtf(E.m2 / E.cnt_all + kLnEps);
     }
 }
 
-// Per-row LayerNorm statistics of v[0:dt), merged into the running (cnt, mean, m2) (Chan et al.)
-template <int DP16, bool FULL>
-__device__ __forceinline__ void stats_vec(EpiCtx& E, int dt, int flags) {
-    if (flags & kStatsReset) { E.cnt = 0.f; E.mean = 0.f; E.m2 = 0.f; }
-    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+// v = accumulator row slice + bias (bias from the shared-memory package, or gathered per row from
+// the time table in forward mode)
+template <int NPC>
+__device__ __forceinline__ void load_vec(EpiCtx& E, uint32_t taddr, const float* bias) {
+    if constexpr (NPC % 2 == 0) {
 #pragma unroll
-    for (int j = 0; j < DP16 * 16; ++j) s4[j & 3] += (FULL || j < dt) ? E.v[j] : 0.f;
-    const float n = FULL ? (float)(DP16 * 16) : (float)dt;
-    const float m = ((s4[0] + s4[1]) + (s4[2] + s4[3])) / n;
-    float q4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < NPC / 2; ++i) tmem_ld16(taddr + i * 16, *reinterpret_cast<float(*)[16]>(&E.v[i * 16]));
+    } else {
 #pragma unroll
-    for (int j = 0; j < DP16 * 16; ++j) {
-        const float d = (FULL || j < dt) ? E.v[j] - m : 0.f;
-        q4[j & 3] = fmaf(d, d, q4[j & 3]);
+        for (int i = 0; i < NPC; ++i) tmem_ld8(taddr + i * 8, &E.v[i * 8]);
     }
-    const float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-    const float tot = E.cnt + n, delta = m - E.mean;
-    E.mean += delta * (n / tot);
-    E.m2 += q + delta * delta * (E.cnt * n / tot);
-    E.cnt = tot;
-    if (flags & kStatsFinish) E.rstd = rsqrtf(E.m2 / E.cnt + kLnEps);
-}
-
-template <int DP16>
-__device__ __forceinline__ void load_tmem_vec(EpiCtx& E, const TcDev& P, uint32_t ta, int off0, int off1, int trow) {
-#pragma unroll
-    for (int g = 0; g < DP16; ++g) tmem_ld16(ta + g * 16, *reinterpret_cast<float(*)[16]>(&E.v[g * 16]));
-    const float4* b4 = reinterpret_cast<const float4*>(P.params + off0);
-    const float4* t4 = reinterpret_cast<const float4*>(P.tt + (size_t)trow * P.tt_stride + (off1 >= 0 ? off1 : 0));
     tmem_ld_wait();
 #pragma unroll
-    for (int g = 0; g < DP16; ++g) {           // one 16-column group (4 x float4) of bias in flight at a time
-        float4 b[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = __ldg(b4 + g * 4 + q);
-        if (off1 >= 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 t = __ldg(t4 + g * 4 + q);
-                b[q].x += t.x; b[q].y += t.y; b[q].z += t.z; b[q].w += t.w;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            E.v[g * 16 + q * 4 + 0] += b[q].x; E.v[g * 16 + q * 4 + 1] += b[q].y;
-            E.v[g * 16 + q * 4 + 2] += b[q].z; E.v[g * 16 + q * 4 + 3] += b[q].w;
-        }
+    for (int q = 0; q < NPC * 2; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
+        E.v[q * 4 + 0] += b.x; E.v[q * 4 + 1] += b.y; E.v[q * 4 + 2] += b.z; E.v[q * 4 + 3] += b.w;
     }
 }
-template <int DP16>
+template <int NPC>
 __device__ __forceinline__ void load_skip_vec(EpiCtx& E, const float4* sk) {
 #pragma unroll
-    for (int q = 0; q < DP16 * 4; ++q) {
+    for (int q = 0; q < NPC * 2; ++q) {
         const float4 t = sk[q * kRows];
         E.v[q * 4 + 0] = t.x; E.v[q * 4 + 1] = t.y; E.v[q * 4 + 2] = t.z; E.v[q * 4 + 3] = t.w;
     }
 }
-template <int DP16>
+template <int NPC>
 __device__ __forceinline__ void store_skip_vec(const EpiCtx& E, float4* sk) {
 #pragma unroll
-    for (int q = 0; q < DP16 * 4; ++q)
+    for (int q = 0; q < NPC * 2; ++q)
         sk[q * kRows] = make_float4(E.v[q * 4], E.v[q * 4 + 1], E.v[q * 4 + 2], E.v[q * 4 + 3]);
 }
 
-// widths the tensor-core engine accepts: 16, 32, 64, 80, 96, 112, 128 columns (dp16 = 1,2,4,5,6,7,8;
-// 3 is folded into 4 by the packer never emitting it -> treated as invalid at attach time)
-#define DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)     \
-    switch (dp16) {                            \
+#define DIFFSG_TC_NPC_SWITCH(npc, CALL)        \
+    switch (npc) {                             \
         case 1: CALL(1); break;                \
         case 2: CALL(2); break;                \
         case 3: CALL(3); break;                \
@@ -228,131 +277,159 @@ __device__ __forceinline__ void store_skip_vec(const EpiCtx& E, float4* sk) {
         case 7: CALL(7); break;                \
         default: CALL(8); break;               \
     }
+// LayerNorm'd vectors are internal widths: powers of two (8 columns are padded to 16)
+#define DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)   \
+    switch (npc) {                             \
+        case 1: CALL(1); break;                \
+        case 2: CALL(2); break;                \
+        case 4: CALL(4); break;                \
+        default: CALL(8); break;               \
+    }
+
+__device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P, const float* scr) {
+    const uint4* img = reinterpret_cast<const uint4*>(scr + P.cond_off);
+    const int nkc = P.Cp / 8;                      // 16-byte K pieces per row; piece k belongs to half k & 1
+    for (int c0 = 0; c0 < nkc; c0 += 8) {
+        const int nk = min(8, nkc - c0);
+        const uint32_t sq = E.aseq;
+        const uint32_t sl = sq % kASlots;
+        mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
+        const uint32_t base = (uint32_t)(E.row >> 3) * (nk * 128) + (E.row & 7) * 16;
+        for (int k = E.half; k < nk; k += 2) {
+            *reinterpret_cast<uint4*>(S.a_hi[sl] + base + k * 128) = img[(size_t)(c0 + k) * kRows + E.row];
+            *reinterpret_cast<uint4*>(S.a_lo[sl] + base + k * 128) = img[(size_t)(nkc + c0 + k) * kRows + E.row];
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_n(&S.a_full[sl], 1u);
+        ++E.aseq;
+    }
+}
 
 template <bool kSampler>
 __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, const RunArgs& R, EpiCtx& E,
-                                             float* scr, int row, int64_t grow, bool valid, int trow,
-                                             bool use_cond, int pass, int step, uint32_t& acc_phase,
+                                             float* scr, int64_t grow, bool valid, int trow, bool use_cond,
+                                             int pass, int step, uint32_t& acc_phase, uint32_t& pseq,
                                              double& st_s, double& st_q) {
-    const uint32_t lane_base = (uint32_t)(row & ~31);
-    const uint32_t tmem_row = S.tmem_base + (lane_base << 16);
+    const int row = E.row;
+    const uint32_t tmem_row = S.tmem_base + ((uint32_t)(row & ~31) << 16);
     for (int si = 0; si < P.n_stages; ++si) {
-        const Stage sg = S.stages[si];
-        if (sg.has_gemm) {
+        const Stage sg = c_stages[si];
+        if (sg.bits & 4) {
             mbar_wait(&S.acc_full, acc_phase);
             acc_phase ^= 1;
             tcgen05_fence_after();
         }
+        const bool has_pkg = (sg.pkg_f4 | sg.tt_f4) != 0;
+        const uint32_t psl = pseq % kPSlots;
+        if (has_pkg) mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1);
+        const float* pk = S.pkg[psl];
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
-            const Epi op = S.epis[ei];
-            const int dp16 = op.dp16, dt = op.dt;
+            const Epi op = c_epis[ei];
+            const int np = op.np, npc = np >> 1, dt = op.dt;
+            const int cb = E.half * npc * 8;                              // first column owned by this thread
+            const int nv = max(0, min(dt - cb, npc * 8));                 // valid (un-padded) columns owned
+            const bool full = nv == npc * 8;
+            const int region = op.misc & 1, flags = op.misc >> 1;
             switch (op.kind) {
-                case TE_LOAD_TMEM: {
-                    const uint32_t ta = tmem_row + op.region * 128;
-#define CALL(W) load_tmem_vec<W>(E, P, ta, op.off0, op.off1, trow)
-                    DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+                case TE_LOAD:
+                case TE_LN_BLOCK: {
+                    const uint32_t ta = tmem_row + region * 128 + cb;
+                    const float* bias = pk + op.off0 * 4 + cb;
+                    if (!kSampler && (flags & kFTime)) bias = P.tt + (size_t)trow * P.tt_stride + sg.tt_src4 * 4 + cb;
+#define CALL(W) load_vec<W>(E, ta, bias)
+                    DIFFSG_TC_NPC_SWITCH(npc, CALL)
 #undef CALL
+                    if (op.kind == TE_LOAD) break;
+                    if (flags & kFPush) {
+                        float4* sk = reinterpret_cast<float4*>(scr + P.skip_off[op.slot]) + (size_t)(cb / 4) * kRows + row;
+#define CALL(W) store_skip_vec<W>(E, sk)
+                        DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
+#undef CALL
+                    }
+                    const float* pg = pk + op.off1 * 4;
+                    const float* pb = pk + op.off2 * 4;
+                    if (full) {
+#define CALL(W) { stats_vec<W, true>(S, E, nv, dt, kStatsReset | kStatsFinish); emit_vec<1, W, true>(S, E, np, nv, pg, pb); }
+                        DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
+#undef CALL
+                    } else {
+                        stats_vec<1, false>(S, E, nv, dt, kStatsReset | kStatsFinish);
+                        emit_vec<1, 1, false>(S, E, np, nv, pg, pb);
+                    }
+                    if ((flags & kFCond) && use_cond) emit_cond(S, E, P, scr);
                     break;
                 }
                 case TE_LOAD_SKIP: {
-                    const float4* sk = reinterpret_cast<const float4*>(scr + P.skip_off[op.slot]) + row;
+                    const float4* sk = reinterpret_cast<const float4*>(scr + P.skip_off[op.slot]) + (size_t)(cb / 4) * kRows + row;
 #define CALL(W) load_skip_vec<W>(E, sk)
-                    DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+                    DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     break;
                 }
                 case TE_STORE_SKIP: {
-                    float4* sk = reinterpret_cast<float4*>(scr + P.skip_off[op.slot]) + row;
+                    float4* sk = reinterpret_cast<float4*>(scr + P.skip_off[op.slot]) + (size_t)(cb / 4) * kRows + row;
 #define CALL(W) store_skip_vec<W>(E, sk)
-                    DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+                    DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     break;
                 }
                 case TE_LOAD_INPUT: {
-                    const float* src = (kSampler ? R.y : R.x) + grow * P.M;
+                    const float* src = (kSampler ? R.y : R.x) + grow * P.M + cb;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (g < dp16) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                E.v[g * 16 + j] = (valid && g * 16 + j < dt) ? src[g * 16 + j] : 0.f;
-                        }
+                    for (int j = 0; j < 64; ++j)
+                        if (j < npc * 8) E.v[j] = (valid && j < nv) ? src[j] : 0.f;
                     break;
                 }
                 case TE_STATS:
-                    if (dt == dp16 * 16) {
-#define CALL(W) stats_vec<W, true>(E, dt, op.flags)
-                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+                    if (full) {
+#define CALL(W) stats_vec<W, true>(S, E, nv, dt, flags)
+                        DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     } else {
-                        stats_vec<1, false>(E, dt, op.flags);      // only 16-wide vectors may be partial
+                        stats_vec<1, false>(S, E, nv, dt, flags);
                     }
                     break;
-                case TE_EMIT_LN:
-                    if (dt == dp16 * 16) {
-#define CALL(W) emit_vec<1, W, true>(S, E, P, row, dt, op.off0, op.off1)
-                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
+                case TE_EMIT_LN: {
+                    const float* pg = pk + op.off0 * 4;
+                    const float* pb = pk + op.off1 * 4;
+                    if (full) {
+#define CALL(W) emit_vec<1, W, true>(S, E, np, nv, pg, pb)
+                        DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     } else {
-                        emit_vec<1, 1, false>(S, E, P, row, dt, op.off0, op.off1);
-                    }
-                    break;
-                case TE_EMIT_RAW:
-                    if (dt == dp16 * 16) {
-#define CALL(W) emit_vec<0, W, true>(S, E, P, row, dt, 0, 0)
-                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
-#undef CALL
-                    } else if (dp16 == 1) {
-                        emit_vec<0, 1, false>(S, E, P, row, dt, 0, 0);
-                    } else {
-#define CALL(W) emit_vec<0, W, false>(S, E, P, row, dt, 0, 0)
-                        DIFFSG_TC_WIDTH_SWITCH(dp16, CALL)
-#undef CALL
-                    }
-                    break;
-                case TE_EMIT_COND: {
-                    if (!use_cond) break;
-                    const uint4* img = reinterpret_cast<const uint4*>(scr + P.cond_off);
-                    const int nkc = P.Cp / 8;                      // 16-byte K pieces per row
-                    for (int c0 = 0; c0 < nkc; c0 += 8) {
-                        const int nk = min(8, nkc - c0);
-                        const uint32_t sbo = (uint32_t)nk * 128;
-                        const uint32_t sl = E.aseq % kASlots;
-                        a_slot_acquire(S, E.aseq);
-                        uint8_t* hi_base = S.a_hi[sl] + (row >> 3) * sbo + (row & 7) * 16;
-                        uint8_t* lo_base = S.a_lo[sl] + (row >> 3) * sbo + (row & 7) * 16;
-                        for (int k = 0; k < nk; ++k) {
-                            *reinterpret_cast<uint4*>(hi_base + k * 128) = img[(size_t)(c0 + k) * kRows + row];
-                            *reinterpret_cast<uint4*>(lo_base + k * 128) = img[(size_t)(nkc + c0 + k) * kRows + row];
-                        }
-                        a_slot_publish(S, E.aseq);
-                        ++E.aseq;
+                        emit_vec<1, 1, false>(S, E, np, nv, pg, pb);
                     }
                     break;
                 }
+                case TE_EMIT_RAW:
+                    if (full) {
+#define CALL(W) emit_vec<0, W, true>(S, E, np, nv, nullptr, nullptr)
+                        DIFFSG_TC_NPC_SWITCH(npc, CALL)
+#undef CALL
+                    } else {
+#define CALL(W) emit_vec<0, W, false>(S, E, np, nv, nullptr, nullptr)
+                        DIFFSG_TC_NPC_SWITCH(npc, CALL)
+#undef CALL
+                    }
+                    break;
+                case TE_EMIT_COND:
+                    if (use_cond) emit_cond(S, E, P, scr);
+                    break;
                 case TE_STORE_OUT: {
                     if (!kSampler) {
                         if (valid) {
 #pragma unroll
-                            for (int g = 0; g < 8; ++g)
-                                if (g < dp16) {
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j)
-                                        if (g * 16 + j < dt) R.eps[grow * P.M + g * 16 + j] = E.v[g * 16 + j];
-                                }
+                            for (int j = 0; j < 64; ++j)
+                                if (j < nv) R.eps[grow * P.M + cb + j] = E.v[j];
                         }
                         break;
                     }
-                    float4* stash = reinterpret_cast<float4*>(scr + P.stash_off) + row;
+                    float4* stash = reinterpret_cast<float4*>(scr + P.stash_off) + (size_t)(cb / 4) * kRows + row;
                     if (pass == 0) {           // unconditional pass: park eps_0
 #pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            if (g < dp16) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    stash[(g * 4 + q) * kRows] = make_float4(E.v[g * 16 + q * 4], E.v[g * 16 + q * 4 + 1],
-                                                                             E.v[g * 16 + q * 4 + 2], E.v[g * 16 + q * 4 + 3]);
-                            }
+                        for (int q = 0; q < 16; ++q)
+                            if (q < npc * 2)
+                                stash[q * kRows] = make_float4(E.v[q * 4], E.v[q * 4 + 1], E.v[q * 4 + 2], E.v[q * 4 + 3]);
                         break;
                     }
                     // conditional pass: guidance mix + posterior update (classifier_free_MSR.py:132-134)
@@ -363,29 +440,26 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const int64_t plane = R.B * (int64_t)P.M;
                     const int64_t pidx = (int64_t)(R.T - 1 - step) * plane;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (g < dp16) {
+                    for (int q = 0; q < 16; ++q)
+                        if (q < npc * 2 && q * 4 < nv) {
+                            const float4 e0 = stash[q * kRows];
+                            const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
+                            float z[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (valid && add_noise && R.noise == nullptr)
+                                philox_normal4((uint64_t)grow + R.offset, (uint32_t)step, (uint32_t)(cb / 4 + q), R.seed, z);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 e0 = stash[(g * 4 + q) * kRows];
-                                const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
-                                float z[4] = {0.f, 0.f, 0.f, 0.f};
-                                if (valid && add_noise && R.noise == nullptr && (g * 16 + q * 4) < dt)
-                                    philox_normal4((uint64_t)grow + R.offset, (uint32_t)step, (uint32_t)(g * 4 + q), R.seed, z);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int c = g * 16 + q * 4 + j;
-                                    if (valid && c < dt) {
-                                        const int64_t idx = grow * P.M + c;
-                                        if (add_noise && R.noise != nullptr) z[j] = R.noise[pidx + idx];
-                                        const float e = w1 * E.v[c] - w0 * e0a[j];
-                                        float yn = (R.y[idx] - ce * e) * crs;
-                                        if (add_noise) yn += cn * z[j];
-                                        R.y[idx] = yn;
-                                        if (R.rec_eps) R.rec_eps[pidx + idx] = e;
-                                        if (R.rec_y && !want_stats) R.rec_y[pidx + idx] = yn;
-                                        if (want_stats) { st_s += (double)yn; st_q += (double)yn * (double)yn; }
-                                    }
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = q * 4 + j;
+                                if (valid && c < nv) {
+                                    const int64_t idx = grow * P.M + cb + c;
+                                    if (add_noise && R.noise != nullptr) z[j] = R.noise[pidx + idx];
+                                    const float e = w1 * E.v[c] - w0 * e0a[j];
+                                    float yn = (R.y[idx] - ce * e) * crs;
+                                    if (add_noise) yn += cn * z[j];
+                                    R.y[idx] = yn;
+                                    if (R.rec_eps) R.rec_eps[pidx + idx] = e;
+                                    if (R.rec_y && !want_stats) R.rec_y[pidx + idx] = yn;
+                                    if (want_stats) { st_s += (double)yn; st_q += (double)yn * (double)yn; }
                                 }
                             }
                         }
@@ -395,25 +469,27 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     break;
             }
         }
+        if (has_pkg) {
+            mbar_arrive(&S.p_empty[psl]);
+            ++pseq;
+        }
     }
 }
 
 template <bool kSampler>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, RunArgs R) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(sm);
     const int w_terms = P.nterms == 3 ? 2 : 1;
-    uint8_t* w_ring = sm + ((sizeof(SmemLayout) + 1023) & ~size_t(1023));   // [kWStages][w_terms][kWStageBytes]
+    uint8_t* w_ring = sm + ((sizeof(SmemLayout) + 127) & ~size_t(127));   // [kWStages][w_terms][kWStageBytes]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup
-    for (int i = threadIdx.x; i < P.n_stages; i += kThreads) S.stages[i] = P.stages[i];
-    for (int i = threadIdx.x; i < P.n_chunks; i += kThreads) S.chunks[i] = P.chunks[i];
-    for (int i = threadIdx.x; i < P.n_epi; i += kThreads) S.epis[i] = P.epis[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kASlots; ++i) { mbar_init(&S.a_full[i], 128); mbar_init(&S.a_empty[i], 1); }
+        for (int i = 0; i < kASlots; ++i) { mbar_init(&S.a_full[i], kEpiThreads); mbar_init(&S.a_empty[i], 1); }
         for (int i = 0; i < kWStages; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < kPSlots; ++i) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], kEpiThreads); }
         mbar_init(&S.acc_full, 1);
         fence_barrier_init();
     }
@@ -429,18 +505,30 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
     if (warp < kEpiWarp0) {
       setmaxnreg_dec();
       if (warp == 0) {
-        // =========================== weight producer
+        // =========================== TMA producer: parameter packages + weight chunks
         if (lane == 0) {
-            uint32_t wseq = 0;
+            uint32_t wseq = 0, pseq = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int step = step_hi; step >= step_lo; --step)
                     for (int pass = 0; pass < n_pass; ++pass) {
                         const bool use_cond = kSampler ? (pass == 1) : true;
                         for (int si = 0; si < P.n_stages; ++si) {
-                            const Stage sg = S.stages[si];
-                            if (!sg.has_gemm) continue;
+                            const Stage sg = c_stages[si];
+                            if (sg.pkg_f4 | sg.tt_f4) {
+                                const uint32_t sl = pseq % kPSlots;
+                                const bool tma_time = kSampler && sg.tt_f4;
+                                const uint32_t tt_bytes = (uint32_t)sg.tt_f4 * 16u, st_bytes = (uint32_t)sg.pkg_f4 * 16u;
+                                mbar_wait(&S.p_empty[sl], ((pseq / kPSlots) & 1) ^ 1);
+                                mbar_arrive_expect_tx(&S.p_full[sl], st_bytes + (tma_time ? tt_bytes : 0u));
+                                if (tma_time)
+                                    tma_load_1d(S.pkg[sl], P.tt + (size_t)step * P.tt_stride + (size_t)sg.tt_src4 * 4, tt_bytes, &S.p_full[sl]);
+                                if (st_bytes)
+                                    tma_load_1d(S.pkg[sl] + sg.tt_f4 * 4, P.params + (size_t)sg.pkg_off4 * 4, st_bytes, &S.p_full[sl]);
+                                ++pseq;
+                            }
+                            if (!(sg.bits & 4)) continue;
                             for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
-                                const Chunk ch = S.chunks[ci];
+                                const Chunk ch = c_chunks[ci];
                                 if ((ch.flags & kChunkCond) && !use_cond) continue;
                                 const uint32_t st = wseq % kWStages, ph = (wseq / kWStages) & 1;
                                 const uint32_t bytes = (uint32_t)sg.n16 * 16u * ch.kw * 2u;
@@ -455,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                         }
                     }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // =========================== MMA issuer
         if (lane == 0) {
             uint32_t wseq = 0, aseq = 0;
@@ -464,13 +552,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                     for (int pass = 0; pass < n_pass; ++pass) {
                         const bool use_cond = kSampler ? (pass == 1) : true;
                         for (int si = 0; si < P.n_stages; ++si) {
-                            const Stage sg = S.stages[si];
-                            if (!sg.has_gemm) continue;
+                            const Stage sg = c_stages[si];
+                            if (!(sg.bits & 4)) continue;
                             const uint32_t idesc = make_idesc_f16(128, (uint32_t)sg.n16 * 16u);
-                            const uint32_t d_tmem = S.tmem_base + sg.region * 128;
-                            uint32_t acc = sg.accumulate;
+                            const uint32_t d_tmem = S.tmem_base + (sg.bits & 1) * 128;
+                            uint32_t acc = (sg.bits >> 1) & 1;
                             for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
-                                const Chunk ch = S.chunks[ci];
+                                const Chunk ch = c_chunks[ci];
                                 if ((ch.flags & kChunkCond) && !use_cond) continue;
                                 const uint32_t st = wseq % kWStages, wph = (wseq / kWStages) & 1;
                                 const uint32_t sl = aseq % kASlots, aph = (aseq / kASlots) & 1;
@@ -500,25 +588,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         }
       }
     } else {
-        // =========================== epilogue / operand producers (thread == row)
+        // =========================== epilogue / operand producers (two threads per row)
         setmaxnreg_inc();
-        const int row = 32 * (warp & 3) + lane;
         EpiCtx E;
-        E.aseq = 0; E.mean = 0.f; E.rstd = 1.f; E.m2 = 0.f; E.cnt = 0.f;
+        E.et = threadIdx.x - kEpiWarp0 * 32;
+        E.half = E.et >> 7;
+        E.row = E.et & 127;
+        E.aseq = 0; E.xpar = 0; E.mean = 0.f; E.rstd = 1.f; E.m2 = 0.f; E.cnt = 0.f; E.cnt_all = 0.f;
 #pragma unroll
-        for (int j = 0; j < 128; ++j) E.v[j] = 0.f;
-        uint32_t acc_phase = 0;
+        for (int j = 0; j < 64; ++j) E.v[j] = 0.f;
+        uint32_t acc_phase = 0, pseq = 0;
         double st_s = 0.0, st_q = 0.0;
         float* scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t grow = tile * kRows + row;
+            const int64_t grow = tile * kRows + E.row;
             const bool valid = grow < R.B;
-            // cond image: swish(cond * mask) as fp16 (hi, lo), K pieces of 8, thread-private scratch
+            // cond image: swish(cond * mask) as fp16 (hi, lo) 16-byte K pieces; piece k is built (and
+            // later copied into the operand ring) by the thread of half k & 1 -> thread-private scratch
             {
                 uint4* img = reinterpret_cast<uint4*>(scr + P.cond_off);
                 const int nkc = P.Cp / 8;
                 const float mk = (!kSampler && R.mask && valid) ? R.mask[grow] : 1.0f;
-                for (int kc = 0; kc < nkc; ++kc) {
+                for (int kc = E.half; kc < nkc; kc += 2) {
                     float x[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -527,16 +618,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                     }
                     uint4 hi, lo;
                     split_pack8(x, hi, lo);
-                    img[(size_t)kc * kRows + row] = hi;
-                    img[(size_t)(nkc + kc) * kRows + row] = lo;
+                    img[(size_t)kc * kRows + E.row] = hi;
+                    img[(size_t)(nkc + kc) * kRows + E.row] = lo;
                 }
             }
             const int trow_fwd = (!kSampler && valid) ? R.t_idx[grow] : 0;
             for (int step = step_hi; step >= step_lo; --step)
                 for (int pass = 0; pass < n_pass; ++pass) {
                     const bool use_cond = kSampler ? (pass == 1) : true;
-                    run_epilogue<kSampler>(S, P, R, E, scr, row, grow, valid, kSampler ? step : trow_fwd, use_cond,
-                                           pass, step, acc_phase, st_s, st_q);
+                    run_epilogue<kSampler>(S, P, R, E, scr, grow, valid, kSampler ? step : trow_fwd, use_cond, pass,
+                                           step, acc_phase, pseq, st_s, st_q);
                 }
         }
         if (kSampler && R.step_hi > R.T - 1 - R.norm_steps) {

@@ -88,6 +88,11 @@ class UNetEngine:
         self._bound_table = None
         self._stat_ws = None
 
+    def info(self) -> dict:
+        q = lambda w: int(self.lib.diffsg_plan_query(self.handle, w))
+        return dict(precision=self.precision, engine="tcgen05" if q(0) == _lib.ENGINE_TC else "simt-fp32",
+                    tc_ctas_per_sm=q(1), tc_smem_bytes=q(2), tc_grid_max=q(3), simt_warps_per_cta=q(5))
+
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:

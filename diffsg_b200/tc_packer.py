@@ -1,12 +1,11 @@
 """Lower a `UNet1D` to the tensor-core engine's stage program (include/diffsg_b200.h,
 "tensor-core program").
 
-One CTA carries a 128-row tile; thread == row == TMEM lane.  The network becomes a list of
-STAGES.  A stage is one GEMM group (every MMA accumulates into one 128-column TMEM region)
-followed by an EPILOGUE: a short list of micro-ops over one per-thread register vector
-v[<=128] that loads the accumulator (+ bias / hoisted time bias), optionally spills it to the
-skip stack, computes LayerNorm statistics, and EMITS the next stage's A operand as fp16
-(hi, lo) K-chunks into the shared-memory operand ring.
+One CTA carries a 128-row tile; TMEM lane == row.  The network becomes a list of STAGES.  A
+stage is one GEMM group (every MMA accumulates into one 128-column TMEM region) followed by an
+EPILOGUE: a short list of micro-ops over a per-row register vector that loads the accumulator
+(+ bias), optionally spills it to the skip stack, computes LayerNorm statistics, and EMITS the
+next stage's A operand as fp16 (hi, lo) K-chunks into the shared-memory operand ring.
 
 Layout decisions made here:
   * activations x live in TMEM as x = acc[region] + xb, with xb a host-precomputed cumulative
@@ -16,6 +15,9 @@ Layout decisions made here:
   * an UpBlock's `lin3(a3) + shortcut(cat(x, skip))` is ONE GEMM group of K = D + 2D;
   * weights are fp16 core-matrix images ([n/8][k/8][n%8][8], one image per <=64-wide K-chunk)
     streamed by 1-D bulk TMA; with nterms == 3 a second image holds the fp16 residual of W;
+  * every fp32 side parameter a stage's epilogue needs (bias, LayerNorm gamma/beta) is packed
+    into ONE contiguous per-stage package that the TMA warp streams into shared memory ahead
+    of the epilogue; the hoisted time bias (+ lin1.bias) comes from the per-step table row;
   * widths are padded to multiples of 16 (UMMA K / N granularity); pad rows/cols are zero.
 Reference semantics: ddpm_opt/UNetCF.py:83-95, :318-356.
 """
@@ -27,22 +29,27 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .unet import AttentionBlock, DownBlock, Downsample, ResidualBlock, UNet1D, UpBlock, Upsample
+from .unet import DownBlock, ResidualBlock, UNet1D, UpBlock
 
 CHUNK_K = 64
 MAX_W = 128
+PKG_MAX_FLOATS = 640
 
-# epilogue micro-op kinds (mirror include/diffsg_b200.h)
-TE_LOAD_TMEM, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT = 1, 2, 3, 4, 5
-TE_STATS, TE_EMIT_LN, TE_EMIT_RAW, TE_EMIT_COND = 6, 7, 8, 9
+# epilogue micro-op kinds (mirror diffsg_b200/csrc/unet_tc.cuh)
+TE_LOAD, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT = 1, 2, 3, 4, 5
+TE_STATS, TE_EMIT_LN, TE_EMIT_RAW, TE_EMIT_COND, TE_LN_BLOCK = 6, 7, 8, 9, 10
 STATS_RESET, STATS_FINISH = 1, 2
+F_TIME, F_COND, F_PUSH = 1, 2, 4          # LOAD: bias is the time-table slice; LN_BLOCK: also emit cond / push skip
+NONE8 = 255
 
-EPI_DT = np.dtype([("kind", "u1"), ("region", "u1"), ("dp16", "u1"), ("flags", "u1"), ("dt", "u2"), ("slot", "u2"),
-                   ("off0", "i4"), ("off1", "i4")])
+EPI_DT = np.dtype([("kind", "u1"), ("np", "u1"), ("dt", "u1"), ("misc", "u1"), ("slot", "u1"), ("off0", "u1"),
+                   ("off1", "u1"), ("off2", "u1")])
 CHUNK_DT = np.dtype([("kw", "u2"), ("flags", "u2"), ("w_off16", "u4")])          # w_off16: offset / 16 bytes
-STAGE_DT = np.dtype([("chunk_begin", "u2"), ("n_chunks", "u2"), ("epi_begin", "u2"), ("n_epi", "u2"),
-                     ("n16", "u1"), ("region", "u1"), ("accumulate", "u1"), ("has_gemm", "u1"), ("pad", "u4")])
+STAGE_DT = np.dtype([("chunk_begin", "u2"), ("epi_begin", "u2"), ("n_chunks", "u1"), ("n_epi", "u1"),
+                     ("n16", "u1"), ("bits", "u1"), ("pkg_off4", "u4"), ("tt_src4", "u2"), ("pkg_f4", "u1"),
+                     ("tt_f4", "u1")])
 CHUNK_COND = 1
+assert EPI_DT.itemsize == 8 and CHUNK_DT.itemsize == 8 and STAGE_DT.itemsize == 16
 
 
 def pad16(n: int) -> int:
@@ -52,8 +59,8 @@ def pad16(n: int) -> int:
 def supported(model: UNet1D) -> str | None:
     """None if the tensor-core engine can run this topology, else the reason it cannot."""
     widths = [model.proj_dim, *model.dims]
-    if any(w > MAX_W for w in widths):
-        return f"width > {MAX_W}"
+    if any(w > MAX_W or w < 8 or (w & (w - 1)) for w in widths):
+        return f"internal widths must be powers of two in [8, {MAX_W}]"
     if model.input_dim > MAX_W or model.cond_dim > MAX_W:
         return f"input_dim / cond_dim > {MAX_W}"
     if any(model.is_attn) or model.middle_attn:
@@ -66,27 +73,36 @@ class TcProgram:
     stages: list = field(default_factory=list)
     chunks: list = field(default_factory=list)
     epis: list = field(default_factory=list)
-    wpieces: list = field(default_factory=list)     # (byte offset, n_pad, kw, fn -> [n, kw] fp32 weight slice)
+    wpieces: list = field(default_factory=list)     # (byte offset, n, npad, k, kw, fn -> [n, k] fp32 weight slice)
     ppieces: list = field(default_factory=list)     # (float offset, n, fn -> flat fp32)
     w_bytes: int = 0
     n_params: int = 0
     skip_widths: list = field(default_factory=list)  # padded widths
-    time_blocks: list = field(default_factory=list)
+    time_blocks: list = field(default_factory=list)  # (t_off, time_emb Linear, lin1 Linear)
     tt_stride: int = 0
     input_dim: int = 0
     cond_dim: int = 0
     nterms: int = 2
     _open: dict | None = None
 
-    # ---- blobs
+    # ---- per-stage parameter package
     def vec(self, fn, n: int, npad: int) -> int:
-        off = self.n_params
-        self.ppieces.append((off, n, fn))
-        self.n_params += (npad + 3) & ~3
-        return off
+        """Append a vector to the open stage's package; returns its float4 offset inside the package."""
+        st = self._open
+        off = st["pkg_floats"]                      # offset inside the static (blob-resident) part
+        self.ppieces.append((st["pkg_off"] + off, n, fn))
+        st["pkg_floats"] += (npad + 3) & ~3
+        assert st["tt_floats"] + st["pkg_floats"] <= PKG_MAX_FLOATS, st
+        return (st["tt_floats"] + off) // 4         # shared-memory package = [time slice | static part]
+
+    def time_slot(self, t_off: int, npad: int) -> int:
+        """Reserve package space that the TMA fills from time_table[step][t_off : t_off + npad]."""
+        st = self._open
+        assert st["tt_src"] is None and st["pkg_floats"] == 0, "the time slice must be the first package entry"
+        st["tt_src"], st["tt_floats"] = t_off, npad
+        return 0
 
     def weight_chunk(self, fn, n: int, npad: int, k: int, kw: int) -> int:
-        """fn() -> [n, k] fp32 (rows = output features, cols = this chunk's K slice)."""
         off = self.w_bytes
         self.wpieces.append((off, n, npad, k, kw, fn))
         self.w_bytes += npad * kw * 2
@@ -96,7 +112,8 @@ class TcProgram:
     def begin_stage(self, n_out: int, region: int, accumulate: bool, has_gemm: bool = True):
         assert self._open is None
         self._open = dict(chunk_begin=len(self.chunks), n16=pad16(n_out) // 16, region=region,
-                          accumulate=int(accumulate), has_gemm=int(has_gemm), epi_begin=None)
+                          accumulate=int(accumulate), has_gemm=int(has_gemm), epi_begin=len(self.epis),
+                          pkg_off=self.n_params, pkg_floats=0, tt_src=None, tt_floats=0)
 
     def add_k_segment(self, weight_fn, n_out: int, k: int, cond: bool = False):
         """Append the K-chunks of one operand segment of width k (weight_fn() -> [n_out, k])."""
@@ -107,33 +124,56 @@ class TcProgram:
             off = self.weight_chunk(lambda k0=k0, kreal=kreal: weight_fn()[:, k0:k0 + kreal], n_out, npad, kreal, kw)
             self.chunks.append(dict(kw=kw, flags=CHUNK_COND if cond else 0, w_off16=off // 16))
 
-    def epi(self, kind, region=0, dp=16, flags=0, dt=0, slot=0, off0=-1, off1=-1):
-        st = self._open
-        if st["epi_begin"] is None:
-            st["epi_begin"] = len(self.epis)
-        self.epis.append(dict(kind=kind, region=region, dp16=dp // 16, flags=flags, dt=dt, slot=slot, off0=off0, off1=off1))
+    def epi(self, kind, width=16, dt=0, region=0, flags=0, slot=0, off0=NONE8, off1=NONE8, off2=NONE8):
+        self.epis.append(dict(kind=kind, np=pad16(width) // 8, dt=dt, region=region, flags=flags, slot=slot,
+                              off0=off0, off1=off1, off2=off2))
 
     def end_stage(self):
         st = self._open
         st["n_chunks"] = len(self.chunks) - st["chunk_begin"]
-        if st["epi_begin"] is None:
-            st["epi_begin"] = len(self.epis)
         st["n_epi"] = len(self.epis) - st["epi_begin"]
+        # shared-memory package = [time slice (from the per-step table row) | static part (blob)]
+        self.n_params += st["pkg_floats"]
+        self._fuse(st)
         self.stages.append(st)
         self._open = None
+
+    def _fuse(self, st):
+        """Peephole: LOAD [+ STORE_SKIP] + STATS(reset|finish) + EMIT_LN [+ EMIT_COND] -> LN_BLOCK."""
+        ops = self.epis[st["epi_begin"]:]
+        if not ops or ops[0]["kind"] != TE_LOAD:
+            return
+        i, push = 1, None
+        if i < len(ops) and ops[i]["kind"] == TE_STORE_SKIP:
+            push, i = ops[i], i + 1
+        if not (i + 1 < len(ops) and ops[i]["kind"] == TE_STATS and ops[i]["flags"] == (STATS_RESET | STATS_FINISH)
+                and ops[i + 1]["kind"] == TE_EMIT_LN):
+            return
+        ln = ops[i + 1]
+        i += 2
+        cond = i < len(ops) and ops[i]["kind"] == TE_EMIT_COND
+        if cond:
+            i += 1
+        ld = ops[0]
+        fused = dict(kind=TE_LN_BLOCK, np=ld["np"], dt=ld["dt"], region=ld["region"],
+                     flags=(ld["flags"] & F_TIME) | (F_COND if cond else 0) | (F_PUSH if push else 0),
+                     slot=push["slot"] if push else 0, off0=ld["off0"], off1=ln["off0"], off2=ln["off1"])
+        self.epis[st["epi_begin"]:] = [fused] + ops[i:]
+        st["n_epi"] = len(self.epis) - st["epi_begin"]
 
     # ---- arrays for the C-ABI
     def arrays(self):
         s = np.zeros(len(self.stages), STAGE_DT)
         for i, d in enumerate(self.stages):
-            for k in ("chunk_begin", "n_chunks", "epi_begin", "n_epi", "n16", "region", "accumulate", "has_gemm"):
-                s[i][k] = d[k]
+            s[i] = (d["chunk_begin"], d["epi_begin"], d["n_chunks"], d["n_epi"], d["n16"],
+                    d["region"] | (d["accumulate"] << 1) | (d["has_gemm"] << 2) | ((d["tt_src"] is not None) << 3),
+                    d["pkg_off"] // 4, (d["tt_src"] or 0) // 4, d["pkg_floats"] // 4, d["tt_floats"] // 4)
         c = np.zeros(len(self.chunks), CHUNK_DT)
         for i, d in enumerate(self.chunks):
             c[i] = (d["kw"], d["flags"], d["w_off16"])
         e = np.zeros(len(self.epis), EPI_DT)
         for i, d in enumerate(self.epis):
-            e[i] = (d["kind"], d["region"], d["dp16"], d["flags"], d["dt"], d["slot"], d["off0"], d["off1"])
+            e[i] = (d["kind"], d["np"], d["dt"], d["region"] | (d["flags"] << 1), d["slot"], d["off0"], d["off1"], d["off2"])
         return s, c, e
 
     def gemm_macs(self):
@@ -147,37 +187,31 @@ class TcProgram:
         return x, c
 
 
-def _emit_next(p: TcProgram, plan, xr, xb_off, width):
+def _emit_next(p: TcProgram, plan, xr, xb_off4, width):
     """Epilogue tail shared by every stage that ends with a finished activation x (in region xr,
-    bias xb): what it must EMIT depends on the module that consumes x next (`plan`)."""
+    cumulative bias at package offset xb_off4): what it must EMIT depends on the module that consumes x next."""
     dp = pad16(width)
     kind = plan[0]
-    if kind == "res":            # identity-shortcut ResidualBlock: LN1 -> Swish
-        blk = plan[1]
-        p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=width)
-        g = p.vec(lambda: blk.norm1.weight, width, dp)
-        b = p.vec(lambda: blk.norm1.bias, width, dp)
-        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g, off1=b)
-    elif kind == "raw":          # Down/Upsample Linear consumes x itself
-        p.epi(TE_EMIT_RAW, dp=dp, dt=width)
-    elif kind == "up":           # UpBlock: LN1 over cat(x, skip); chunks: skip part, then x part
+    if kind in ("res", "final"):   # identity-shortcut ResidualBlock / output head: LN -> Swish
+        norm = plan[1].norm1 if kind == "res" else plan[1]
+        p.epi(TE_STATS, width=dp, dt=width, flags=STATS_RESET | STATS_FINISH)
+        g = p.vec(lambda: norm.weight, width, dp)
+        b = p.vec(lambda: norm.bias, width, dp)
+        p.epi(TE_EMIT_LN, width=dp, dt=width, off0=g, off1=b)
+    elif kind == "raw":            # Down/Upsample Linear consumes x itself
+        p.epi(TE_EMIT_RAW, width=dp, dt=width)
+    elif kind == "up":             # UpBlock: LN1 over cat(x, skip); chunks: skip part, then x part
         blk, slot = plan[1], plan[2]
         g_x = p.vec(lambda: blk.norm1.weight[:width], width, dp)
         b_x = p.vec(lambda: blk.norm1.bias[:width], width, dp)
         g_s = p.vec(lambda: blk.norm1.weight[width:], width, dp)
         b_s = p.vec(lambda: blk.norm1.bias[width:], width, dp)
-        p.epi(TE_STATS, flags=STATS_RESET, dp=dp, dt=width)
-        p.epi(TE_LOAD_SKIP, dp=dp, dt=width, slot=slot)
-        p.epi(TE_STATS, flags=STATS_FINISH, dp=dp, dt=width)
-        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g_s, off1=b_s)
-        p.epi(TE_LOAD_TMEM, region=xr, dp=dp, dt=width, off0=xb_off)
-        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g_x, off1=b_x)
-    elif kind == "final":
-        norm = plan[1]
-        p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=width)
-        g = p.vec(lambda: norm.weight, width, dp)
-        b = p.vec(lambda: norm.bias, width, dp)
-        p.epi(TE_EMIT_LN, dp=dp, dt=width, off0=g, off1=b)
+        p.epi(TE_STATS, width=dp, dt=width, flags=STATS_RESET)
+        p.epi(TE_LOAD_SKIP, width=dp, dt=width, slot=slot)
+        p.epi(TE_STATS, width=dp, dt=width, flags=STATS_FINISH)
+        p.epi(TE_EMIT_LN, width=dp, dt=width, off0=g_s, off1=b_s)
+        p.epi(TE_LOAD, width=dp, dt=width, region=xr, off0=xb_off4)
+        p.epi(TE_EMIT_LN, width=dp, dt=width, off0=g_x, off1=b_x)
     else:
         raise ValueError(kind)
 
@@ -214,10 +248,14 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             return ("up", mod, pop_slot[i])
         return ("final", model.norm)
 
+    def sum_fn(fns):
+        fns = tuple(fns)
+        return lambda: sum(f() for f in fns)
+
     # ---- stage 0: operand of feature_proj = the raw input row
     p.begin_stage(16, 0, False, has_gemm=False)
-    p.epi(TE_LOAD_INPUT, dp=pad16(M), dt=M)
-    p.epi(TE_EMIT_RAW, dp=pad16(M), dt=M)
+    p.epi(TE_LOAD_INPUT, width=pad16(M), dt=M)
+    p.epi(TE_EMIT_RAW, width=pad16(M), dt=M)
     p.end_stage()
 
     # ---- feature_proj
@@ -226,24 +264,16 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
     xr = 0
     p.begin_stage(width, xr, False)
     p.add_k_segment(lambda: fp.weight, width, M)
-    xb = [lambda: fp.bias]                 # list of bias terms summed into the cumulative vector
-    xb_off = p.vec(lambda xb=tuple(xb): sum(f() for f in xb), width, pad16(width))
-    p.epi(TE_LOAD_TMEM, region=xr, dp=pad16(width), dt=width, off0=xb_off)
+    xb = [lambda: fp.bias]                 # bias terms summed into the cumulative vector of x
+    xoff = p.vec(sum_fn(xb), width, pad16(width))
+    p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
     slot = 0
     p.skip_widths.append(pad16(width))
-    p.epi(TE_STORE_SKIP, dp=pad16(width), dt=width, slot=slot)
-    _emit_next(p, consumer_plan(0), xr, xb_off, width)
+    p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
+    _emit_next(p, consumer_plan(0), xr, xoff, width)
     p.end_stage()
     slot += 1
     n_down = len(model.down)
-
-    def res_inner(blk: ResidualBlock, din, dout, hr):
-        """G1 and G2 of a ResidualBlock (operands of G1 already emitted); leaves A3 emitted."""
-        t_off = p.tt_stride
-        p.time_blocks.append((t_off, blk.time_emb))
-        p.tt_stride += pad16(dout)
-        dp = pad16(dout)
-        return t_off, dp
 
     for i, (kind, mod) in enumerate(seq):
         nxt = consumer_plan(i + 1) if i + 1 < len(seq) else None
@@ -255,13 +285,13 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             width = lin.out_features
             xr = hr
             xb = [lambda lin=lin: lin.bias]
-            xb_off = p.vec(lambda xb=tuple(xb): sum(f() for f in xb), width, pad16(width))
-            p.epi(TE_LOAD_TMEM, region=xr, dp=pad16(width), dt=width, off0=xb_off)
+            xoff = p.vec(sum_fn(xb), width, pad16(width))
+            p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
             if i < n_down:
                 p.skip_widths.append(pad16(width))
-                p.epi(TE_STORE_SKIP, dp=pad16(width), dt=width, slot=slot)
+                p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
                 slot += 1
-            _emit_next(p, nxt, xr, xb_off, width)
+            _emit_next(p, nxt, xr, xoff, width)
             p.end_stage()
         elif kind in ("down_res", "mid_res", "up_res"):
             blk: ResidualBlock = mod
@@ -270,21 +300,20 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             hr = 1 - xr
             is_up = kind == "up_res"
             t_off = p.tt_stride
-            p.time_blocks.append((t_off, blk.time_emb))
+            p.time_blocks.append((t_off, blk.time_emb, blk.lin1))
             p.tt_stride += dp
-            # ---- G1: h = lin1(a1) + b1 + time
+            # ---- G1: h = lin1(a1) + [b1 + time]  (bias = the per-step table slice)
             p.begin_stage(dout, hr, False)
             if is_up:   # K order: skip part (cat columns [width:]) then x part (cat columns [:width])
                 p.add_k_segment(lambda blk=blk, w=width: blk.lin1.weight[:, w:], dout, blk.in_dim - width)
                 p.add_k_segment(lambda blk=blk, w=width: blk.lin1.weight[:, :w], dout, width)
             else:
                 p.add_k_segment(lambda blk=blk: blk.lin1.weight, dout, blk.in_dim)
-            b1 = p.vec(lambda blk=blk: blk.lin1.bias, dout, dp)
-            p.epi(TE_LOAD_TMEM, region=hr, dp=dp, dt=dout, off0=b1, off1=t_off)
-            p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=dout)
+            p.epi(TE_LOAD, width=dout, dt=dout, region=hr, flags=F_TIME, off0=p.time_slot(t_off, dp))
+            p.epi(TE_STATS, width=dout, dt=dout, flags=STATS_RESET | STATS_FINISH)
             g = p.vec(lambda blk=blk: blk.norm2.weight, dout, dp)
             b = p.vec(lambda blk=blk: blk.norm2.bias, dout, dp)
-            p.epi(TE_EMIT_LN, dp=dp, dt=dout, off0=g, off1=b)
+            p.epi(TE_EMIT_LN, width=dout, dt=dout, off0=g, off1=b)
             p.epi(TE_EMIT_COND)
             p.end_stage()
             # ---- G2: h = lin2(a2) + b2 + cond_emb(swish(cond))
@@ -292,17 +321,17 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             p.add_k_segment(lambda blk=blk: blk.lin2.weight, dout, dout)
             p.add_k_segment(lambda blk=blk: blk.cond_emb.weight, dout, C, cond=True)
             b2 = p.vec(lambda blk=blk: blk.lin2.bias + blk.cond_emb.bias, dout, dp)
-            p.epi(TE_LOAD_TMEM, region=hr, dp=dp, dt=dout, off0=b2)
-            p.epi(TE_STATS, flags=STATS_RESET | STATS_FINISH, dp=dp, dt=dout)
+            p.epi(TE_LOAD, width=dout, dt=dout, region=hr, off0=b2)
+            p.epi(TE_STATS, width=dout, dt=dout, flags=STATS_RESET | STATS_FINISH)
             g = p.vec(lambda blk=blk: blk.norm3.weight, dout, dp)
             b = p.vec(lambda blk=blk: blk.norm3.bias, dout, dp)
-            p.epi(TE_EMIT_LN, dp=dp, dt=dout, off0=g, off1=b)
+            p.epi(TE_EMIT_LN, width=dout, dt=dout, off0=g, off1=b)
             if is_up:   # raw operands of the shortcut Linear: x part, then skip part
                 sw = blk.in_dim - width
-                p.epi(TE_LOAD_TMEM, region=xr, dp=pad16(width), dt=width, off0=xb_off)
-                p.epi(TE_EMIT_RAW, dp=pad16(width), dt=width)
-                p.epi(TE_LOAD_SKIP, dp=pad16(sw), dt=sw, slot=pop_slot[i])
-                p.epi(TE_EMIT_RAW, dp=pad16(sw), dt=sw)
+                p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=p.vec(sum_fn(xb), width, pad16(width)))
+                p.epi(TE_EMIT_RAW, width=width, dt=width)
+                p.epi(TE_LOAD_SKIP, width=sw, dt=sw, slot=pop_slot[i])
+                p.epi(TE_EMIT_RAW, width=sw, dt=sw)
             p.end_stage()
             # ---- G3: x' = lin3(a3) + b3 + shortcut(x)
             if is_up:
@@ -318,29 +347,28 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
                 p.add_k_segment(lambda blk=blk: blk.lin3.weight, dout, dout)
                 xb = xb + [lambda blk=blk: blk.lin3.bias]
             width = dout
-            xb_off = p.vec(lambda xb=tuple(xb): sum(f() for f in xb), width, dp)
-            p.epi(TE_LOAD_TMEM, region=xr, dp=dp, dt=width, off0=xb_off)
+            xoff = p.vec(sum_fn(xb), width, dp)
+            p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
             if kind == "down_res" and i < n_down:
                 p.skip_widths.append(dp)
-                p.epi(TE_STORE_SKIP, dp=dp, dt=width, slot=slot)
+                p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
                 slot += 1
-            _emit_next(p, nxt, xr, xb_off, width)
+            _emit_next(p, nxt, xr, xoff, width)
             p.end_stage()
         elif kind == "final":
             fin = model.final
             hr = 1 - xr
             p.begin_stage(M, hr, False)
             p.add_k_segment(lambda: fin.weight, M, fin.in_features)
-            bf = p.vec(lambda: fin.bias, M, pad16(M))
-            p.epi(TE_LOAD_TMEM, region=hr, dp=pad16(M), dt=M, off0=bf)
-            p.epi(TE_STORE_OUT, dp=pad16(M), dt=M)
+            p.epi(TE_LOAD, width=M, dt=M, region=hr, off0=p.vec(lambda: fin.bias, M, pad16(M)))
+            p.epi(TE_STORE_OUT, width=M, dt=M)
             p.end_stage()
     assert slot == n_push, (slot, n_push)
     return p
 
 
 def pack_tc_weights(p: TcProgram, device):
-    """-> (w_hi uint8 blob, w_lo uint8 blob or None, params fp32 blob) on `device`."""
+    """-> (w_hi fp16 blob, w_lo fp16 blob or None, params fp32 blob) on `device`."""
     with torch.no_grad():
         hi = torch.zeros(max(p.w_bytes // 2, 8), dtype=torch.float16, device=device)
         lo = torch.zeros_like(hi) if p.nterms >= 3 else None
@@ -360,7 +388,8 @@ def pack_tc_weights(p: TcProgram, device):
 
 
 def time_table_tc(model: UNet1D, p: TcProgram, t_values: torch.Tensor) -> torch.Tensor:
-    """Same hoisted time path as packer.time_table, laid out for this program's t_off."""
+    """Hoisted time path for this program's t_off layout, with each block's lin1.bias folded in:
+    row r, block k -> lin1_k.bias + time_emb_k(Swish(TimeEmbedding(t_values[r])))."""
     from .packer import _swish, sinusoid
     te = model.time_emb
     F = torch.nn.functional
@@ -369,6 +398,6 @@ def time_table_tc(model: UNet1D, p: TcProgram, t_values: torch.Tensor) -> torch.
         e = F.linear(_swish(F.linear(e, te.lin1.weight, te.lin1.bias)), te.lin2.weight, te.lin2.bias)
         a = _swish(e)
         tab = torch.zeros(a.shape[0], max(p.tt_stride, 4), dtype=torch.float32, device=a.device)
-        for t_off, lin in p.time_blocks:
-            tab[:, t_off:t_off + lin.out_features] = F.linear(a, lin.weight, lin.bias)
+        for t_off, lin, lin1 in p.time_blocks:
+            tab[:, t_off:t_off + lin.out_features] = F.linear(a, lin.weight, lin.bias) + lin1.bias
     return tab.contiguous()

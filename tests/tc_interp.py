@@ -1,6 +1,7 @@
 """Test-only CPU interpreter of the tensor-core stage program (diffsg_b200.tc_packer): same
-dataflow as diffsg_b200/csrc/unet_tc.cuh (TMEM regions, register vector, operand chunk queue),
-evaluated in fp32 (optionally with the fp16 operand rounding of the real engine)."""
+dataflow as diffsg_b200/csrc/unet_tc.cuh (TMEM regions, per-row vector, operand chunk queue,
+per-stage parameter packages), evaluated in fp32 (optionally with the fp16 operand rounding of
+the real engine)."""
 import torch
 
 from diffsg_b200 import tc_packer as T
@@ -17,8 +18,6 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
     v = torch.zeros(B, 128)
     stats = dict(cnt=0.0, mean=torch.zeros(B), m2=torch.zeros(B), rstd=torch.ones(B))
     out = None
-    w16 = w_hi.view(torch.float16) if w_hi.dtype != torch.float16 else w_hi
-    w16lo = None if w_lo is None else w_lo
 
     def split(a):
         if not emulate_fp16:
@@ -30,6 +29,26 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
         for k0 in range(0, dp, 64):
             queue.append(split(vec[:, k0:min(dp, k0 + 64)].clone()))
 
+    def do_stats(dt, flags):
+        if flags & T.STATS_RESET:
+            stats.update(cnt=0.0, mean=torch.zeros(B), m2=torch.zeros(B))
+        m = v[:, :dt].mean(dim=1)
+        q = ((v[:, :dt] - m[:, None]) ** 2).sum(dim=1)
+        tot = stats["cnt"] + dt
+        delta = m - stats["mean"]
+        stats["mean"] = stats["mean"] + delta * (dt / tot)
+        stats["m2"] = stats["m2"] + q + delta * delta * (stats["cnt"] * dt / tot)
+        stats["cnt"] = tot
+        if flags & T.STATS_FINISH:
+            stats["rstd"] = 1.0 / torch.sqrt(stats["m2"] / tot + 1e-5)
+
+    def do_emit_ln(pkg, dp, dt, og, ob):
+        g, b = pkg[:, og * 4:og * 4 + dp], pkg[:, ob * 4:ob * 4 + dp]
+        t = (v[:, :dp] - stats["mean"][:, None]) * stats["rstd"][:, None] * g + b
+        t = t * torch.sigmoid(t)
+        t[:, dt:] = 0
+        emit(t, dp)
+
     for st in p.stages:
         if st["has_gemm"]:
             N = st["n16"] * 16
@@ -39,18 +58,30 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
                 a = queue.pop(0)
                 assert a.shape[1] == kw, (a.shape, kw)
                 off = ch["w_off16"] * 8
-                img = w16[off:off + N * kw].float()
+                img = w_hi[off:off + N * kw].float()
                 if p.nterms >= 3:
-                    img = img + w16lo[off:off + N * kw].float()
+                    img = img + w_lo[off:off + N * kw].float()
                 W = img.reshape(N // 8, kw // 8, 8, 8).permute(0, 2, 1, 3).reshape(N, kw)
                 acc = acc + a @ W.t()
             regions[st["region"]][:, :N] = acc
+        # per-row package = [time slice of the row's table entry | static part]
+        static = params[st["pkg_off"]:st["pkg_off"] + st["pkg_floats"]][None, :].expand(B, -1)
+        if st["tt_src"] is not None:
+            tt = table[t_idx][:, st["tt_src"]:st["tt_src"] + st["tt_floats"]]
+            pkg = torch.cat((tt, static), dim=1)
+        else:
+            pkg = static
         for op in p.epis[st["epi_begin"]:st["epi_begin"] + st["n_epi"]]:
-            k, dp, dt = op["kind"], op["dp16"] * 16, op["dt"]
-            if k == T.TE_LOAD_TMEM:
-                v[:, :dp] = regions[op["region"]][:, :dp] + params[op["off0"]:op["off0"] + dp]
-                if op["off1"] >= 0:
-                    v[:, :dp] += table[t_idx][:, op["off1"]:op["off1"] + dp]
+            k, dp, dt = op["kind"], op["np"] * 8, op["dt"]
+            if k in (T.TE_LOAD, T.TE_LN_BLOCK):
+                v[:, :dp] = regions[op["region"]][:, :dp] + pkg[:, op["off0"] * 4:op["off0"] * 4 + dp]
+                if k == T.TE_LN_BLOCK:
+                    if op["flags"] & T.F_PUSH:
+                        skips[op["slot"]] = v[:, :dp].clone()
+                    do_stats(dt, T.STATS_RESET | T.STATS_FINISH)
+                    do_emit_ln(pkg, dp, dt, op["off1"], op["off2"])
+                    if op["flags"] & T.F_COND:
+                        emit(cpad, cpad.shape[1])
             elif k == T.TE_LOAD_SKIP:
                 v[:, :dp] = skips[op["slot"]][:, :dp]
             elif k == T.TE_STORE_SKIP:
@@ -59,23 +90,9 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
                 v[:, :dp] = 0
                 v[:, :dt] = x
             elif k == T.TE_STATS:
-                if op["flags"] & T.STATS_RESET:
-                    stats.update(cnt=0.0, mean=torch.zeros(B), m2=torch.zeros(B))
-                m = v[:, :dt].mean(dim=1)
-                q = ((v[:, :dt] - m[:, None]) ** 2).sum(dim=1)
-                tot = stats["cnt"] + dt
-                delta = m - stats["mean"]
-                stats["mean"] = stats["mean"] + delta * (dt / tot)
-                stats["m2"] = stats["m2"] + q + delta * delta * (stats["cnt"] * dt / tot)
-                stats["cnt"] = tot
-                if op["flags"] & T.STATS_FINISH:
-                    stats["rstd"] = 1.0 / torch.sqrt(stats["m2"] / tot + 1e-5)
+                do_stats(dt, op["flags"])
             elif k == T.TE_EMIT_LN:
-                g, b = params[op["off0"]:op["off0"] + dp], params[op["off1"]:op["off1"] + dp]
-                t = (v[:, :dp] - stats["mean"][:, None]) * stats["rstd"][:, None] * g + b
-                t = t * torch.sigmoid(t)
-                t[:, dt:] = 0
-                emit(t, dp)
+                do_emit_ln(pkg, dp, dt, op["off0"], op["off1"])
             elif k == T.TE_EMIT_RAW:
                 t = v[:, :dp].clone()
                 t[:, dt:] = 0
