@@ -205,7 +205,7 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     for (int i = 0; i < g->n_epi; ++i) {
         const Epi& e = ep[i];
         const bool ln = e.kind == TE_STATS || e.kind == TE_EMIT_LN || e.kind == TE_LN_BLOCK || e.kind == TE_LOAD_SKIP || e.kind == TE_STORE_SKIP;
-        const int npc = e.np / 2;
+        const int npc = e.np / 2;     // pieces per half-row: LayerNorm'd widths are powers of two (16..128 columns)
         if (e.kind < TE_LOAD || e.kind > TE_LN_BLOCK || e.np > 16 || (e.np & 1) || e.dt > e.np * 8 ||
             (ln && npc != 1 && npc != 2 && npc != 4 && npc != 8) ||
             (ln && e.dt != e.np * 8 && e.np != 2) ||

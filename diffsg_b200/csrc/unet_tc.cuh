@@ -28,14 +28,20 @@ constexpr int kSlotBytes = kRows * kChunkK * 2;      // 16 KB: one fp16 A chunk
 constexpr int kASlots = 2;
 constexpr int kWStages = 2;
 constexpr int kWStageBytes = 128 * kChunkK * 2;      // 16 KB: one fp16 W chunk (N <= 128)
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
-constexpr int kEpiWarp0 = 4;                         // epilogue warps 4..11 (two aligned warpgroups)
+#ifndef DIFFSG_TC_SPLIT
+#define DIFFSG_TC_SPLIT 1
+#endif
+constexpr int kSplit = DIFFSG_TC_SPLIT;              // threads per row in the epilogue (1 or 2)
+constexpr int kEpiThreads = 128 * kSplit;
+constexpr int kThreads = 128 + kEpiThreads;
+constexpr int kEpiWarp0 = 4;                         // epilogue warps 4.. (aligned warpgroups)
+constexpr int kVecRegs = 128 / kSplit;               // columns a thread keeps in registers
 constexpr int kTmemCols = 256;                       // two 128-column regions
 constexpr int kMaxStages = 256, kMaxChunks = 512, kMaxEpi = 1024;   // program lives in __constant__ memory (16 KB)
 constexpr int kPkgFloats = 640, kPSlots = 2;
 constexpr int kCtasPerSm = 2;
-constexpr int kRegsProducer = 24, kRegsEpilogue = 104;   // setmaxnreg split of the 80-per-thread launch budget
+// setmaxnreg split of the per-thread launch budget (split 1: 128 -> 32 / 224; split 2: 80 -> 24 / 104)
+constexpr int kRegsProducer = kSplit == 1 ? 32 : 24, kRegsEpilogue = kSplit == 1 ? 224 : 104;
 
 enum : int { TE_LOAD = 1, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT, TE_STATS, TE_EMIT_LN,
              TE_EMIT_RAW, TE_EMIT_COND, TE_LN_BLOCK };
@@ -74,7 +80,7 @@ struct SmemLayout {
     uint8_t a_hi[kASlots][kSlotBytes];
     uint8_t a_lo[kASlots][kSlotBytes];
     float pkg[kPSlots][kPkgFloats];
-    float2 xchg[2][kEpiThreads];
+    float2 xchg[2][kSplit == 2 ? kEpiThreads : 1];
     uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], p_full[kPSlots],
         p_empty[kPSlots], acc_full;
     uint32_t tmem_base, pad_;
@@ -110,7 +116,7 @@ __device__ __forceinline__ float swish_f(float x) {
 }
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer)); }
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue)); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
@@ -127,7 +133,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // Per-thread epilogue state.  A vector of `np` 8-column pieces is split between the two threads of
 // a row: half 0 owns pieces [0, np/2), half 1 owns [np/2, np); each thread keeps its pieces in v[].
 struct EpiCtx {
-    float v[64];
+    float v[kVecRegs];
     float mean, rstd, m2, cnt, cnt_all;
     uint32_t aseq;          // A-ring sequence number (chunks published so far by the whole tile)
     uint32_t xpar;          // parity of the statistics exchange buffer
@@ -162,9 +168,9 @@ __device__ __forceinline__ void emit_pieces(SmemLayout& S, EpiCtx& E, int np, F 
     tcgen05_fence_before();
     const int n0 = np >> 1;
     for (int c = c_first; c <= c_last; ++c) {
-        // both halves contribute to chunk c iff it straddles the split point n0
-        const bool both = (8 * c < n0) && (min(8 * c + 8, np) > n0);
-        mbar_arrive_n(&S.a_full[(E.aseq + c) % kASlots], both ? 1u : 2u);
+        // split rows: both halves contribute to chunk c iff it straddles the split point n0
+        const bool both = kSplit == 2 && (8 * c < n0) && (min(8 * c + 8, np) > n0);
+        mbar_arrive_n(&S.a_full[(E.aseq + c) % kASlots], (kSplit == 1 || both) ? 1u : 2u);
     }
     E.aseq += nch;
 }
@@ -219,15 +225,17 @@ __device__ __forceinline__ void stats_vec(SmemLayout& S, EpiCtx& E, int nv, int 
     }
     E.cnt_all += (float)dt;
     if (flags & kStatsFinish) {
-        S.xchg[E.xpar][E.et] = make_float2(E.mean, E.m2);
-        epi_bar_sync();
-        const float2 o = S.xchg[E.xpar][E.et ^ 128];
-        E.xpar ^= 1;
-        const float on = E.cnt_all - E.cnt;                    // the partner's column count
-        if (on > 0.f) {
-            const float delta = o.x - E.mean;
-            E.mean += delta * (on / E.cnt_all);
-            E.m2 += o.y + delta * delta * (E.cnt * on / E.cnt_all);
+        if (kSplit == 2) {
+            S.xchg[E.xpar][E.et] = make_float2(E.mean, E.m2);
+            epi_bar_sync();
+            const float2 o = S.xchg[E.xpar][E.et ^ 128];
+            E.xpar ^= 1;
+            const float on = E.cnt_all - E.cnt;                    // the partner's column count
+            if (on > 0.f) {
+                const float delta = o.x - E.mean;
+                E.mean += delta * (on / E.cnt_all);
+                E.m2 += o.y + delta * delta * (E.cnt * on / E.cnt_all);
+            }
         }
         E.rstd = rsqrtf(E.m2 / E.cnt_all + kLnEps);
     }
@@ -237,6 +245,7 @@ __device__ __forceinline__ void stats_vec(SmemLayout& S, EpiCtx& E, int nv, int 
 // the time table in forward mode)
 template <int NPC>
 __device__ __forceinline__ void load_vec(EpiCtx& E, uint32_t taddr, const float* bias) {
+    static_assert(NPC * 8 <= kVecRegs, "vector does not fit the per-thread register slice");
     if constexpr (NPC % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < NPC / 2; ++i) tmem_ld16(taddr + i * 16, *reinterpret_cast<float(*)[16]>(&E.v[i * 16]));
@@ -266,6 +275,9 @@ __device__ __forceinline__ void store_skip_vec(const EpiCtx& E, float4* sk) {
         sk[q * kRows] = make_float4(E.v[q * 4], E.v[q * 4 + 1], E.v[q * 4 + 2], E.v[q * 4 + 3]);
 }
 
+// npc = pieces (8 columns each) owned by one thread: np / kSplit.  Vectors are padded to 16 columns,
+// so with split 1 npc is even (2..16), with split 2 it is 1..8.
+#if DIFFSG_TC_SPLIT == 2
 #define DIFFSG_TC_NPC_SWITCH(npc, CALL)        \
     switch (npc) {                             \
         case 1: CALL(1); break;                \
@@ -285,6 +297,27 @@ __device__ __forceinline__ void store_skip_vec(const EpiCtx& E, float4* sk) {
         case 4: CALL(4); break;                \
         default: CALL(8); break;               \
     }
+#else
+#define DIFFSG_TC_NPC_SWITCH(npc, CALL)        \
+    switch (npc) {                             \
+        case 2: CALL(2); break;                \
+        case 4: CALL(4); break;                \
+        case 6: CALL(6); break;                \
+        case 8: CALL(8); break;                \
+        case 10: CALL(10); break;              \
+        case 12: CALL(12); break;              \
+        case 14: CALL(14); break;              \
+        default: CALL(16); break;              \
+    }
+#define DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)   \
+    switch (npc) {                             \
+        case 2: CALL(2); break;                \
+        case 4: CALL(4); break;                \
+        case 8: CALL(8); break;                \
+        default: CALL(16); break;              \
+    }
+#endif
+constexpr int kNpcPartial = kSplit == 2 ? 1 : 2;   // the only vector that may be partially valid: 16 padded columns
 
 __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P, const float* scr) {
     const uint4* img = reinterpret_cast<const uint4*>(scr + P.cond_off);
@@ -295,7 +328,7 @@ __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev&
         const uint32_t sl = sq % kASlots;
         mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
         const uint32_t base = (uint32_t)(E.row >> 3) * (nk * 128) + (E.row & 7) * 16;
-        for (int k = E.half; k < nk; k += 2) {
+        for (int k = E.half; k < nk; k += kSplit) {
             *reinterpret_cast<uint4*>(S.a_hi[sl] + base + k * 128) = img[(size_t)(c0 + k) * kRows + E.row];
             *reinterpret_cast<uint4*>(S.a_lo[sl] + base + k * 128) = img[(size_t)(nkc + c0 + k) * kRows + E.row];
         }
@@ -325,7 +358,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
         const float* pk = S.pkg[psl];
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
             const Epi op = c_epis[ei];
-            const int np = op.np, npc = np >> 1, dt = op.dt;
+            const int np = op.np, npc = np / kSplit, dt = op.dt;
             const int cb = E.half * npc * 8;                              // first column owned by this thread
             const int nv = max(0, min(dt - cb, npc * 8));                 // valid (un-padded) columns owned
             const bool full = nv == npc * 8;
@@ -353,8 +386,8 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     } else {
-                        stats_vec<1, false>(S, E, nv, dt, kStatsReset | kStatsFinish);
-                        emit_vec<1, 1, false>(S, E, np, nv, pg, pb);
+                        stats_vec<kNpcPartial, false>(S, E, nv, dt, kStatsReset | kStatsFinish);
+                        emit_vec<1, kNpcPartial, false>(S, E, np, nv, pg, pb);
                     }
                     if ((flags & kFCond) && use_cond) emit_cond(S, E, P, scr);
                     break;
@@ -376,7 +409,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                 case TE_LOAD_INPUT: {
                     const float* src = (kSampler ? R.y : R.x) + grow * P.M + cb;
 #pragma unroll
-                    for (int j = 0; j < 64; ++j)
+                    for (int j = 0; j < kVecRegs; ++j)
                         if (j < npc * 8) E.v[j] = (valid && j < nv) ? src[j] : 0.f;
                     break;
                 }
@@ -386,7 +419,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     } else {
-                        stats_vec<1, false>(S, E, nv, dt, flags);
+                        stats_vec<kNpcPartial, false>(S, E, nv, dt, flags);
                     }
                     break;
                 case TE_EMIT_LN: {
@@ -397,7 +430,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
                     } else {
-                        emit_vec<1, 1, false>(S, E, np, nv, pg, pb);
+                        emit_vec<1, kNpcPartial, false>(S, E, np, nv, pg, pb);
                     }
                     break;
                 }
@@ -419,7 +452,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     if (!kSampler) {
                         if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 64; ++j)
+                            for (int j = 0; j < kVecRegs; ++j)
                                 if (j < nv) R.eps[grow * P.M + cb + j] = E.v[j];
                         }
                         break;
@@ -427,7 +460,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     float4* stash = reinterpret_cast<float4*>(scr + P.stash_off) + (size_t)(cb / 4) * kRows + row;
                     if (pass == 0) {           // unconditional pass: park eps_0
 #pragma unroll
-                        for (int q = 0; q < 16; ++q)
+                        for (int q = 0; q < kVecRegs / 4; ++q)
                             if (q < npc * 2)
                                 stash[q * kRows] = make_float4(E.v[q * 4], E.v[q * 4 + 1], E.v[q * 4 + 2], E.v[q * 4 + 3]);
                         break;
@@ -440,7 +473,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const int64_t plane = R.B * (int64_t)P.M;
                     const int64_t pidx = (int64_t)(R.T - 1 - step) * plane;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q)
+                    for (int q = 0; q < kVecRegs / 4; ++q)
                         if (q < npc * 2 && q * 4 < nv) {
                             const float4 e0 = stash[q * kRows];
                             const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
@@ -592,11 +625,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         setmaxnreg_inc();
         EpiCtx E;
         E.et = threadIdx.x - kEpiWarp0 * 32;
-        E.half = E.et >> 7;
+        E.half = kSplit == 2 ? (E.et >> 7) : 0;
         E.row = E.et & 127;
         E.aseq = 0; E.xpar = 0; E.mean = 0.f; E.rstd = 1.f; E.m2 = 0.f; E.cnt = 0.f; E.cnt_all = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) E.v[j] = 0.f;
+        for (int j = 0; j < kVecRegs; ++j) E.v[j] = 0.f;
         uint32_t acc_phase = 0, pseq = 0;
         double st_s = 0.0, st_q = 0.0;
         float* scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats;
@@ -609,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                 uint4* img = reinterpret_cast<uint4*>(scr + P.cond_off);
                 const int nkc = P.Cp / 8;
                 const float mk = (!kSampler && R.mask && valid) ? R.mask[grow] : 1.0f;
-                for (int kc = E.half; kc < nkc; kc += 2) {
+                for (int kc = E.half; kc < nkc; kc += kSplit) {
                     float x[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
