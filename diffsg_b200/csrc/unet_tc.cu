@@ -384,6 +384,20 @@ int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
         count_launch();
     }
     DIFFSG_CUDA_OK(cudaGetLastError());
+#ifdef DIFFSG_TC_TIMING
+    {
+        static long long* dbg = nullptr;
+        if (!dbg) { cudaMalloc(&dbg, 12 * sizeof(long long)); }
+        p->tc->dev.debug = dbg;
+        cudaStreamSynchronize(st);
+        long long h[12];
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[12] = {"acc_wait", "pkg_wait", "load", "stats", "emit", "a_empty_wait", "publish", "cond", "skip_ld", "out", "total", "emit_raw"};
+        fprintf(stderr, "[tc timing, cycles of thread 0 / CTA 0, previous launch]");
+        for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
+        fprintf(stderr, "\n");
+    }
+#endif
     return DIFFSG_OK;
 }
 

@@ -70,6 +70,7 @@ struct TcDev {
     const float* params; const float* tt;
     int tt_stride, nterms;
     int M, Mp, C, Cp;
+    long long* debug;                               // DIFFSG_TC_TIMING builds: 12 clock64 accumulators
     float* scratch;                                 // per CTA: skip stack + eps stash + cond image
     size_t scratch_floats;                          // per CTA
     int skip_off[kMaxSkip];                         // float offset of each skip slot inside the CTA scratch
@@ -132,7 +133,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 
 // Per-thread epilogue state.  A vector of `np` 8-column pieces is split between the two threads of
 // a row: half 0 owns pieces [0, np/2), half 1 owns [np/2, np); each thread keeps its pieces in v[].
+#ifdef DIFFSG_TC_TIMING
+#define TCT_BEGIN() const long long _t0 = clock64()
+#define TCT_END(slot) E.tacc[slot] += clock64() - _t0
+#else
+#define TCT_BEGIN()
+#define TCT_END(slot)
+#endif
 struct EpiCtx {
+#ifdef DIFFSG_TC_TIMING
+    long long tacc[12];   // 0 acc wait, 1 pkg wait, 2 load, 3 stats, 4 emit total, 5 a_empty wait, 6 publish, 7 cond, 8 skip ld/st, 9 out, 10 whole
+#endif
     float v[kVecRegs];
     float mean, rstd, m2, cnt, cnt_all;
     uint32_t aseq;          // A-ring sequence number (chunks published so far by the whole tile)
@@ -149,9 +160,13 @@ __device__ __forceinline__ void emit_pieces(SmemLayout& S, EpiCtx& E, int np, F 
     const int nch = (np + 7) >> 3;
     // chunks touched by this thread: first = pbeg >> 3, last = (pbeg + NPC - 1) >> 3  (at most two)
     const int c_first = pbeg >> 3, c_last = (pbeg + NPC - 1) >> 3;
-    for (int c = c_first; c <= c_last; ++c) {
-        const uint32_t sq = E.aseq + c;
-        mbar_wait(&S.a_empty[sq % kASlots], ((sq / kASlots) & 1) ^ 1);
+    {
+        TCT_BEGIN();
+        for (int c = c_first; c <= c_last; ++c) {
+            const uint32_t sq = E.aseq + c;
+            mbar_wait(&S.a_empty[sq % kASlots], ((sq / kASlots) & 1) ^ 1);
+        }
+        TCT_END(5);
     }
 #pragma unroll
     for (int i = 0; i < NPC; ++i) {
@@ -164,13 +179,17 @@ __device__ __forceinline__ void emit_pieces(SmemLayout& S, EpiCtx& E, int np, F 
         *reinterpret_cast<uint4*>(S.a_hi[sl] + off) = hi;
         *reinterpret_cast<uint4*>(S.a_lo[sl] + off) = lo;
     }
-    fence_proxy_async_smem();
-    tcgen05_fence_before();
-    const int n0 = np >> 1;
-    for (int c = c_first; c <= c_last; ++c) {
-        // split rows: both halves contribute to chunk c iff it straddles the split point n0
-        const bool both = kSplit == 2 && (8 * c < n0) && (min(8 * c + 8, np) > n0);
-        mbar_arrive_n(&S.a_full[(E.aseq + c) % kASlots], (kSplit == 1 || both) ? 1u : 2u);
+    {
+        TCT_BEGIN();
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        const int n0 = np >> 1;
+        for (int c = c_first; c <= c_last; ++c) {
+            // split rows: both halves contribute to chunk c iff it straddles the split point n0
+            const bool both = kSplit == 2 && (8 * c < n0) && (min(8 * c + 8, np) > n0);
+            mbar_arrive_n(&S.a_full[(E.aseq + c) % kASlots], (kSplit == 1 || both) ? 1u : 2u);
+        }
+        TCT_END(6);
     }
     E.aseq += nch;
 }
@@ -348,13 +367,15 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
     for (int si = 0; si < P.n_stages; ++si) {
         const Stage sg = c_stages[si];
         if (sg.bits & 4) {
+            TCT_BEGIN();
             mbar_wait(&S.acc_full, acc_phase);
             acc_phase ^= 1;
             tcgen05_fence_after();
+            TCT_END(0);
         }
         const bool has_pkg = (sg.pkg_f4 | sg.tt_f4) != 0;
         const uint32_t psl = pseq % kPSlots;
-        if (has_pkg) mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1);
+        if (has_pkg) { TCT_BEGIN(); mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1); TCT_END(1); }
         const float* pk = S.pkg[psl];
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
             const Epi op = c_epis[ei];
@@ -369,9 +390,13 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const uint32_t ta = tmem_row + region * 128 + cb;
                     const float* bias = pk + op.off0 * 4 + cb;
                     if (!kSampler && (flags & kFTime)) bias = P.tt + (size_t)trow * P.tt_stride + sg.tt_src4 * 4 + cb;
+                    {
+                        TCT_BEGIN();
 #define CALL(W) load_vec<W>(E, ta, bias)
-                    DIFFSG_TC_NPC_SWITCH(npc, CALL)
+                        DIFFSG_TC_NPC_SWITCH(npc, CALL)
 #undef CALL
+                        TCT_END(2);
+                    }
                     if (op.kind == TE_LOAD) break;
                     if (flags & kFPush) {
                         float4* sk = reinterpret_cast<float4*>(scr + P.skip_off[op.slot]) + (size_t)(cb / 4) * kRows + row;
@@ -382,21 +407,33 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const float* pg = pk + op.off1 * 4;
                     const float* pb = pk + op.off2 * 4;
                     if (full) {
-#define CALL(W) { stats_vec<W, true>(S, E, nv, dt, kStatsReset | kStatsFinish); emit_vec<1, W, true>(S, E, np, nv, pg, pb); }
+                        {
+                            TCT_BEGIN();
+#define CALL(W) stats_vec<W, true>(S, E, nv, dt, kStatsReset | kStatsFinish)
+                            DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
+#undef CALL
+                            TCT_END(3);
+                        }
+                        TCT_BEGIN();
+#define CALL(W) emit_vec<1, W, true>(S, E, np, nv, pg, pb)
                         DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
+                        TCT_END(4);
                     } else {
                         stats_vec<kNpcPartial, false>(S, E, nv, dt, kStatsReset | kStatsFinish);
                         emit_vec<1, kNpcPartial, false>(S, E, np, nv, pg, pb);
                     }
-                    if ((flags & kFCond) && use_cond) emit_cond(S, E, P, scr);
+                    if ((flags & kFCond) && use_cond) { TCT_BEGIN(); emit_cond(S, E, P, scr); TCT_END(7); }
                     break;
                 }
                 case TE_LOAD_SKIP: {
+                    TCT_BEGIN();
                     const float4* sk = reinterpret_cast<const float4*>(scr + P.skip_off[op.slot]) + (size_t)(cb / 4) * kRows + row;
 #define CALL(W) load_skip_vec<W>(E, sk)
                     DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
 #undef CALL
+                    E.v[0] += 0.f * E.v[npc * 8 - 1];   // (timing builds only) make the loads complete inside the timed region
+                    TCT_END(8);
                     break;
                 }
                 case TE_STORE_SKIP: {
@@ -413,7 +450,8 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         if (j < npc * 8) E.v[j] = (valid && j < nv) ? src[j] : 0.f;
                     break;
                 }
-                case TE_STATS:
+                case TE_STATS: {
+                    TCT_BEGIN();
                     if (full) {
 #define CALL(W) stats_vec<W, true>(S, E, nv, dt, flags)
                         DIFFSG_TC_NPC_SWITCH_POW2(npc, CALL)
@@ -421,8 +459,11 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     } else {
                         stats_vec<kNpcPartial, false>(S, E, nv, dt, flags);
                     }
+                    TCT_END(3);
                     break;
+                }
                 case TE_EMIT_LN: {
+                    TCT_BEGIN();
                     const float* pg = pk + op.off0 * 4;
                     const float* pb = pk + op.off1 * 4;
                     if (full) {
@@ -432,9 +473,11 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     } else {
                         emit_vec<1, kNpcPartial, false>(S, E, np, nv, pg, pb);
                     }
+                    TCT_END(4);
                     break;
                 }
-                case TE_EMIT_RAW:
+                case TE_EMIT_RAW: {
+                    TCT_BEGIN();
                     if (full) {
 #define CALL(W) emit_vec<0, W, true>(S, E, np, nv, nullptr, nullptr)
                         DIFFSG_TC_NPC_SWITCH(npc, CALL)
@@ -444,11 +487,14 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         DIFFSG_TC_NPC_SWITCH(npc, CALL)
 #undef CALL
                     }
+                    TCT_END(11);
                     break;
+                }
                 case TE_EMIT_COND:
                     if (use_cond) emit_cond(S, E, P, scr);
                     break;
                 case TE_STORE_OUT: {
+                    TCT_BEGIN();
                     if (!kSampler) {
                         if (valid) {
 #pragma unroll
@@ -496,6 +542,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                                 }
                             }
                         }
+                    TCT_END(9);
                     break;
                 }
                 default:
@@ -627,6 +674,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         E.et = threadIdx.x - kEpiWarp0 * 32;
         E.half = kSplit == 2 ? (E.et >> 7) : 0;
         E.row = E.et & 127;
+#ifdef DIFFSG_TC_TIMING
+        for (int i = 0; i < 12; ++i) E.tacc[i] = 0;
+#endif
         E.aseq = 0; E.xpar = 0; E.mean = 0.f; E.rstd = 1.f; E.m2 = 0.f; E.cnt = 0.f; E.cnt_all = 0.f;
 #pragma unroll
         for (int j = 0; j < kVecRegs; ++j) E.v[j] = 0.f;
@@ -659,10 +709,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
             for (int step = step_hi; step >= step_lo; --step)
                 for (int pass = 0; pass < n_pass; ++pass) {
                     const bool use_cond = kSampler ? (pass == 1) : true;
+                    TCT_BEGIN();
                     run_epilogue<kSampler>(S, P, R, E, scr, grow, valid, kSampler ? step : trow_fwd, use_cond, pass,
                                            step, acc_phase, pseq, st_s, st_q);
+                    TCT_END(10);
                 }
         }
+#ifdef DIFFSG_TC_TIMING
+        if (blockIdx.x == 0 && E.et == 0 && P.debug)
+            for (int i = 0; i < 12; ++i) P.debug[i] = E.tacc[i];
+#endif
         if (kSampler && R.step_hi > R.T - 1 - R.norm_steps) {
             st_s = warp_sum(st_s);
             st_q = warp_sum(st_q);
