@@ -204,12 +204,9 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
         if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16) { set_error("attach_tc: chunk %d kw=%d", i, ch[i].kw); return DIFFSG_E_INVALID; }
     for (int i = 0; i < g->n_epi; ++i) {
         const Epi& e = ep[i];
-        const bool ln = e.kind == TE_STATS || e.kind == TE_EMIT_LN || e.kind == TE_LN_BLOCK || e.kind == TE_LOAD_SKIP || e.kind == TE_STORE_SKIP;
-        const int npc = e.np / 2;     // pieces per half-row: LayerNorm'd widths are powers of two (16..128 columns)
-        if (e.kind < TE_LOAD || e.kind > TE_LN_BLOCK || e.np > 16 || (e.np & 1) || e.dt > e.np * 8 ||
-            (ln && npc != 1 && npc != 2 && npc != 4 && npc != 8) ||
-            (ln && e.dt != e.np * 8 && e.np != 2) ||
-            ((e.kind == TE_LOAD_SKIP || e.kind == TE_STORE_SKIP || (e.kind == TE_LN_BLOCK && ((e.misc >> 1) & kFPush))) && e.slot >= g->n_skip)) {
+        const bool skip = e.kind == OP_CATLN || e.kind == OP_RAW_S || ((e.misc >> 1) & kFPush);
+        if (e.kind < OP_LN || e.kind > OP_OUT || e.np > 16 || (e.np & 1) || e.np == 0 || e.dt > e.np * 8 || e.dt == 0 ||
+            (skip && e.slot >= g->n_skip)) {
             set_error("attach_tc: epilogue op %d malformed", i); return DIFFSG_E_INVALID;
         }
     }

@@ -35,11 +35,15 @@ CHUNK_K = 64
 MAX_W = 128
 PKG_MAX_FLOATS = 640
 
-# epilogue micro-op kinds (mirror diffsg_b200/csrc/unet_tc.cuh)
+# primitive micro-ops emitted by the lowering below (an intermediate form; `_select_ops` turns each
+# stage's primitive sequence into the streaming ops the kernel implements)
 TE_LOAD, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT = 1, 2, 3, 4, 5
-TE_STATS, TE_EMIT_LN, TE_EMIT_RAW, TE_EMIT_COND, TE_LN_BLOCK = 6, 7, 8, 9, 10
+TE_STATS, TE_EMIT_LN, TE_EMIT_RAW, TE_EMIT_COND = 6, 7, 8, 9
 STATS_RESET, STATS_FINISH = 1, 2
-F_TIME, F_COND, F_PUSH = 1, 2, 4          # LOAD: bias is the time-table slice; LN_BLOCK: also emit cond / push skip
+# streaming epilogue ops (mirror diffsg_b200/csrc/unet_tc.cuh).  Each walks its source in groups of
+# 16 columns; nothing but the current group lives in registers.
+OP_LN, OP_CATLN, OP_RAW_T, OP_RAW_S, OP_RAW_IN, OP_OUT = 1, 2, 3, 4, 5, 6
+F_TIME, F_COND, F_PUSH, F_DEFER = 1, 2, 4, 8
 NONE8 = 255
 
 EPI_DT = np.dtype([("kind", "u1"), ("np", "u1"), ("dt", "u1"), ("misc", "u1"), ("slot", "u1"), ("off0", "u1"),
@@ -134,32 +138,75 @@ class TcProgram:
         st["n_epi"] = len(self.epis) - st["epi_begin"]
         # shared-memory package = [time slice (from the per-step table row) | static part (blob)]
         self.n_params += st["pkg_floats"]
-        self._fuse(st)
+        self._select_ops(st)
         self.stages.append(st)
         self._open = None
 
-    def _fuse(self, st):
-        """Peephole: LOAD [+ STORE_SKIP] + STATS(reset|finish) + EMIT_LN [+ EMIT_COND] -> LN_BLOCK."""
-        ops = self.epis[st["epi_begin"]:]
-        if not ops or ops[0]["kind"] != TE_LOAD:
-            return
-        i, push = 1, None
-        if i < len(ops) and ops[i]["kind"] == TE_STORE_SKIP:
-            push, i = ops[i], i + 1
-        if not (i + 1 < len(ops) and ops[i]["kind"] == TE_STATS and ops[i]["flags"] == (STATS_RESET | STATS_FINISH)
-                and ops[i + 1]["kind"] == TE_EMIT_LN):
-            return
-        ln = ops[i + 1]
-        i += 2
-        cond = i < len(ops) and ops[i]["kind"] == TE_EMIT_COND
-        if cond:
-            i += 1
-        ld = ops[0]
-        fused = dict(kind=TE_LN_BLOCK, np=ld["np"], dt=ld["dt"], region=ld["region"],
-                     flags=(ld["flags"] & F_TIME) | (F_COND if cond else 0) | (F_PUSH if push else 0),
-                     slot=push["slot"] if push else 0, off0=ld["off0"], off1=ln["off0"], off2=ln["off1"])
-        self.epis[st["epi_begin"]:] = [fused] + ops[i:]
-        st["n_epi"] = len(self.epis) - st["epi_begin"]
+    def _select_ops(self, st):
+        """Rewrite the stage's primitive op sequence into streaming ops."""
+        prim = self.epis[st["epi_begin"]:]
+        out, i = [], 0
+
+        def kind(j):
+            return prim[j]["kind"] if j < len(prim) else None
+
+        def op(k, src, **kw):
+            d = dict(kind=k, np=src["np"], dt=src["dt"], region=src.get("region", 0), flags=0, slot=0,
+                     off0=NONE8, off1=NONE8, off2=NONE8)
+            d.update(kw)
+            out.append(d)
+
+        while i < len(prim):
+            o = prim[i]
+            if o["kind"] == TE_LOAD_INPUT and kind(i + 1) == TE_EMIT_RAW:
+                op(OP_RAW_IN, o)
+                i += 2
+            elif o["kind"] == TE_LOAD_SKIP and kind(i + 1) == TE_EMIT_RAW:
+                op(OP_RAW_S, o, slot=o["slot"])
+                i += 2
+            elif o["kind"] == TE_LOAD:
+                j, flags, slot = i + 1, o["flags"] & F_TIME, 0
+                if kind(j) == TE_STORE_SKIP:
+                    flags, slot, j = flags | F_PUSH, prim[j]["slot"], j + 1
+                if kind(j) == TE_STORE_OUT:
+                    op(OP_OUT, o, off0=o["off0"])
+                    i = j + 1
+                elif kind(j) == TE_EMIT_RAW:
+                    op(OP_RAW_T, o, flags=flags, slot=slot, off0=o["off0"])
+                    i = j + 1
+                elif kind(j) == TE_STATS and prim[j]["flags"] == (STATS_RESET | STATS_FINISH) and kind(j + 1) == TE_EMIT_LN:
+                    ln = prim[j + 1]
+                    j += 2
+                    if kind(j) == TE_EMIT_COND:
+                        flags, j = flags | F_COND, j + 1
+                    op(OP_LN, o, flags=flags, slot=slot, off0=o["off0"], off1=ln["off0"], off2=ln["off1"])
+                    i = j
+                elif (kind(j) == TE_STATS and kind(j + 1) == TE_LOAD_SKIP and kind(j + 2) == TE_STATS
+                      and kind(j + 3) == TE_EMIT_LN and kind(j + 4) == TE_LOAD and kind(j + 5) == TE_EMIT_LN):
+                    sk, ln_s, ln_x = prim[j + 1], prim[j + 3], prim[j + 5]
+                    dp4 = o["np"] * 2
+                    # package order fixed by _emit_next: gamma_x, beta_x, gamma_s, beta_s (contiguous)
+                    assert ln_x["off1"] == ln_x["off0"] + dp4 and ln_s["off0"] == ln_x["off0"] + 2 * dp4 \
+                        and ln_s["off1"] == ln_x["off0"] + 3 * dp4 and sk["np"] == o["np"]
+                    assert not (flags & F_PUSH)
+                    op(OP_CATLN, o, flags=flags, slot=sk["slot"], off0=o["off0"], off1=ln_x["off0"])
+                    i = j + 6
+                else:
+                    raise AssertionError(f"no streaming op for primitive sequence at {i}: {[q['kind'] for q in prim]}")
+            else:
+                raise AssertionError(f"no streaming op for primitive sequence at {i}: {[q['kind'] for q in prim]}")
+        self.epis[st["epi_begin"]:] = out
+        st["n_epi"] = len(out)
+
+    def mark_deferred(self):
+        """An LN whose source region is overwritten by the NEXT stage's GEMM must not let that GEMM
+        start before the source has been read completely: its operand chunks are published at the end."""
+        for a, b in zip(self.stages, self.stages[1:]):
+            if not b["has_gemm"]:
+                continue
+            for o in self.epis[a["epi_begin"]:a["epi_begin"] + a["n_epi"]]:
+                if o["kind"] == OP_LN and o["region"] == b["region"]:
+                    o["flags"] |= F_DEFER
 
     # ---- arrays for the C-ABI
     def arrays(self):
@@ -364,6 +411,7 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             p.epi(TE_STORE_OUT, width=M, dt=M)
             p.end_stage()
     assert slot == n_push, (slot, n_push)
+    p.mark_deferred()
     return p
 
 

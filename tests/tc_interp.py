@@ -73,34 +73,39 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
             pkg = static
         for op in p.epis[st["epi_begin"]:st["epi_begin"] + st["n_epi"]]:
             k, dp, dt = op["kind"], op["np"] * 8, op["dt"]
-            if k in (T.TE_LOAD, T.TE_LN_BLOCK):
-                v[:, :dp] = regions[op["region"]][:, :dp] + pkg[:, op["off0"] * 4:op["off0"] * 4 + dp]
-                if k == T.TE_LN_BLOCK:
-                    if op["flags"] & T.F_PUSH:
-                        skips[op["slot"]] = v[:, :dp].clone()
+            bias = lambda o4: pkg[:, o4 * 4:o4 * 4 + dp]
+            if k == T.OP_RAW_IN:
+                t = torch.zeros(B, dp)
+                t[:, :dt] = x
+                emit(t, dp)
+            elif k == T.OP_RAW_S:
+                t = skips[op["slot"]][:, :dp].clone()
+                t[:, dt:] = 0
+                emit(t, dp)
+            elif k in (T.OP_RAW_T, T.OP_LN, T.OP_OUT, T.OP_CATLN):
+                v[:, :dp] = regions[op["region"]][:, :dp] + bias(op["off0"])
+                if op["flags"] & T.F_PUSH:
+                    skips[op["slot"]] = v[:, :dp].clone()
+                if k == T.OP_OUT:
+                    out = v[:, :dt].clone()
+                elif k == T.OP_RAW_T:
+                    t = v[:, :dp].clone()
+                    t[:, dt:] = 0
+                    emit(t, dp)
+                elif k == T.OP_LN:
                     do_stats(dt, T.STATS_RESET | T.STATS_FINISH)
                     do_emit_ln(pkg, dp, dt, op["off1"], op["off2"])
                     if op["flags"] & T.F_COND:
                         emit(cpad, cpad.shape[1])
-            elif k == T.TE_LOAD_SKIP:
-                v[:, :dp] = skips[op["slot"]][:, :dp]
-            elif k == T.TE_STORE_SKIP:
-                skips[op["slot"]] = v[:, :dp].clone()
-            elif k == T.TE_LOAD_INPUT:
-                v[:, :dp] = 0
-                v[:, :dt] = x
-            elif k == T.TE_STATS:
-                do_stats(dt, op["flags"])
-            elif k == T.TE_EMIT_LN:
-                do_emit_ln(pkg, dp, dt, op["off0"], op["off1"])
-            elif k == T.TE_EMIT_RAW:
-                t = v[:, :dp].clone()
-                t[:, dt:] = 0
-                emit(t, dp)
-            elif k == T.TE_EMIT_COND:
-                emit(cpad, cpad.shape[1])
-            elif k == T.TE_STORE_OUT:
-                out = v[:, :dt].clone()
+                else:   # CATLN: LayerNorm over cat(x, skip); operands: skip part first, x part second
+                    dp4 = dp // 4
+                    xv = v[:, :dp].clone()
+                    do_stats(dt, T.STATS_RESET)
+                    v[:, :dp] = skips[op["slot"]][:, :dp]
+                    do_stats(dt, T.STATS_FINISH)
+                    do_emit_ln(pkg, dp, dt, op["off1"] + 2 * dp4, op["off1"] + 3 * dp4)
+                    v[:, :dp] = xv
+                    do_emit_ln(pkg, dp, dt, op["off1"], op["off1"] + dp4)
             else:
                 raise ValueError(k)
     assert not queue, f"{len(queue)} operand chunks were emitted but never consumed"
