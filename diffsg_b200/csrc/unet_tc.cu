@@ -389,7 +389,7 @@ int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
         cudaStreamSynchronize(st);
         long long h[12];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[12] = {"acc_wait", "pkg_wait", "load", "stats", "emit", "a_empty_wait", "publish", "cond", "skip_ld", "out", "total", "emit_raw"};
+        const char* names[12] = {"acc_wait", "pkg_wait", "ln_pass1", "exchange", "ln_pass2", "a_empty_wait", "publish", "cond", "catln", "out", "total", "raw"};
         fprintf(stderr, "[tc timing, cycles of thread 0 / CTA 0, previous launch]");
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
         fprintf(stderr, "\n");

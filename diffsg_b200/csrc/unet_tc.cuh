@@ -29,9 +29,16 @@ constexpr int kSlotBytes = kRows * kChunkK * 2;      // 16 KB: one fp16 A chunk
 constexpr int kASlots = 2;
 constexpr int kWStages = 2;
 constexpr int kWStageBytes = 128 * kChunkK * 2;      // 16 KB: one fp16 W chunk (N <= 128)
-constexpr int kEpiThreads = 128;
-constexpr int kEpiWarp0 = 2;                         // warps 2..5: TMEM lane quarter = warp % 4
-constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 192
+#ifndef DIFFSG_TC_SETS
+#define DIFFSG_TC_SETS 1
+#endif
+// Epilogue warp sets: set s owns the 16-column groups g == s (mod kEpiSets) of every vector, so with
+// two sets eight warps (two per TMEM lane quarter) share one tile's epilogue.
+constexpr int kEpiSets = DIFFSG_TC_SETS;
+constexpr int kEpiThreads = 128 * kEpiSets;
+constexpr int kEpiWarp0 = kEpiSets == 1 ? 2 : 4;     // sets=1: warps 2..5; sets=2: warps 4..11 (aligned warpgroups)
+constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 192 / 384
+constexpr int kRegsProducer = 24, kRegsEpilogue = 104;   // sets=2: setmaxnreg split of the 80-per-thread launch budget
 constexpr int kTmemCols = 256;                       // two 128-column regions
 constexpr int kMaxStages = 256, kMaxChunks = 512, kMaxEpi = 1024;   // program lives in __constant__ memory (16 KB)
 constexpr int kPkgFloats = 640, kPSlots = 2;
@@ -75,6 +82,7 @@ struct SmemLayout {
     uint8_t a_hi[kASlots][kSlotBytes];
     uint8_t a_lo[kASlots][kSlotBytes];
     float pkg[kPSlots][kPkgFloats];
+    float2 xch[2][kEpiSets == 2 ? 256 : 1];         // per-row moment exchange between the two sets
     uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], p_full[kPSlots],
         p_empty[kPSlots], acc_full;
     uint32_t tmem_base, pad_;
@@ -109,13 +117,33 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ float swish_f(float x) {
     return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer)); }
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue)); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 
+#ifdef DIFFSG_TC_TIMING
+#define TCT_BEGIN(v) const long long v = clock64()
+#define TCT_END(v, slot) E.tacc[slot] += clock64() - v
+#else
+#define TCT_BEGIN(v)
+#define TCT_END(v, slot)
+#endif
 // Per-thread epilogue context
 struct EpiCtx {
-    int row;
+#ifdef DIFFSG_TC_TIMING
+    long long tacc[12];   // 0 acc wait, 1 pkg wait, 2 LN pass 1, 3 exchange, 4 LN pass 2 (incl 5, 6), 5 a_empty wait, 6 publish, 7 cond, 8 catln, 9 out, 10 total, 11 raw ops
+#endif
+    int row, set, et;
+    uint32_t xpar;          // parity of the moment-exchange buffer
     uint32_t tmem_row;      // TMEM address of this thread's lane, column 0
     uint32_t aseq;          // A-ring sequence number (chunks published so far by the tile)
     float* scr;             // this CTA's global scratch
@@ -123,24 +151,43 @@ struct EpiCtx {
     bool valid;
 };
 
-// ---- A-operand ring (producer side): one vector of `np` 8-column pieces -> ceil(np / 8) K-chunks
+// ---- A-operand ring (producer side): one vector of `np` 8-column pieces -> ceil(np / 8) K-chunks.
+// Group g (pieces 2g, 2g+1) is written by set g % kEpiSets; EVERY epilogue thread arrives once per
+// chunk (after waiting for the slot), whether or not it wrote into it.
 struct Emitter {
     uint32_t seq0;
-    int np;
+    int np, ng;
     bool defer;
 };
 __device__ __forceinline__ void emit_begin(Emitter& em, const EpiCtx& E, int np, bool defer) {
-    em.seq0 = E.aseq; em.np = np; em.defer = defer;
+    em.seq0 = E.aseq; em.np = np; em.ng = np >> 1; em.defer = defer;
+}
+#ifdef DIFFSG_TC_TIMING
+#define emit_wait_slot(S, sq) { TCT_BEGIN(_tw); mbar_wait(&(S).a_empty[(sq) % kASlots], ((((sq)) / kASlots) & 1) ^ 1); TCT_END(_tw, 5); }
+#define emit_publish(S, sq) { TCT_BEGIN(_tp); fence_proxy_async_smem(); tcgen05_fence_before(); mbar_arrive(&(S).a_full[(sq) % kASlots]); TCT_END(_tp, 6); }
+#else
+__device__ __forceinline__ void emit_wait_slot(SmemLayout& S, uint32_t sq) {
+    mbar_wait(&S.a_empty[sq % kASlots], ((sq / kASlots) & 1) ^ 1);
 }
 __device__ __forceinline__ void emit_publish(SmemLayout& S, uint32_t sq) {
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
     mbar_arrive(&S.a_full[sq % kASlots]);
 }
-// pieces 2g, 2g+1 (columns 16g .. 16g+15) of the vector
-__device__ __forceinline__ void emit_group(SmemLayout& S, const EpiCtx& E, const Emitter& em, int g, const float (&x)[16]) {
+#endif
+// first / last group of chunk c owned by set `set` (first > last: none)
+__device__ __forceinline__ void my_groups(const Emitter& em, int c, int set, int& first, int& last) {
+    const int lo = 4 * c, hi = min(4 * c + 3, em.ng - 1);
+    first = lo + ((set - lo) & (kEpiSets - 1));
+    last = hi - ((hi - set) & (kEpiSets - 1));
+}
+__device__ __forceinline__ void emit_group(SmemLayout& S, EpiCtx& E, const Emitter& em, int g, const float (&x)[16]) {
     const int c = g >> 2;
     const uint32_t sq = em.seq0 + c;
     const uint32_t sl = sq % kASlots;
-    if ((g & 3) == 0) mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
+    int first, last;
+    my_groups(em, c, E.set, first, last);
+    if (g == first) emit_wait_slot(S, sq);
     const int cnt = min(8, em.np - 8 * c);                                     // pieces in chunk c
     const uint32_t off = (uint32_t)(E.row >> 3) * (cnt * 128) + ((g & 3) * 2) * 128 + (E.row & 7) * 16;
     uint4 hi, lo;
@@ -150,18 +197,16 @@ __device__ __forceinline__ void emit_group(SmemLayout& S, const EpiCtx& E, const
     split_pack8(*reinterpret_cast<const float(*)[8]>(&x[8]), hi, lo);
     *reinterpret_cast<uint4*>(S.a_hi[sl] + off + 128) = hi;
     *reinterpret_cast<uint4*>(S.a_lo[sl] + off + 128) = lo;
-    if (!em.defer && ((g & 3) == 3 || 2 * g + 2 >= em.np)) {                  // chunk complete
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        emit_publish(S, sq);
-    }
+    if (!em.defer && g == last) emit_publish(S, sq);
 }
 __device__ __forceinline__ void emit_end(SmemLayout& S, EpiCtx& E, const Emitter& em) {
     const int nch = (em.np + 7) >> 3;
-    if (em.defer) {
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        for (int c = 0; c < nch; ++c) emit_publish(S, em.seq0 + c);
+    for (int c = 0; c < nch; ++c) {
+        int first, last;
+        my_groups(em, c, E.set, first, last);
+        const bool mine = first <= last;
+        if (!mine) emit_wait_slot(S, em.seq0 + c);          // no group of this chunk is mine: still take part
+        if (!mine || em.defer) emit_publish(S, em.seq0 + c);
     }
     E.aseq += nch;
 }
@@ -180,6 +225,27 @@ __device__ __forceinline__ void load_group_tmem(float (&x)[16], uint32_t ta, con
         x[q * 4 + 0] += b[q].x; x[q * 4 + 1] += b[q].y; x[q * 4 + 2] += b[q].z; x[q * 4 + 3] += b[q].w;
     }
 }
+// Software-pipelined walk over the accumulator: the raw TMEM load of group g+1 is in flight while
+// group g is processed.  `raw` holds the prefetched group (no bias yet).
+struct TmemWalk {
+    float raw[16];
+};
+__device__ __forceinline__ void walk_begin(TmemWalk& w, uint32_t ta) {
+    tmem_ld16(ta, w.raw);
+    tmem_ld_wait();
+}
+// x = prefetched group + bias; start fetching the next group (if any); caller must call walk_sync()
+// before the next walk_next()
+__device__ __forceinline__ void walk_next(TmemWalk& w, float (&x)[16], const float* bias, bool more, uint32_t ta_next) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
+        x[q * 4 + 0] = w.raw[q * 4 + 0] + b.x; x[q * 4 + 1] = w.raw[q * 4 + 1] + b.y;
+        x[q * 4 + 2] = w.raw[q * 4 + 2] + b.z; x[q * 4 + 3] = w.raw[q * 4 + 3] + b.w;
+    }
+    if (more) tmem_ld16(ta_next, w.raw);
+}
+__device__ __forceinline__ void walk_sync() { tmem_ld_wait(); }
 __device__ __forceinline__ void load_group_skip(float (&x)[16], const float4* sk) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -239,6 +305,18 @@ __device__ __forceinline__ void finish_moments(float s1, float s2, float shift, 
     a_shift = -(shift + md) * rstd;
 }
 
+// sum the partial moments of the two sets of a row
+__device__ __forceinline__ void exchange_moments(SmemLayout& S, EpiCtx& E, float& s1, float& s2) {
+    if (kEpiSets == 2) {
+        S.xch[E.xpar][E.et] = make_float2(s1, s2);
+        epi_bar_sync();
+        const float2 o = S.xch[E.xpar][E.et ^ 128];
+        E.xpar ^= 1;
+        s1 += o.x;
+        s2 += o.y;
+    }
+}
+
 __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P) {
     const uint4* img = reinterpret_cast<const uint4*>(E.scr + P.cond_off);
     const int nkc = P.Cp / 8;                      // 16-byte K pieces per row
@@ -247,19 +325,19 @@ __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev&
         const uint32_t sq = E.aseq, sl = sq % kASlots;
         mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
         const uint32_t base = (uint32_t)(E.row >> 3) * (nk * 128) + (E.row & 7) * 16;
-        for (int k0 = 0; k0 < nk; k0 += 4) {       // 8 independent 16-byte loads in flight
+        for (int k0 = E.set; k0 < nk; k0 += 4 * kEpiSets) {   // 8 independent 16-byte loads in flight; piece k -> set k % kEpiSets
             uint4 h[4], l[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k0 + k < nk) {
-                    h[k] = img[(size_t)(c0 + k0 + k) * kRows + E.row];
-                    l[k] = img[(size_t)(nkc + c0 + k0 + k) * kRows + E.row];
+                if (k0 + k * kEpiSets < nk) {
+                    h[k] = img[(size_t)(c0 + k0 + k * kEpiSets) * kRows + E.row];
+                    l[k] = img[(size_t)(nkc + c0 + k0 + k * kEpiSets) * kRows + E.row];
                 }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k0 + k < nk) {
-                    *reinterpret_cast<uint4*>(S.a_hi[sl] + base + (k0 + k) * 128) = h[k];
-                    *reinterpret_cast<uint4*>(S.a_lo[sl] + base + (k0 + k) * 128) = l[k];
+                if (k0 + k * kEpiSets < nk) {
+                    *reinterpret_cast<uint4*>(S.a_hi[sl] + base + (k0 + k * kEpiSets) * 128) = h[k];
+                    *reinterpret_cast<uint4*>(S.a_lo[sl] + base + (k0 + k * kEpiSets) * 128) = l[k];
                 }
         }
         fence_proxy_async_smem();
@@ -276,13 +354,15 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
     for (int si = 0; si < P.n_stages; ++si) {
         const Stage sg = c_stages[si];
         if (sg.bits & 4) {
+            TCT_BEGIN(_ta);
             mbar_wait(&S.acc_full, acc_phase);
             acc_phase ^= 1;
             tcgen05_fence_after();
+            TCT_END(_ta, 0);
         }
         const bool has_pkg = (sg.pkg_f4 | sg.tt_f4) != 0;
         const uint32_t psl = pseq % kPSlots;
-        if (has_pkg) mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1);
+        if (has_pkg) { TCT_BEGIN(_tk); mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1); TCT_END(_tk, 1); }
         const float* pk = S.pkg[psl];
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
             const Epi op = c_epis[ei];
@@ -292,70 +372,90 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             const float* bias = pk + op.off0 * 4;
             if (!kSampler && (flags & kFTime)) bias = P.tt + (size_t)trow * P.tt_stride + sg.tt_src4 * 4;
             float x[16];
+            constexpr int G = kEpiSets;       // group stride: this thread owns groups set, set + G, ...
+            const int g0 = E.set;
             switch (op.kind) {
                 case OP_LN: {
                     float4* sk = reinterpret_cast<float4*>(E.scr + P.skip_off[op.slot]) + row;
+                    // shift for the one-pass moments: column 0 of the (bias-added) vector
                     float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                    for (int g = 0; g < ng; ++g) {
-                        load_group_tmem(x, ta + g * 16, bias + g * 16);
+                    if (G == 2 && g0 != 0) shift = tmem_ld1(ta) + bias[0];
+                    TmemWalk w;
+                    TCT_BEGIN(_t1);
+                    if (g0 < ng) walk_begin(w, ta + g0 * 16);
+                    for (int g = g0; g < ng; g += G) {
+                        walk_next(w, x, bias + g * 16, g + G < ng, ta + (g + G) * 16);
                         if (flags & kFPush) store_group_skip(x, sk + (size_t)g * 4 * kRows);
                         if (g == 0) shift = x[0];
                         moments_group(x, dt - g * 16, shift, s1, s2);
+                        walk_sync();
                     }
+                    TCT_END(_t1, 2);
+                    TCT_BEGIN(_t2);
+                    exchange_moments(S, E, s1, s2);
+                    TCT_END(_t2, 3);
+                    TCT_BEGIN(_t3);
                     float a_scale, a_shift;
                     finish_moments(s1, s2, shift, (float)dt, a_scale, a_shift);
                     Emitter em;
                     emit_begin(em, E, np, (flags & kFDefer) != 0);
                     const float* pg = pk + op.off1 * 4;
                     const float* pb = pk + op.off2 * 4;
-                    for (int g = 0; g < ng; ++g) {
-                        load_group_tmem(x, ta + g * 16, bias + g * 16);
+                    if (g0 < ng) walk_begin(w, ta + g0 * 16);
+                    for (int g = g0; g < ng; g += G) {
+                        walk_next(w, x, bias + g * 16, g + G < ng, ta + (g + G) * 16);
                         ln_swish_group(x, dt - g * 16, a_scale, a_shift, pg + g * 16, pb + g * 16);
                         emit_group(S, E, em, g, x);
+                        walk_sync();
                     }
                     emit_end(S, E, em);
-                    if ((flags & kFCond) && use_cond) emit_cond(S, E, P);
+                    TCT_END(_t3, 4);
+                    if ((flags & kFCond) && use_cond) { TCT_BEGIN(_t4); emit_cond(S, E, P); TCT_END(_t4, 7); }
                     break;
                 }
                 case OP_CATLN: {
+                    TCT_BEGIN(_t5);
                     // LayerNorm over cat(x, skip): statistics over both, operands: skip part, then x part
                     const float4* sk = reinterpret_cast<const float4*>(E.scr + P.skip_off[op.slot]) + row;
                     float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                    for (int g = 0; g < ng; ++g) {
+                    if (G == 2 && g0 != 0) shift = tmem_ld1(ta) + bias[0];
+                    for (int g = g0; g < ng; g += G) {
                         load_group_tmem(x, ta + g * 16, bias + g * 16);
                         if (g == 0) shift = x[0];
                         moments_group(x, dt - g * 16, shift, s1, s2);
                     }
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
                         load_group_skip(x, sk + (size_t)g * 4 * kRows);
                         moments_group(x, dt - g * 16, shift, s1, s2);
                     }
+                    exchange_moments(S, E, s1, s2);
                     float a_scale, a_shift;
                     finish_moments(s1, s2, shift, (float)(2 * dt), a_scale, a_shift);
                     const float* pgx = pk + op.off1 * 4;            // gamma_x | beta_x | gamma_s | beta_s
                     const int dp = np * 8;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
                         load_group_skip(x, sk + (size_t)g * 4 * kRows);
                         ln_swish_group(x, dt - g * 16, a_scale, a_shift, pgx + 2 * dp + g * 16, pgx + 3 * dp + g * 16);
                         emit_group(S, E, em, g, x);
                     }
                     emit_end(S, E, em);
                     emit_begin(em, E, np, false);
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
                         load_group_tmem(x, ta + g * 16, bias + g * 16);
                         ln_swish_group(x, dt - g * 16, a_scale, a_shift, pgx + g * 16, pgx + dp + g * 16);
                         emit_group(S, E, em, g, x);
                     }
                     emit_end(S, E, em);
+                    TCT_END(_t5, 8);
                     break;
                 }
                 case OP_RAW_T: {
                     float4* sk = reinterpret_cast<float4*>(E.scr + P.skip_off[op.slot]) + row;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
                         load_group_tmem(x, ta + g * 16, bias + g * 16);
                         if (flags & kFPush) store_group_skip(x, sk + (size_t)g * 4 * kRows);
                         emit_group(S, E, em, g, x);                  // pad columns are exact zeros (zero W rows, zero bias)
@@ -367,7 +467,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const float4* sk = reinterpret_cast<const float4*>(E.scr + P.skip_off[op.slot]) + row;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
                         load_group_skip(x, sk + (size_t)g * 4 * kRows);
                         emit_group(S, E, em, g, x);
                     }
@@ -378,7 +478,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const float* src = (kSampler ? R.y : R.x) + E.grow * P.M;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) x[j] = (E.valid && g * 16 + j < dt) ? src[g * 16 + j] : 0.f;
                         emit_group(S, E, em, g, x);
@@ -394,7 +494,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const bool want_stats = step > R.T - 1 - R.norm_steps;
                     const int64_t plane = R.B * (int64_t)P.M;
                     const int64_t pidx = (int64_t)(R.T - 1 - step) * plane;
-                    for (int g = 0; g < ng; ++g) {
+                    for (int g = g0; g < ng; g += G) {
                         load_group_tmem(x, ta + g * 16, bias + g * 16);
                         if (!kSampler) {
                             if (E.valid) {
@@ -475,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
     const int step_hi = kSampler ? R.step_hi : 0, step_lo = kSampler ? R.step_lo : 0;
 
     if (warp < kEpiWarp0) {
+      if (kEpiSets == 2) setmaxnreg_dec();
       if (warp == 0) {
         // =========================== TMA producer: parameter packages + weight chunks
         if (lane == 0) {
@@ -560,10 +661,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
       }
     } else {
         // =========================== epilogue / operand producers (thread == row == TMEM lane)
+        if (kEpiSets == 2) setmaxnreg_inc();
         EpiCtx E;
+        E.et = threadIdx.x - kEpiWarp0 * 32;
+        E.set = E.et >> 7;
         E.row = 32 * (warp & 3) + lane;
         E.tmem_row = S.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
         E.aseq = 0;
+        E.xpar = 0;
+#ifdef DIFFSG_TC_TIMING
+        for (int i = 0; i < 12; ++i) E.tacc[i] = 0;
+#endif
         E.scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats;
         uint32_t acc_phase = 0, pseq = 0;
         double st_s = 0.0, st_q = 0.0;
@@ -575,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                 uint4* img = reinterpret_cast<uint4*>(E.scr + P.cond_off);
                 const int nkc = P.Cp / 8;
                 const float mk = (!kSampler && R.mask && E.valid) ? R.mask[E.grow] : 1.0f;
-                for (int kc = 0; kc < nkc; ++kc) {
+                for (int kc = E.set; kc < nkc; kc += kEpiSets) {
                     float x[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -592,10 +700,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
             for (int step = step_hi; step >= step_lo; --step)
                 for (int pass = 0; pass < n_pass; ++pass) {
                     const bool use_cond = kSampler ? (pass == 1) : true;
+                    TCT_BEGIN(_tt);
                     run_epilogue<kSampler>(S, P, R, E, kSampler ? step : trow_fwd, use_cond, pass, step, acc_phase,
                                            pseq, st_s, st_q);
+                    TCT_END(_tt, 10);
                 }
         }
+#ifdef DIFFSG_TC_TIMING
+        if (blockIdx.x == 0 && E.et == 0 && P.debug)
+            for (int i = 0; i < 12; ++i) P.debug[i] = E.tacc[i];
+#endif
         if (kSampler && R.step_hi > R.T - 1 - R.norm_steps) {
             st_s = warp_sum(st_s);
             st_q = warp_sum(st_q);
