@@ -80,6 +80,8 @@ SYMBOLS = {
     "diffsg_plan_attach_tc": (C.c_int, [_P, C.POINTER(TcProgramC)]),
     "diffsg_plan_set_tc_weights": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _I32]),
     "diffsg_plan_set_engine": (C.c_int, [_P, _I32]),
+    "diffsg_lnsw_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "diffsg_lnsw_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P]),
     "diffsg_plan_query": (C.c_int, [_P, _I32]),
     "diffsg_debug_tc_gemm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, C.c_uint32, C.c_uint32, _I32, _P]),
 }

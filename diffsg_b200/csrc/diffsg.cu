@@ -1,6 +1,7 @@
 // diffsg_b200 C-ABI: plan management, fp32 warp-row UNet forward, CFG sampler driver.
 // Interfaces replaced (reference repo): UNet1D.forward ddpm_opt/UNetCF.py:318-356,
 // DDPM.sample ddpm_opt/classifier_free_MSR.py:114-155 (== _NU.py:143-180, _CO.py:117-154).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -14,7 +15,7 @@
 namespace diffsg {
 
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs backward kernels on its own thread
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -22,7 +23,7 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ----------------------------------------------------------------------------- kernels
 extern __shared__ __align__(16) float g_smem[];
@@ -240,9 +241,7 @@ extern "C" {
 const char* diffsg_last_error(void) { return g_err; }
 int diffsg_abi_version(void) { return DIFFSG_ABI_VERSION; }
 int64_t diffsg_launch_count(int reset) {
-    const int64_t v = g_launches;
-    if (reset) g_launches = 0;
-    return v;
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int diffsg_plan_create(const diffsg_cfg* cfg, const diffsg_op* ops, int32_t n_ops,

@@ -295,3 +295,123 @@ int diffsg_cost_co(const float* x, const float* alloc, float* cost, int64_t B, i
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- LayerNorm + Swish (training)
+// y = swish(LN(x) * gamma + beta) row-wise; one warp per row.  Forward keeps (mean, rstd) for the
+// backward pass.  Reference: ddpm_opt/UNetCF.py:90,92,94,356 (nn.LayerNorm -> Swish).
+namespace diffsg {
+
+__global__ void lnsw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean,
+                                float* __restrict__ rstd, int64_t B, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < B; r += nw) {
+        const float* xr = x + r * D;
+        float s = 0.f;
+        for (int c = lane; c < D; c += 32) s += xr[c];
+        const float m = warp_sum(s) / (float)D;
+        float q = 0.f;
+        for (int c = lane; c < D; c += 32) { const float d = xr[c] - m; q = fmaf(d, d, q); }
+        const float rs = 1.0f / sqrtf(warp_sum(q) / (float)D + kLnEps);
+        for (int c = lane; c < D; c += 32) {
+            const float t = (xr[c] - m) * rs * gamma[c] + beta[c];
+            y[r * D + c] = swish_exact(t);
+        }
+        if (lane == 0) { mean[r] = m; rstd[r] = rs; }
+    }
+}
+
+// dx, and per-block partial dgamma / dbeta (reduced by lnsw_bwd_reduce_kernel)
+__global__ void lnsw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ dy,
+                                float* __restrict__ dx, float* __restrict__ dgamma_part,
+                                float* __restrict__ dbeta_part, int64_t B, int D) {
+    extern __shared__ float sh[];          // [2][D] per-block accumulators
+    float* sg = sh;
+    float* sb = sh + D;
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sh[c] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < B; r += nw) {
+        const float m = mean[r], rs = rstd[r];
+        const float* xr = x + r * D;
+        const float* dyr = dy + r * D;
+        // dt = dy * swish'(t);  dxhat = dt * gamma;  dx = rs * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < D; c += 32) {
+            const float xh = (xr[c] - m) * rs;
+            const float t = xh * gamma[c] + beta[c];
+            const float sg_ = 1.0f / (1.0f + expf(-t));
+            const float dt = dyr[c] * (sg_ * (1.0f + t * (1.0f - sg_)));
+            const float dxh = dt * gamma[c];
+            s1 += dxh;
+            s2 = fmaf(dxh, xh, s2);
+            atomicAdd(&sg[c], dt * xh);
+            atomicAdd(&sb[c], dt);
+        }
+        s1 = warp_sum(s1) / (float)D;
+        s2 = warp_sum(s2) / (float)D;
+        for (int c = lane; c < D; c += 32) {
+            const float xh = (xr[c] - m) * rs;
+            const float t = xh * gamma[c] + beta[c];
+            const float sg_ = 1.0f / (1.0f + expf(-t));
+            const float dxh = dyr[c] * (sg_ * (1.0f + t * (1.0f - sg_))) * gamma[c];
+            dx[r * D + c] = rs * (dxh - s1 - xh * s2);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        dgamma_part[(size_t)blockIdx.x * D + c] = sg[c];
+        dbeta_part[(size_t)blockIdx.x * D + c] = sb[c];
+    }
+}
+
+__global__ void lnsw_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int nblocks, int D) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    float g = 0.f, b = 0.f;
+    for (int k = 0; k < nblocks; ++k) { g += part_g[(size_t)k * D + c]; b += part_b[(size_t)k * D + c]; }
+    dgamma[c] = g;
+    dbeta[c] = b;
+}
+
+}  // namespace diffsg
+
+extern "C" {
+
+int diffsg_lnsw_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                        int64_t B, int32_t D, void* stream) {
+    if (!x || !gamma || !beta || !y || !mean || !rstd || B <= 0 || D <= 0) { set_error("lnsw_forward: bad argument"); return DIFFSG_E_INVALID; }
+    lnsw_fwd_kernel<<<blocks_for(B, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, rstd, B, D);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_lnsw_backward(const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                         const float* dy, float* dx, float* dgamma, float* dbeta, float* workspace,
+                         int64_t workspace_floats, int64_t B, int32_t D, void* stream) {
+    if (!x || !gamma || !beta || !mean || !rstd || !dy || !dx || !dgamma || !dbeta || !workspace || B <= 0 || D <= 0 || D > 4096) {
+        set_error("lnsw_backward: bad argument");
+        return DIFFSG_E_INVALID;
+    }
+    int nb = blocks_for(B, 8, 148 * 2);
+    if ((int64_t)nb * 2 * D > workspace_floats) nb = (int)(workspace_floats / (2 * (int64_t)D));
+    if (nb < 1) { set_error("lnsw_backward: workspace too small (needs >= %d floats)", 2 * D); return DIFFSG_E_INVALID; }
+    float* pg = workspace;
+    float* pb = workspace + (size_t)nb * D;
+    cudaStream_t st = (cudaStream_t)stream;
+    lnsw_bwd_kernel<<<nb, 256, 2 * D * sizeof(float), st>>>(x, gamma, beta, mean, rstd, dy, dx, pg, pb, B, D);
+    lnsw_bwd_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(pg, pb, dgamma, dbeta, nb, D);
+    count_launch(2);
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+}  // extern "C"

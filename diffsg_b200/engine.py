@@ -104,7 +104,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ parameter binding
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        return (self.model._param_epoch,) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
     def refresh(self):
         """Re-pack the blob if any parameter changed (optimizer step, load_state_dict, ...)."""

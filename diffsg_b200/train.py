@@ -1,7 +1,111 @@
-"""Differentiable UNet forward (training path).  Filled in by the training milestone."""
+"""Differentiable UNet1D forward for training (eps-MSE step of DDPM.forward).
+
+The training graph keeps PyTorch autograd as the glue and cuBLAS for the plain [B,K]x[K,N]
+Linear GEMMs (forward, dgrad, wgrad); the 82 LayerNorm -> Swish pairs per forward — the
+non-GEMM bulk of the step — run as ONE fused kernel each way (C-ABI diffsg_lnsw_forward /
+diffsg_lnsw_backward).  Semantics: reference ddpm_opt/UNetCF.py:83-95 (ResidualBlock),
+:123-157 (attention), :318-356 (UNet1D.forward); loss: classifier_free_MSR.py:100-112.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
 from . import _lib
+from .packer import sinusoid
+from .unet import AttentionBlock, DownBlock, UpBlock
+
+
+class _LnSwish(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        lib = _lib.load()
+        x = x.contiguous()
+        B, D = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(B, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.diffsg_lnsw_forward(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                               mean.data_ptr(), rstd.data_ptr(), B, D, _lib.stream_ptr()),
+                       "diffsg_lnsw_forward")
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        lib = _lib.load()
+        dy = dy.contiguous()
+        B, D = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(gamma)
+        db = torch.empty_like(beta)
+        ws = torch.empty(2 * D * 296, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.diffsg_lnsw_backward(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                                rstd.data_ptr(), dy.data_ptr(), dx.data_ptr(), dg.data_ptr(),
+                                                db.data_ptr(), ws.data_ptr(), ws.numel(), B, D, _lib.stream_ptr()),
+                       "diffsg_lnsw_backward")
+        return dx, dg, db
+
+
+def ln_swish(x, norm):
+    """swish(LayerNorm(x)) through the fused kernels (fp32, contiguous, CUDA)."""
+    return _LnSwish.apply(x, norm.weight, norm.bias)
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def _res(blk, x, temb_act, cond_act):
+    h = F.linear(ln_swish(x, blk.norm1), blk.lin1.weight, blk.lin1.bias)
+    h = h + F.linear(temb_act, blk.time_emb.weight, blk.time_emb.bias)
+    h = F.linear(ln_swish(h, blk.norm2), blk.lin2.weight, blk.lin2.bias)
+    h = h + F.linear(cond_act, blk.cond_emb.weight, blk.cond_emb.bias)
+    h = F.linear(ln_swish(h, blk.norm3), blk.lin3.weight, blk.lin3.bias)
+    if isinstance(blk.shortcut, torch.nn.Linear):
+        return h + F.linear(x, blk.shortcut.weight, blk.shortcut.bias)
+    return h + x
+
+
+def _attn(att, x):
+    if not isinstance(att, AttentionBlock):
+        return x
+    dk, nh = att.d_k, att.n_heads
+    rows = torch.cat([torch.arange(h * 3 * dk + 2 * dk, (h + 1) * 3 * dk, device=x.device) for h in range(nh)])
+    v = F.linear(x, att.projection.weight[rows], att.projection.bias[rows])     # sequence length 1: softmax == 1
+    return x + F.linear(v, att.output.weight, att.output.bias)
 
 
 def unet_forward_train(model, x, t, cond, cond_mask):
-    raise _lib.DiffsgError("diffsg_b200: the training forward/backward kernels are not built yet; "
-                           "call the model under torch.no_grad() for inference")
+    if not x.is_cuda:
+        raise _lib.DiffsgError("diffsg_b200 training runs on CUDA only (no CPU implementation)")
+    x = x.to(torch.float32).reshape(-1, model.input_dim)
+    B = x.shape[0]
+    te = model.time_emb
+    e = sinusoid(t.reshape(-1).to(torch.float32), model.proj_dim)
+    temb = F.linear(_swish(F.linear(e, te.lin1.weight, te.lin1.bias)), te.lin2.weight, te.lin2.bias)
+    if temb.shape[0] == 1 and B > 1:
+        temb = temb.expand(B, -1)
+    temb_act = _swish(temb)
+    cond_act = _swish(cond.to(torch.float32).reshape(B, -1) * cond_mask.to(torch.float32).reshape(-1, 1))
+    h = F.linear(x, model.feature_proj.weight, model.feature_proj.bias)
+    skips = [h]
+    for m in model.down:
+        if isinstance(m, DownBlock):
+            h = _attn(m.attn, _res(m.res, h, temb_act, cond_act))
+        else:
+            h = F.linear(h, m.lin.weight, m.lin.bias)
+        skips.append(h)
+    h = _res(model.middle.res1, h, temb_act, cond_act)
+    h = _attn(model.middle.attn, h)
+    h = _res(model.middle.res2, h, temb_act, cond_act)
+    for m in model.up:
+        if isinstance(m, UpBlock):
+            h = torch.cat((h, skips.pop()), dim=1)
+            h = _attn(m.attn, _res(m.res, h, temb_act, cond_act))
+        else:
+            h = F.linear(h, m.lin.weight, m.lin.bias)
+    return F.linear(ln_swish(h, model.norm), model.final.weight, model.final.bias)

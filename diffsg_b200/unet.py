@@ -151,6 +151,7 @@ class UNet1D(nn.Module):
 
         self._engine = None  # lazily-built kernel plan (diffsg_b200.engine.UNetEngine)
         self.precision = "auto"  # "auto" | "fp32" | "fp16x2" | "fp16x3" (see engine.UNetEngine)
+        self._param_epoch = 0    # bumped by mark_params_changed()
 
     # ------------------------------------------------------------------ kernel glue
     def engine(self):
@@ -160,6 +161,11 @@ class UNet1D(nn.Module):
             self._engine = UNetEngine(self, self.precision)
             self._engine.precision_request = self.precision
         return self._engine
+
+    def mark_params_changed(self):
+        """Tell the kernel plan that parameter VALUES changed through a path autograd's version
+        counters do not see (e.g. an optimiser stepping a flat buffer the parameters are views of)."""
+        self._param_epoch += 1
 
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.float(): packed weights are stale
         self._engine = None

@@ -182,8 +182,8 @@ int diffsg_plan_set_engine(diffsg_plan* plan, int32_t engine);
  * Returns -1 when not applicable. */
 int diffsg_plan_query(const diffsg_plan* plan, int32_t what);
 
-/* Number of kernel launches issued by this library on the calling thread since the last
- * reset (bench.py's `gpu_launches`). */
+/* Number of kernel launches issued by this library (process-wide) since the last reset
+ * (bench.py's `gpu_launches`). */
 int64_t diffsg_launch_count(int reset);
 
 /* Fill out[n] with the sampler's Philox normals for (seed, offset, step) — the exact
@@ -229,6 +229,18 @@ int diffsg_decode_co(const float* y_dev, float* dec_out_dev, int64_t B, int32_t 
                      void* stream);
 int diffsg_cost_co(const float* x_dev, const float* alloc_dev, float* cost_dev, int64_t B,
                    int32_t n, void* stream);
+
+/* ---- training: fused LayerNorm + Swish, forward and backward -----------------------------
+ * y = swish(layer_norm(x; gamma, beta, eps=1e-5)) for x[B, D]; forward also returns the per-row
+ * (mean, rstd) the backward needs.  Replaces the nn.LayerNorm -> Swish pairs of
+ * ddpm_opt/UNetCF.py:90,92,94,356 in the training graph (82 per forward for MSR). */
+int diffsg_lnsw_forward(const float* x_dev, const float* gamma_dev, const float* beta_dev, float* y_dev,
+                        float* mean_dev, float* rstd_dev, int64_t B, int32_t D, void* stream);
+/* workspace: >= 2 * D floats (more lets more CTAs accumulate dgamma/dbeta privately). */
+int diffsg_lnsw_backward(const float* x_dev, const float* gamma_dev, const float* beta_dev,
+                         const float* mean_dev, const float* rstd_dev, const float* dy_dev, float* dx_dev,
+                         float* dgamma_dev, float* dbeta_dev, float* workspace_dev,
+                         int64_t workspace_floats, int64_t B, int32_t D, void* stream);
 
 /* ---- test hooks (not part of the product surface) ------------------------------------
  * One 128-row tcgen05 GEMM tile: C[128,N] = A[128,K] . W[N,K]^T with A split into fp16
