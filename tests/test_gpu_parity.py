@@ -324,3 +324,73 @@ def test_data_parallel_trainer_single_gpu_step_reduces_loss():
     assert all(p.data_ptr() >= tr.flat.flat.data_ptr() for p in ddpm.model.parameters())
     y0 = ddpm.sample(X[:64], 1.0)
     assert torch.isfinite(y0).all()
+
+
+def _train_standin(kind, X, Y, cfg_net, steps, lr=1e-3):
+    """Stand-in checkpoint for a configuration whose real checkpoint is missing from the reference
+    repo: the reference recipe (init_weights, Adam, bs 512) at lr 1e-3, trained here
+    with the data-parallel trainer."""
+    from diffsg_b200.parallel import DataParallelTrainer
+    torch.manual_seed(0)
+    model = D.UNet1D(**cfg_net)
+    alphas = 1.0 - D.generate_cosine_schedule(T)
+    M = cfg_net["input_dim"]
+    if kind == "co":
+        ddpm = D.co.DDPM(T, model, M, alphas, DEV, (1, M), {}, 0.1, 0.9999, 10, 5, False)
+    else:
+        ddpm = D.msr.DDPM(T, model, M, 10.0, alphas, DEV, (1, M), {}, 0.1, 0.9999, 10, 5, False)
+    ddpm.apply(D.init_weights)
+    ddpm.to(DEV)
+    tr = DataParallelTrainer(ddpm, lr=lr)
+    n = X.shape[0]
+    g = torch.Generator().manual_seed(1)
+    first = last = None
+    for s in range(steps):
+        idx = torch.randint(0, n, (512,), generator=g).to(DEV)
+        last = float(tr.step(Y[idx], X[idx]))
+        first = last if first is None else first
+    return ddpm, first, last
+
+
+def _oracle_state(ddpm):
+    return {k: v.detach().cpu().clone() for k, v in ddpm.state_dict().items() if not k.startswith("ema.")}
+
+
+@pytest.mark.parametrize("kind", ["msr", "co"])
+def test_objective_parity_on_trained_standin(kind):
+    """BASELINE configs 1 / 4: objective of the sampled solutions on the bundled test split, same weights
+    and identical injected noise, CUDA engines vs the CPU oracle: within 0.5 % (stand-in checkpoint)."""
+    if kind == "msr":
+        d = load_golden("msr_data.npz")
+        net = CONFIGS["msr3c"][1]
+        lo, hi, W = (float(v) for v in d["scaler"])
+    else:
+        d = load_golden("co_data.npz")
+        net = CONFIGS["co"][1]
+        lo, hi = (float(v) for v in d["scaler"])
+    Xtr, Ytr = cuda(d["X_train"]), cuda(d["Y_train"])
+    ddpm, first, last = _train_standin(kind, Xtr, Ytr, net, steps=400)
+    assert last < 0.6 * first, (first, last)           # it actually learned something
+    B, M = 512, net["input_dim"]
+    Xte = torch.tensor(d["X_test"][:B])
+    sd = _oracle_state(ddpm)
+    omegas = (500.0,) if kind == "msr" else (0.0, 10.0, 500.0)      # CO: guidance-weight sweep (config 4)
+    for omega in omegas:
+        y_T, steps = O.draw_noise(B, (1, M), T, 11)
+        with torch.no_grad():
+            y_ref = O.sample(sd, T, Xte, omega, y_T, steps)
+        raw = Xte * (hi - lo) + lo
+        if kind == "msr":
+            obj_ref = O.msr_rate(W * O.msr_decode(y_ref), raw)
+        else:
+            obj_ref = O.co_cost(raw, O.co_decode(y_ref))
+        for precision in ("fp32", "fp16x3", "fp16x2"):
+            ddpm.model.precision = precision
+            y0 = ddpm.sample(Xte.to(DEV), omega, y_init=y_T.reshape(B, M), noise=torch.stack(steps).reshape(T - 2, B, M))
+            if kind == "msr":
+                obj = D.objectives.msr_decode_rate(y0, raw.to(DEV), W)
+            else:
+                obj = D.co.cost_calc(raw.to(DEV), D.co.customized_real_decoder(y0))
+            ratio = float(obj.mean()) / float(obj_ref.mean())
+            print(f"[{kind} omega={omega} {precision}] objective mean {float(obj.mean()):.5f} vs oracle {float(obj_ref.mean()):.5f}")
+            assert abs(ratio - 1) < 5e-3, (kind, omega, precision, ratio)
