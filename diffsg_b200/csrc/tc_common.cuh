@@ -42,6 +42,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Producer-side wait (TMA / MMA threads): let the hardware park the thread for up to `ns` per probe
+// instead of spinning, so the waiting warp does not steal issue slots from the epilogue warp that
+// shares its scheduler.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 2000) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
 
 // ------------------------------------------------------------------------------ fences
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)

@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                                 const uint32_t sl = pseq % kPSlots;
                                 const bool tma_time = kSampler && sg.tt_f4;
                                 const uint32_t tt_bytes = (uint32_t)sg.tt_f4 * 16u, st_bytes = (uint32_t)sg.pkg_f4 * 16u;
-                                mbar_wait(&S.p_empty[sl], ((pseq / kPSlots) & 1) ^ 1);
+                                mbar_wait_parked(&S.p_empty[sl], ((pseq / kPSlots) & 1) ^ 1);
                                 mbar_arrive_expect_tx(&S.p_full[sl], st_bytes + (tma_time ? tt_bytes : 0u));
                                 if (tma_time)
                                     tma_load_1d(S.pkg[sl], P.tt + (size_t)step * P.tt_stride + (size_t)sg.tt_src4 * 4, tt_bytes, &S.p_full[sl]);
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                                 if ((ch.flags & kChunkCond) && !use_cond) continue;
                                 const uint32_t st = wseq % kWStages, ph = (wseq / kWStages) & 1;
                                 const uint32_t bytes = (uint32_t)sg.n16 * 16u * ch.kw * 2u;
-                                mbar_wait(&S.w_empty[st], ph ^ 1);
+                                mbar_wait_parked(&S.w_empty[st], ph ^ 1);
                                 mbar_arrive_expect_tx(&S.w_full[st], bytes * w_terms);
                                 uint8_t* dst = w_ring + (size_t)st * w_terms * kWStageBytes;
                                 tma_load_1d(dst, P.w_hi + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
@@ -634,8 +634,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                                 if ((ch.flags & kChunkCond) && !use_cond) continue;
                                 const uint32_t st = wseq % kWStages, wph = (wseq / kWStages) & 1;
                                 const uint32_t sl = aseq % kASlots, aph = (aseq / kASlots) & 1;
-                                mbar_wait(&S.a_full[sl], aph);
-                                mbar_wait(&S.w_full[st], wph);
+                                mbar_wait_parked(&S.a_full[sl], aph);
+                                mbar_wait_parked(&S.w_full[st], wph);
                                 tcgen05_fence_after();
                                 const uint32_t sbo = (uint32_t)ch.kw * 16u;
                                 const uint8_t* wst = w_ring + (size_t)st * w_terms * kWStageBytes;

@@ -394,3 +394,46 @@ def test_objective_parity_on_trained_standin(kind):
             ratio = float(obj.mean()) / float(obj_ref.mean())
             print(f"[{kind} omega={omega} {precision}] objective mean {float(obj.mean()):.5f} vs oracle {float(obj_ref.mean()):.5f}")
             assert abs(ratio - 1) < 5e-3, (kind, omega, precision, ratio)
+
+
+@pytest.mark.parametrize("name,precision", [("attn", "fp32"), ("nu_like", "fp16x3"), ("nu_like", "fp32")])
+def test_short_schedule_every_step_renormalised(name, precision):
+    """T = 3 < 5: the reference's `i > T - 5` makes EVERY step (including the last) re-normalise over the
+    batch, and no step draws noise except i = 2 (`i > 1`)."""
+    from oracle.standin import make_state_dict
+    Ts = 3
+    kind, cfg = CONFIGS[name]
+    model = D.UNet1D(**cfg)
+    sdm = make_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=1234)
+    model.load_state_dict(sdm)
+    alphas = 1.0 - D.generate_cosine_schedule(Ts)
+    M = cfg["input_dim"]
+    ddpm = D.msr.DDPM(Ts, model, M, 10.0, alphas, DEV, (1, M), {}).to(DEV)
+    ddpm.model.precision = precision
+    full = {"model." + k: v for k, v in sdm.items()}
+    full.update(O.ddpm_buffers(alphas))
+    B = 37
+    g = torch.Generator().manual_seed(4)
+    cond = torch.rand(B, cfg["cond_dim"], generator=g)
+    y_T, steps = O.draw_noise(B, (1, M), Ts, 9)
+    assert len(steps) == 1
+    with torch.no_grad():
+        want = O.sample(full, Ts, cond, 2.0, y_T, steps)
+    y0 = ddpm.sample(cond.to(DEV), 2.0, y_init=y_T.reshape(B, M), noise=torch.stack(steps).reshape(1, B, M))
+    assert rel_l2(y0.cpu(), want) < 5e-4
+    # the output of a batch-normalised last step has zero mean / unit (unbiased) variance over the batch
+    assert abs(float(y0.mean())) < 1e-4 and abs(float(y0.var()) - 1.0) < 1e-3
+
+
+def test_degenerate_batches():
+    ddpm, cfg = standin_model("nu_like", DEV)
+    M, C = cfg["input_dim"], cfg["cond_dim"]
+    ddpm.noise_mode = "philox"
+    y = ddpm.sample(torch.rand(1, C, device=DEV), 3.0)
+    assert y.shape == (M,) and torch.isfinite(y).all()          # torch.squeeze semantics of the reference (MSR.py:116)
+    with torch.no_grad():
+        eps = ddpm.model(torch.rand(1, M, device=DEV), torch.zeros(1, 1, device=DEV), torch.rand(1, C, device=DEV),
+                         torch.ones(1, 1, device=DEV))
+    assert eps.shape == (1, M)
+    y = ddpm.sample(torch.rand(129, C, device=DEV), 3.0)         # one full tile + one row
+    assert y.shape == (129, M) and torch.isfinite(y).all()
