@@ -81,12 +81,19 @@ class DDPMBase(nn.Module):
     # ------------------------------------------------------------------ sampling
     def step_coefficients(self):
         """(c_eps, c_rs, c_noise)[T] exactly as the reference forms them in fp32 (MSR.py:133-134)."""
+        key = tuple((b.data_ptr(), b._version) for b in (self.betas, self.alphas_cumprod, self.reciprocal_sqrt_alphas,
+                                                         self.sqrt_one_minus_alphas_cumprod))
+        cached = getattr(self, "_coef_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]                   # no device->host read (and no stream sync) per sample() call
         T = self.T
         prev = torch.arange(T, device=self.betas.device).sub(1).clamp_min(0)
         c_eps = self.betas / self.sqrt_one_minus_alphas_cumprod
         c_rs = self.reciprocal_sqrt_alphas
         c_noise = (1.0 - self.alphas_cumprod[prev]) / (1.0 - self.alphas_cumprod)
-        return torch.cat((c_eps, c_rs, c_noise)).to(torch.float32).cpu().tolist()
+        coef = torch.cat((c_eps, c_rs, c_noise)).to(torch.float32).cpu().tolist()
+        self._coef_cache = (key, coef)
+        return coef
 
     def draw_reference_noise(self, B):
         """y_T and the T-2 per-step draws, consumed from torch's CPU generator in the

@@ -49,7 +49,7 @@ def _worker(rank, world, port, out):
         gathered = [torch.empty_like(flat.flat) for _ in range(world)]
         dist.all_gather(gathered, flat.flat)
         if rank == 0:
-            out.put([t.clone() for t in gathered])
+            out.put([t.numpy().copy() for t in gathered])      # by value: the child may exit before the parent reads
     finally:
         dist.destroy_process_group()
 
@@ -66,6 +66,7 @@ def test_flat_allreduce_matches_single_process_full_batch():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    gathered = [torch.from_numpy(a) for a in gathered]
     assert torch.equal(gathered[0], gathered[1])               # replicas stay bit-identical
     # equal shards + averaged gradients == full-batch gradient descent in one process
     torch.manual_seed(0)
