@@ -258,6 +258,30 @@ __device__ __forceinline__ void store_group_skip(const float (&x)[16], float4* s
     for (int q = 0; q < 4; ++q) sk[q * kRows] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
 }
 
+// Walk a skip vector (global scratch slab, L2 / HBM resident, ~1 us latency) in batches of two groups:
+// all 8 16-byte loads of a batch are issued back to back, so the latency is paid once per batch
+// instead of once per group.  (Loads are NOT kept in flight across body(): the operand-publish fence
+// inside emit_group would wait for them.)
+template <typename F>
+__device__ __forceinline__ void skip_walk2(const float4* sk, int g0, int G, int ng, F body) {
+    for (int gb = g0; gb < ng; gb += 2 * G) {
+        const bool two = gb + G < ng;
+        const float4* p0 = sk + (size_t)gb * 4 * kRows;
+        const float4* p1 = sk + (size_t)(two ? gb + G : gb) * 4 * kRows;
+        const float4 a0 = p0[0], a1 = p0[kRows], a2 = p0[2 * kRows], a3 = p0[3 * kRows];
+        const float4 c0 = p1[0], c1 = p1[kRows], c2 = p1[2 * kRows], c3 = p1[3 * kRows];
+        float x[16];
+        x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+        x[8] = a2.x; x[9] = a2.y; x[10] = a2.z; x[11] = a2.w; x[12] = a3.x; x[13] = a3.y; x[14] = a3.z; x[15] = a3.w;
+        body(gb, x);
+        if (two) {
+            x[0] = c0.x; x[1] = c0.y; x[2] = c0.z; x[3] = c0.w; x[4] = c1.x; x[5] = c1.y; x[6] = c1.z; x[7] = c1.w;
+            x[8] = c2.x; x[9] = c2.y; x[10] = c2.z; x[11] = c2.w; x[12] = c3.x; x[13] = c3.y; x[14] = c3.z; x[15] = c3.w;
+            body(gb + G, x);
+        }
+    }
+}
+
 // shifted one-pass moments: s1 += (x - shift), s2 += (x - shift)^2 over the first `nval` columns
 __device__ __forceinline__ void moments_group(const float (&x)[16], int nval, float shift, float& s1, float& s2) {
     float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -424,10 +448,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         if (g == 0) shift = x[0];
                         moments_group(x, dt - g * 16, shift, s1, s2);
                     }
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_skip(x, sk + (size_t)g * 4 * kRows);
-                        moments_group(x, dt - g * 16, shift, s1, s2);
-                    }
+                    skip_walk2(sk, g0, G, ng, [&](int g, const float (&xg)[16]) { moments_group(xg, dt - g * 16, shift, s1, s2); });
                     exchange_moments(S, E, s1, s2);
                     float a_scale, a_shift;
                     finish_moments(s1, s2, shift, (float)(2 * dt), a_scale, a_shift);
@@ -435,11 +456,10 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const int dp = np * 8;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_skip(x, sk + (size_t)g * 4 * kRows);
-                        ln_swish_group(x, dt - g * 16, a_scale, a_shift, pgx + 2 * dp + g * 16, pgx + 3 * dp + g * 16);
-                        emit_group(S, E, em, g, x);
-                    }
+                    skip_walk2(sk, g0, G, ng, [&](int g, float (&xg)[16]) {
+                        ln_swish_group(xg, dt - g * 16, a_scale, a_shift, pgx + 2 * dp + g * 16, pgx + 3 * dp + g * 16);
+                        emit_group(S, E, em, g, xg);
+                    });
                     emit_end(S, E, em);
                     emit_begin(em, E, np, false);
                     for (int g = g0; g < ng; g += G) {
@@ -467,10 +487,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const float4* sk = reinterpret_cast<const float4*>(E.scr + P.skip_off[op.slot]) + row;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_skip(x, sk + (size_t)g * 4 * kRows);
-                        emit_group(S, E, em, g, x);
-                    }
+                    skip_walk2(sk, g0, G, ng, [&](int g, const float (&xg)[16]) { emit_group(S, E, em, g, xg); });
                     emit_end(S, E, em);
                     break;
                 }
