@@ -82,11 +82,13 @@ __device__ __forceinline__ void philox_normal4(uint64_t row, uint32_t step, uint
     for (int h = 0; h < 2; ++h) {
         const float u0 = (float)((r.v[2 * h] >> 8) + 1u) * s;       // (0, 1]
         const float u1 = (float)(r.v[2 * h + 1] >> 8) * s;          // [0, 1)
-        const float rad = sqrtf(-2.0f * logf(u0));
+        // MUFU-based log / sincos (abs error ~1e-6): angle folded to [-pi, pi), where the fast
+        // sin/cos are most accurate; cos(t + pi) = -cos(t), sin(t + pi) = -sin(t)
+        const float rad = sqrtf(-2.0f * __logf(u0));
         float sn, cs;
-        sincosf(k2pi * u1, &sn, &cs);
-        out[2 * h] = rad * cs;
-        out[2 * h + 1] = rad * sn;
+        __sincosf(k2pi * (u1 - 0.5f), &sn, &cs);
+        out[2 * h] = -rad * cs;
+        out[2 * h + 1] = -rad * sn;
     }
 }
 

@@ -526,29 +526,52 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                             continue;
                         }
                         // conditional pass: guidance mix + posterior update (classifier_free_MSR.py:132-134)
+                        const bool vec4 = (P.M & 3) == 0;           // rows are 16-byte aligned: float4 traffic
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int c0 = g * 16 + q * 4;
-                            if (c0 >= dt) continue;
+                            if (c0 >= dt || !E.valid) continue;
+                            const int64_t idx = E.grow * P.M + c0;
                             const float4 e0 = stash[(size_t)(g * 4 + q) * kRows];
                             const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
-                            float z[4] = {0.f, 0.f, 0.f, 0.f};
-                            if (E.valid && add_noise && R.noise == nullptr)
-                                philox_normal4((uint64_t)E.grow + R.offset, (uint32_t)step, (uint32_t)(g * 4 + q), R.seed, z);
+                            float z[4] = {0.f, 0.f, 0.f, 0.f}, yo[4], yn[4], ev[4];
+                            if (add_noise) {
+                                if (R.noise == nullptr) {
+                                    philox_normal4((uint64_t)E.grow + R.offset, (uint32_t)step, (uint32_t)(g * 4 + q), R.seed, z);
+                                } else if (vec4) {
+                                    const float4 t = *reinterpret_cast<const float4*>(R.noise + pidx + idx);
+                                    z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) if (c0 + j < dt) z[j] = R.noise[pidx + idx + j];
+                                }
+                            }
+                            if (vec4) {
+                                const float4 t = *reinterpret_cast<const float4*>(R.y + idx);
+                                yo[0] = t.x; yo[1] = t.y; yo[2] = t.z; yo[3] = t.w;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) yo[j] = (c0 + j < dt) ? R.y[idx + j] : 0.f;
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const int c = c0 + j;
-                                if (E.valid && c < dt) {
-                                    const int64_t idx = E.grow * P.M + c;
-                                    if (add_noise && R.noise != nullptr) z[j] = R.noise[pidx + idx];
-                                    const float e = w1 * x[q * 4 + j] - w0 * e0a[j];
-                                    float yn = (R.y[idx] - ce * e) * crs;
-                                    if (add_noise) yn += cn * z[j];
-                                    R.y[idx] = yn;
-                                    if (R.rec_eps) R.rec_eps[pidx + idx] = e;
-                                    if (R.rec_y && !want_stats) R.rec_y[pidx + idx] = yn;
-                                    if (want_stats) { st_s += (double)yn; st_q += (double)yn * (double)yn; }
-                                }
+                                ev[j] = w1 * x[q * 4 + j] - w0 * e0a[j];
+                                yn[j] = (yo[j] - ce * ev[j]) * crs;
+                                if (add_noise) yn[j] += cn * z[j];
+                                if (want_stats && c0 + j < dt) { st_s += (double)yn[j]; st_q += (double)yn[j] * (double)yn[j]; }
+                            }
+                            if (vec4) {
+                                *reinterpret_cast<float4*>(R.y + idx) = make_float4(yn[0], yn[1], yn[2], yn[3]);
+                                if (R.rec_eps) *reinterpret_cast<float4*>(R.rec_eps + pidx + idx) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                                if (R.rec_y && !want_stats) *reinterpret_cast<float4*>(R.rec_y + pidx + idx) = make_float4(yn[0], yn[1], yn[2], yn[3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (c0 + j < dt) {
+                                        R.y[idx + j] = yn[j];
+                                        if (R.rec_eps) R.rec_eps[pidx + idx + j] = ev[j];
+                                        if (R.rec_y && !want_stats) R.rec_y[pidx + idx + j] = yn[j];
+                                    }
                             }
                         }
                     }
