@@ -124,6 +124,11 @@ def cpu_reference_run(sd, rows, reps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is entitled to every host core
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     ddpm = build_model("cpu")
     sd = {k: v.detach().clone() for k, v in ddpm.state_dict().items()}
     rows = args.ref_rows
@@ -236,6 +241,11 @@ def main():
         e2e = total / (ms2 * 1e-3)
         peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         ach_tf = (B * args.steps * f_alg) / (ms * 1e-3) / 1e12     # per GPU (rank 0's kernels)
+        traffic = None                       # DRAM bytes of the kernels of one step, scaled from the committed ncu capture
+        tpath = Path(__file__).resolve().parent / "profiles" / "r01_traffic_tc.json"
+        if engine.precision != "fp32" and tpath.exists():
+            tj = json.loads(tpath.read_text())
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / (tj["rows"] * tj["steps"]) * B * T
         line = {"metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if engine.precision == "fp32" else "f16", "data": "synthetic",
@@ -250,7 +260,9 @@ def main():
                         "d2h_bytes_per_step": B * M * 4 * world, "ms_per_step": ms2 / args.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": ach_tf / peak_tf, "traffic": None,
+                             "frac": ach_tf / peak_tf, "traffic": traffic,
+                             "traffic_note": "bytes per step per GPU = ncu dram read+write per (row, reverse step) of the phase-B launch "
+                                             "(profiles/r01_traffic_tc.json) x rows x T; not measured in this run",
                              "kernel": "sample_*_kernel (all launches of one sample() call)",
                              "flop_per_solution": f_alg, "peak_source": f"{pk_kind} bf16 sustained"}}
         if world == 1 and not args.no_cpu_baseline:
