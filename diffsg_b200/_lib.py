@@ -17,8 +17,19 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libdiffsg_b200.so"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 SOURCES = ("diffsg.cu", "side_kernels.cu", "unet_tc.cu")
+# Build variant of the tensor-core engine (diffsg_b200/csrc/unet_tc.cuh): K columns per operand chunk, A-ring
+# depth, TMEM columns per accumulator region (= widest vector), co-resident CTAs per SM.  One variant per
+# build; DIFFSG_TC_VARIANT="chunk=32,aslots=3,region=64,ctas=3" overrides it for experiments.
+TC_VARIANT = dict(chunk=64, aslots=2, region=128, ctas=2)
+for _kv in filter(None, os.environ.get("DIFFSG_TC_VARIANT", "").split(",")):
+    _k, _v = _kv.split("=")
+    if _k not in TC_VARIANT:
+        raise ValueError(f"DIFFSG_TC_VARIANT: unknown key {_k!r}")
+    TC_VARIANT[_k] = int(_v)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared")
+              "-Xcompiler", "-fPIC", "-shared",
+              f"-DDIFFSG_TC_CHUNK={TC_VARIANT['chunk']}", f"-DDIFFSG_TC_ASLOTS={TC_VARIANT['aslots']}",
+              f"-DDIFFSG_TC_REGION={TC_VARIANT['region']}", f"-DDIFFSG_TC_CTAS={TC_VARIANT['ctas']}")
 
 ABI_VERSION = 1
 OP_GEMM, OP_LNSW, OP_PUSH, OP_POP = 1, 2, 3, 4

@@ -189,14 +189,14 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     }
     if (g->nterms < 1 || g->nterms > 3) { set_error("attach_tc: nterms must be 1..3"); return DIFFSG_E_INVALID; }
     const int M = p->cfg.input_dim, C = p->cfg.cond_dim;
-    if (M > 128 || C > 128) { set_error("attach_tc: input_dim / cond_dim > 128"); return DIFFSG_E_UNSUPPORTED; }
+    if (M > kRegionCols || C > 128) { set_error("attach_tc: input_dim > %d or cond_dim > 128", kRegionCols); return DIFFSG_E_UNSUPPORTED; }
     // validate records
     const Stage* st = (const Stage*)g->stages;
     const Chunk* ch = (const Chunk*)g->chunks;
     const Epi* ep = (const Epi*)g->epis;
     for (int i = 0; i < g->n_stages; ++i) {
         if (st[i].chunk_begin + st[i].n_chunks > g->n_chunks || st[i].epi_begin + st[i].n_epi > g->n_epi ||
-            st[i].n16 < 1 || st[i].n16 > 8 || (st[i].pkg_f4 + st[i].tt_f4) * 4 > kPkgFloats) {
+            st[i].n16 < 1 || st[i].n16 * 16 > kRegionCols || (st[i].pkg_f4 + st[i].tt_f4) * 4 > kPkgFloats) {
             set_error("attach_tc: stage %d malformed", i); return DIFFSG_E_INVALID;
         }
     }
@@ -205,7 +205,7 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     for (int i = 0; i < g->n_epi; ++i) {
         const Epi& e = ep[i];
         const bool skip = e.kind == OP_CATLN || e.kind == OP_RAW_S || ((e.misc >> 1) & kFPush);
-        if (e.kind < OP_LN || e.kind > OP_OUT || e.np > 16 || (e.np & 1) || e.np == 0 || e.dt > e.np * 8 || e.dt == 0 ||
+        if (e.kind < OP_LN || e.kind > OP_OUT || e.np * 8 > kRegionCols || (e.np & 1) || e.np == 0 || e.dt > e.np * 8 || e.dt == 0 ||
             (skip && e.slot >= g->n_skip)) {
             set_error("attach_tc: epilogue op %d malformed", i); return DIFFSG_E_INVALID;
         }
@@ -276,8 +276,8 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     if (occ < 1) { set_error("attach_tc: kernel does not fit on an SM (smem %zu B)", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }
     // The occupancy API reports 1 for every kernel that contains tcgen05.alloc (it cannot see how many
     // TMEM columns are requested); two CTAs x (256 columns, <= 113 KB smem, 30 K registers) do fit.
-    const bool two = 2 * (h->smem_bytes + 1024) <= 233472;
-    h->occupancy = two ? kCtasPerSm : 1;
+    int fit = (int)(233472 / (h->smem_bytes + 1024));
+    h->occupancy = fit < 1 ? 1 : (fit > kCtasPerSm ? kCtasPerSm : fit);
     h->grid_max = p->sm_count * h->occupancy;
     return DIFFSG_OK;
 }
@@ -302,6 +302,8 @@ int tc_query(const diffsg_plan* p, int what) {
         case 2: return (int)p->tc->smem_bytes;
         case 3: return p->tc->grid_max;
         case 4: return p->tc->dev.nterms;
+        case 6: return kChunkK;
+        case 7: return kRegionCols;
         default: return -1;
     }
 }

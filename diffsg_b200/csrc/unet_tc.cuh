@@ -23,12 +23,30 @@
 namespace diffsg {
 namespace tc {
 
+// Build variant (diffsg_b200/_lib.py TC_VARIANT): K columns per operand chunk, A-ring depth, TMEM columns per
+// accumulator region and the number of co-resident CTAs (tiles) per SM the resources are budgeted for.
+#ifndef DIFFSG_TC_CHUNK
+#define DIFFSG_TC_CHUNK 64
+#endif
+#ifndef DIFFSG_TC_ASLOTS
+#define DIFFSG_TC_ASLOTS 2
+#endif
+#ifndef DIFFSG_TC_REGION
+#define DIFFSG_TC_REGION 128
+#endif
+#ifndef DIFFSG_TC_CTAS
+#define DIFFSG_TC_CTAS 2
+#endif
 constexpr int kRows = 128;
-constexpr int kChunkK = 64;
-constexpr int kSlotBytes = kRows * kChunkK * 2;      // 16 KB: one fp16 A chunk
-constexpr int kASlots = 2;
+constexpr int kChunkK = DIFFSG_TC_CHUNK;
+constexpr int kGroupsPerChunk = kChunkK / 16, kPiecesPerChunk = kChunkK / 8;
+constexpr int kSlotBytes = kRows * kChunkK * 2;      // one fp16 A chunk (16 KB at 64 columns)
+constexpr int kASlots = DIFFSG_TC_ASLOTS;
 constexpr int kWStages = 2;
-constexpr int kWStageBytes = 128 * kChunkK * 2;      // 16 KB: one fp16 W chunk (N <= 128)
+constexpr int kRegionCols = DIFFSG_TC_REGION;        // widest vector the engine carries
+constexpr int kWStageBytes = kRegionCols * kChunkK * 2;   // one fp16 W chunk (N <= kRegionCols)
+static_assert(kChunkK == 32 || kChunkK == 64, "chunk width");
+static_assert(kRegionCols == 64 || kRegionCols == 128, "region width");
 #ifndef DIFFSG_TC_SETS
 #define DIFFSG_TC_SETS 1
 #endif
@@ -36,13 +54,28 @@ constexpr int kWStageBytes = 128 * kChunkK * 2;      // 16 KB: one fp16 W chunk 
 // two sets eight warps (two per TMEM lane quarter) share one tile's epilogue.
 constexpr int kEpiSets = DIFFSG_TC_SETS;
 constexpr int kEpiThreads = 128 * kEpiSets;
-constexpr int kEpiWarp0 = kEpiSets == 1 ? 2 : 4;     // sets=1: warps 2..5; sets=2: warps 4..11 (aligned warpgroups)
-constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 192 / 384
-constexpr int kRegsProducer = 24, kRegsEpilogue = 104;   // sets=2: setmaxnreg split of the 80-per-thread launch budget
-constexpr int kTmemCols = 256;                       // two 128-column regions
+constexpr int kCtasPerSm = DIFFSG_TC_CTAS;
+// Register split (setmaxnreg): needed for > 2 CTAs per SM or two epilogue sets.  setmaxnreg is a WARPGROUP
+// instruction (4 aligned warps execute the same one), so the split build pads the producer side to a full
+// warpgroup: warps 0-3 = producers (TMA lane, MMA lane, two idle warps), epilogue from warp 4.
+#ifndef DIFFSG_TC_SPLITREGS
+#define DIFFSG_TC_SPLITREGS (kEpiSets == 2 || kCtasPerSm > 2)
+#endif
+constexpr bool kSplitRegs = DIFFSG_TC_SPLITREGS;
+constexpr int kEpiWarp0 = kSplitRegs ? 4 : 2;        // no split: warps 2..5 are the epilogue
+constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 192 (default) / 256 / 384
+// Launch budget L per thread: the register file is 4 x 16384 (one bank per scheduler), a scheduler hosts
+// ceil(CTAs x warps / 4) warps, L is that share rounded down to 8 (what ptxas derives from __launch_bounds__).
+// The producer warpgroup keeps kRegsProducer, the epilogue threads get everything that frees.
+constexpr int kWarpsPerScheduler = (kCtasPerSm * (kThreads / 32) + 3) / 4;
+constexpr int kRegsLaunch = (16384 / (kWarpsPerScheduler * 32)) / 8 * 8;
+constexpr int kRegsProducer = 24;
+constexpr int kRegsEpilogue = (kRegsLaunch + (kRegsLaunch - kRegsProducer) * (kEpiWarp0 * 32) / kEpiThreads) / 8 * 8;
+static_assert(!kSplitRegs || (kRegsProducer * kEpiWarp0 * 32 + kRegsEpilogue * kEpiThreads <= kRegsLaunch * kThreads && kRegsEpilogue <= 232),
+              "setmaxnreg split exceeds the CTA's register allocation");
+constexpr int kTmemCols = 2 * kRegionCols;           // two accumulator regions
 constexpr int kMaxStages = 256, kMaxChunks = 512, kMaxEpi = 1024;   // program lives in __constant__ memory (16 KB)
 constexpr int kPkgFloats = 640, kPSlots = 2;
-constexpr int kCtasPerSm = 2;
 
 // streaming epilogue ops (diffsg_b200/tc_packer.py)
 enum : int { OP_LN = 1, OP_CATLN, OP_RAW_T, OP_RAW_S, OP_RAW_IN, OP_OUT };
@@ -88,8 +121,8 @@ struct SmemLayout {
     uint32_t tmem_base, pad_;
     // followed by the W ring: kWStages * (nterms == 3 ? 2 : 1) * kWStageBytes (dynamic)
 };
-static_assert(((sizeof(SmemLayout) + 127) & ~size_t(127)) + kWStages * kWStageBytes + 128 <= 114688,
-              "two CTAs per SM: <= 112 KB each");
+static_assert((((sizeof(SmemLayout) + 127) & ~size_t(127)) + kWStages * kWStageBytes + 128 + 1024) * kCtasPerSm <= 233472,
+              "kCtasPerSm CTAs (fp16x2) must fit the SM's 228 KB of shared memory");
 
 // What one launch does: kSampler -> steps step_hi..step_lo, two passes each; else one forward.
 struct RunArgs {
@@ -177,19 +210,19 @@ __device__ __forceinline__ void emit_publish(SmemLayout& S, uint32_t sq) {
 #endif
 // first / last group of chunk c owned by set `set` (first > last: none)
 __device__ __forceinline__ void my_groups(const Emitter& em, int c, int set, int& first, int& last) {
-    const int lo = 4 * c, hi = min(4 * c + 3, em.ng - 1);
+    const int lo = kGroupsPerChunk * c, hi = min(kGroupsPerChunk * c + kGroupsPerChunk - 1, em.ng - 1);
     first = lo + ((set - lo) & (kEpiSets - 1));
     last = hi - ((hi - set) & (kEpiSets - 1));
 }
 __device__ __forceinline__ void emit_group(SmemLayout& S, EpiCtx& E, const Emitter& em, int g, const float (&x)[16]) {
-    const int c = g >> 2;
+    const int c = g / kGroupsPerChunk;
     const uint32_t sq = em.seq0 + c;
     const uint32_t sl = sq % kASlots;
     int first, last;
     my_groups(em, c, E.set, first, last);
     if (g == first) emit_wait_slot(S, sq);
-    const int cnt = min(8, em.np - 8 * c);                                     // pieces in chunk c
-    const uint32_t off = (uint32_t)(E.row >> 3) * (cnt * 128) + ((g & 3) * 2) * 128 + (E.row & 7) * 16;
+    const int cnt = min(kPiecesPerChunk, em.np - kPiecesPerChunk * c);         // pieces in chunk c
+    const uint32_t off = (uint32_t)(E.row >> 3) * (cnt * 128) + ((g % kGroupsPerChunk) * 2) * 128 + (E.row & 7) * 16;
     uint4 hi, lo;
     split_pack8(*reinterpret_cast<const float(*)[8]>(&x[0]), hi, lo);
     *reinterpret_cast<uint4*>(S.a_hi[sl] + off) = hi;
@@ -200,7 +233,7 @@ __device__ __forceinline__ void emit_group(SmemLayout& S, EpiCtx& E, const Emitt
     if (!em.defer && g == last) emit_publish(S, sq);
 }
 __device__ __forceinline__ void emit_end(SmemLayout& S, EpiCtx& E, const Emitter& em) {
-    const int nch = (em.np + 7) >> 3;
+    const int nch = (em.np + kPiecesPerChunk - 1) / kPiecesPerChunk;
     for (int c = 0; c < nch; ++c) {
         int first, last;
         my_groups(em, c, E.set, first, last);
@@ -344,8 +377,8 @@ __device__ __forceinline__ void exchange_moments(SmemLayout& S, EpiCtx& E, float
 __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P) {
     const uint4* img = reinterpret_cast<const uint4*>(E.scr + P.cond_off);
     const int nkc = P.Cp / 8;                      // 16-byte K pieces per row
-    for (int c0 = 0; c0 < nkc; c0 += 8) {
-        const int nk = min(8, nkc - c0);
+    for (int c0 = 0; c0 < nkc; c0 += kPiecesPerChunk) {
+        const int nk = min(kPiecesPerChunk, nkc - c0);
         const uint32_t sq = E.aseq, sl = sq % kASlots;
         mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
         const uint32_t base = (uint32_t)(E.row >> 3) * (nk * 128) + (E.row & 7) * 16;
@@ -392,7 +425,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             const Epi op = c_epis[ei];
             const int np = op.np, ng = np >> 1, dt = op.dt;
             const int region = op.misc & 1, flags = op.misc >> 1;
-            const uint32_t ta = E.tmem_row + region * 128;
+            const uint32_t ta = E.tmem_row + region * kRegionCols;
             const float* bias = pk + op.off0 * 4;
             if (!kSampler && (flags & kFTime)) bias = P.tt + (size_t)trow * P.tt_stride + sg.tt_src4 * 4;
             float x[16];
@@ -615,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
     const int step_hi = kSampler ? R.step_hi : 0, step_lo = kSampler ? R.step_lo : 0;
 
     if (warp < kEpiWarp0) {
-      if (kEpiSets == 2) setmaxnreg_dec();
+      if (kSplitRegs) setmaxnreg_dec();
       if (warp == 0) {
         // =========================== TMA producer: parameter packages + weight chunks
         if (lane == 0) {
@@ -667,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                             const Stage sg = c_stages[si];
                             if (!(sg.bits & 4)) continue;
                             const uint32_t idesc = make_idesc_f16(128, (uint32_t)sg.n16 * 16u);
-                            const uint32_t d_tmem = S.tmem_base + (sg.bits & 1) * 128;
+                            const uint32_t d_tmem = S.tmem_base + (sg.bits & 1) * kRegionCols;
                             uint32_t acc = (sg.bits >> 1) & 1;
                             for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
                                 const Chunk ch = c_chunks[ci];
@@ -701,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
       }
     } else {
         // =========================== epilogue / operand producers (thread == row == TMEM lane)
-        if (kEpiSets == 2) setmaxnreg_inc();
+        if (kSplitRegs) setmaxnreg_inc();
         EpiCtx E;
         E.et = threadIdx.x - kEpiWarp0 * 32;
         E.set = E.et >> 7;

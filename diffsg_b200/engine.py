@@ -80,6 +80,10 @@ class UNetEngine:
                                    n_chunks=len(ch), n_epi=len(ep), n_skip=len(self.tc.skip_widths),
                                    nterms=self.tc.nterms, tt_stride=max(self.tc.tt_stride, 4))
             _lib.check(self.lib.diffsg_plan_attach_tc(self.handle, C.byref(prog)), "diffsg_plan_attach_tc")
+            built = (int(self.lib.diffsg_plan_query(self.handle, 6)), int(self.lib.diffsg_plan_query(self.handle, 7)))
+            if built != (tc_packer.CHUNK_K, tc_packer.MAX_W):
+                raise _lib.DiffsgError(f"libdiffsg_b200.so was built for (chunk, region) = {built}, the packer lowers for "
+                                       f"{(tc_packer.CHUNK_K, tc_packer.MAX_W)}: rebuild (diffsg_b200._lib.build_library(force=True))")
             _lib.check(self.lib.diffsg_plan_set_engine(self.handle, _lib.ENGINE_TC), "diffsg_plan_set_engine")
         self._sig = None
         self._blob = None

@@ -29,10 +29,11 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .unet import DownBlock, ResidualBlock, UNet1D, UpBlock
 
-CHUNK_K = 64
-MAX_W = 128
+CHUNK_K = _lib.TC_VARIANT["chunk"]      # K columns per operand chunk (must match the library build)
+MAX_W = _lib.TC_VARIANT["region"]       # widest vector = TMEM columns per accumulator region
 PKG_MAX_FLOATS = 640
 
 # primitive micro-ops emitted by the lowering below (an intermediate form; `_select_ops` turns each
@@ -65,8 +66,8 @@ def supported(model: UNet1D) -> str | None:
     widths = [model.proj_dim, *model.dims]
     if any(w > MAX_W or w < 8 or (w & (w - 1)) for w in widths):
         return f"internal widths must be powers of two in [8, {MAX_W}]"
-    if model.input_dim > MAX_W or model.cond_dim > MAX_W:
-        return f"input_dim / cond_dim > {MAX_W}"
+    if model.input_dim > MAX_W or model.cond_dim > 128:
+        return f"input_dim > {MAX_W} or cond_dim > 128"
     if any(model.is_attn) or model.middle_attn:
         return "attention blocks"
     return None
