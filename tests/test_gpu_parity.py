@@ -326,6 +326,37 @@ def test_data_parallel_trainer_single_gpu_step_reduces_loss():
     assert torch.isfinite(y0).all()
 
 
+def test_trainer_cuda_graph_mode():
+    """cuda_graph=True: capturing must not change the model (lr-0 warm-up, optimiser state reset), and the
+    replayed step trains like the eager one (different RNG streams: compare the loss level, not bits)."""
+    from diffsg_b200.parallel import DataParallelTrainer
+    kind, cfg = CONFIGS["nu_like"]
+    M = cfg["input_dim"]
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(512, cfg["cond_dim"], generator=g).to(DEV)
+    Y = torch.rand(512, M, generator=g).to(DEV)
+    finals = {}
+    for mode in (False, True):
+        torch.manual_seed(0)
+        model = D.UNet1D(**cfg)
+        ddpm = D.msr.DDPM(T, model, M, 10.0, 1.0 - D.generate_cosine_schedule(T), DEV, (1, M), {}).to(DEV)
+        ddpm.apply(D.init_weights)
+        tr = DataParallelTrainer(ddpm, lr=1e-3, cuda_graph=mode)
+        if mode:
+            before = tr.flat.flat.clone()
+            tr._graphs[((512, M), (512, cfg["cond_dim"]))] = tr._capture(Y, X)
+            assert torch.equal(before, tr.flat.flat)
+            assert all(float(v.abs().sum()) == 0 for st in tr.opt.state.values() for v in st.values() if torch.is_tensor(v))
+        losses = [tr.step(Y, X) for _ in range(150)]
+        first, last = float(torch.stack(losses[:10]).mean()), float(torch.stack(losses[-30:]).mean())
+        assert last < 0.7 * first, (mode, first, last)
+        assert torch.isfinite(tr.flat.flat).all()
+        finals[mode] = last
+        y0 = ddpm.sample(X[:64], 1.0)                 # the inference engine sees the graph-updated weights
+        assert torch.isfinite(y0).all()
+    assert abs(finals[True] / finals[False] - 1) < 0.25, finals
+
+
 def _train_standin(kind, X, Y, cfg_net, steps, lr=1e-3):
     """Stand-in checkpoint for a configuration whose real checkpoint is missing from the reference
     repo: the reference recipe (init_weights, Adam, bs 512) at lr 1e-3, trained here
