@@ -153,6 +153,10 @@ namespace tc {
 
 static std::mutex g_prog_mutex;
 static uint64_t g_resident[64] = {0};
+// Recorded after every tensor-core launch: the kernels read the stage program from __constant__ memory, so
+// before ANOTHER plan's program is uploaded (possibly on a different stream) that stream must wait for the
+// last kernel of the program it replaces.
+static cudaEvent_t g_last_launch[64] = {nullptr};
 
 struct TcHost {
     TcDev dev{};
@@ -315,10 +319,19 @@ static int tc_activate(diffsg_plan* p, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_prog_mutex);
     const int dev = p->cfg.device & 63;
     if (g_resident[dev] == h->serial) return DIFFSG_OK;
+    if (g_last_launch[dev]) DIFFSG_CUDA_OK(cudaStreamWaitEvent(st, g_last_launch[dev], 0));
     DIFFSG_CUDA_OK(cudaMemcpyToSymbolAsync(c_stages, h->stages.data(), sizeof(Stage) * h->stages.size(), 0, cudaMemcpyHostToDevice, st));
     DIFFSG_CUDA_OK(cudaMemcpyToSymbolAsync(c_chunks, h->chunks.data(), sizeof(Chunk) * h->chunks.size(), 0, cudaMemcpyHostToDevice, st));
     DIFFSG_CUDA_OK(cudaMemcpyToSymbolAsync(c_epis, h->epis.data(), sizeof(Epi) * h->epis.size(), 0, cudaMemcpyHostToDevice, st));
     g_resident[dev] = h->serial;
+    return DIFFSG_OK;
+}
+
+static int tc_mark_launch(const diffsg_plan* p, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_prog_mutex);
+    const int dev = p->cfg.device & 63;
+    if (!g_last_launch[dev]) DIFFSG_CUDA_OK(cudaEventCreateWithFlags(&g_last_launch[dev], cudaEventDisableTiming));
+    DIFFSG_CUDA_OK(cudaEventRecord(g_last_launch[dev], st));
     return DIFFSG_OK;
 }
 
@@ -337,7 +350,7 @@ int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float
     tc_unet_kernel<false><<<tc_grid(p, B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
     count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
-    return DIFFSG_OK;
+    return tc_mark_launch(p, st);
 }
 
 __global__ void tc_renorm_kernel(float* __restrict__ y, float* __restrict__ rec, const double* __restrict__ stt, int64_t n) {
@@ -383,6 +396,7 @@ int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
         count_launch();
     }
     DIFFSG_CUDA_OK(cudaGetLastError());
+    if (int rc = tc_mark_launch(p, st)) return rc;
 #ifdef DIFFSG_TC_TIMING
     {
         static long long* dbg = nullptr;

@@ -16,6 +16,9 @@
  *     duration of the call (weights: until the next diffsg_plan_set_weights / destroy).
  *   - all work is enqueued on the caller's stream (`stream` = cudaStream_t cast to
  *     void*); no call synchronises the device.
+ *   - a plan owns per-CTA scratch: calls on ONE plan must be ordered on one stream (or by events);
+ *     different plans may run concurrently on different streams (the library orders the swap of the
+ *     tensor-core stage program, which lives in __constant__ memory, behind the kernels still using it).
  *   - there is no CPU path: a missing/unsupported GPU is an error, never a fallback.
  */
 #ifndef DIFFSG_B200_H

@@ -47,3 +47,37 @@ def test_tc_gemm_tile(K, N):
     e3 = rel_l2(run_gemm(A, W, 3), want)
     print(f"K={K} N={N}: rel-L2 fp16x1 {e1:.2e}  x2 {e2:.2e}  x3 {e3:.2e}")
     assert e1 < 2e-3 and e2 < 5e-4 and e3 < 2e-6
+
+
+def test_two_programs_on_two_streams():
+    """The stage program lives in __constant__ memory, one program resident per device: two plans used
+    concurrently from two streams must still see their own program (the upload waits for the last kernel of the
+    program it replaces)."""
+    import diffsg_b200 as D
+    from conftest import standin_model
+    models = []
+    for name in ("nu_like", "co"):
+        ddpm, cfg = standin_model(name)
+        ddpm = ddpm.to(DEV)
+        ddpm.model.precision = "fp16x2"
+        n = 40000                                    # 313 tiles: more than one wave, so launches overlap in time
+        g = torch.Generator().manual_seed(7)
+        x = torch.randn(n, cfg["input_dim"], generator=g).to(DEV)
+        c = torch.rand(n, cfg["cond_dim"], generator=g).to(DEV)
+        t = (torch.randint(0, 20, (1, n), generator=g) / 20).to(DEV)
+        m = torch.ones(n, 1, device=DEV)
+        with torch.no_grad():
+            want = ddpm.model(x, t, c, m).clone()
+        models.append((ddpm, x, t, c, m, want))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=DEV) for _ in models]
+    outs = [[] for _ in models]
+    with torch.no_grad():
+        for rep in range(6):
+            for i, (ddpm, x, t, c, m, _) in enumerate(models):
+                with torch.cuda.stream(streams[i]):
+                    outs[i].append(ddpm.model(x, t, c, m))
+    torch.cuda.synchronize()
+    for i, (_, _, _, _, _, want) in enumerate(models):
+        for o in outs[i]:
+            assert torch.equal(o, want)
