@@ -75,7 +75,11 @@ class DDPMBase(nn.Module):
 
     def loss_from(self, y_t, ts, cond, cond_mask, noise):
         """Deterministic part of `forward` (fixed `(ts, noise, cond_mask)`), used by parity tests."""
-        est = self.model(y_t, ts / self.T, cond, cond_mask)
+        m = self.model
+        if y_t.is_cuda and torch.is_grad_enabled() and hasattr(m, "forward_steps"):
+            est = m.forward_steps(y_t, ts, self.T, cond, cond_mask)      # integer steps: hoisted time path
+        else:
+            est = m(y_t, ts / self.T, cond, cond_mask)
         return torch.nn.functional.mse_loss(noise.reshape(est.shape), est)
 
     # ------------------------------------------------------------------ sampling

@@ -59,9 +59,10 @@ def _swish(x):
     return x * torch.sigmoid(x)
 
 
-def _res(blk, x, temb_act, cond_act):
+def _res(blk, x, temb_act, cond_act, t_sel=None):
     h = F.linear(ln_swish(x, blk.norm1), blk.lin1.weight, blk.lin1.bias)
-    h = h + F.linear(temb_act, blk.time_emb.weight, blk.time_emb.bias)
+    tb = F.linear(temb_act, blk.time_emb.weight, blk.time_emb.bias)
+    h = h + (tb if t_sel is None else torch.index_select(tb, 0, t_sel))
     h = F.linear(ln_swish(h, blk.norm2), blk.lin2.weight, blk.lin2.bias)
     h = h + F.linear(cond_act, blk.cond_emb.weight, blk.cond_emb.bias)
     h = F.linear(ln_swish(h, blk.norm3), blk.lin3.weight, blk.lin3.bias)
@@ -79,15 +80,23 @@ def _attn(att, x):
     return x + F.linear(v, att.output.weight, att.output.bias)
 
 
-def unet_forward_train(model, x, t, cond, cond_mask):
+def unet_forward_train(model, x, t, cond, cond_mask, t_index=None, n_steps=None):
+    """`t_index` [B] (integer step of every row) with `n_steps` = T hoists the time path exactly as the sampler
+    does: TimeEmbedding and every block's `time_emb` Linear are evaluated on the T grid values i / T only
+    ([T, 4P] instead of [B, 4P] operands: 60 % of the forward MACs of the 80c net disappear) and gathered per row;
+    gradients flow back through the gather.  Without it `t` [1, B] may hold arbitrary values."""
     if not x.is_cuda:
         raise _lib.DiffsgError("diffsg_b200 training runs on CUDA only (no CPU implementation)")
     x = x.to(torch.float32).reshape(-1, model.input_dim)
     B = x.shape[0]
     te = model.time_emb
+    t_sel = None
+    if t_index is not None:
+        t_sel = t_index.reshape(-1).to(torch.long)
+        t = torch.arange(int(n_steps), device=x.device, dtype=torch.float32) / float(n_steps)
     e = sinusoid(t.reshape(-1).to(torch.float32), model.proj_dim)
     temb = F.linear(_swish(F.linear(e, te.lin1.weight, te.lin1.bias)), te.lin2.weight, te.lin2.bias)
-    if temb.shape[0] == 1 and B > 1:
+    if t_sel is None and temb.shape[0] == 1 and B > 1:
         temb = temb.expand(B, -1)
     temb_act = _swish(temb)
     cond_act = _swish(cond.to(torch.float32).reshape(B, -1) * cond_mask.to(torch.float32).reshape(-1, 1))
@@ -95,17 +104,17 @@ def unet_forward_train(model, x, t, cond, cond_mask):
     skips = [h]
     for m in model.down:
         if isinstance(m, DownBlock):
-            h = _attn(m.attn, _res(m.res, h, temb_act, cond_act))
+            h = _attn(m.attn, _res(m.res, h, temb_act, cond_act, t_sel))
         else:
             h = F.linear(h, m.lin.weight, m.lin.bias)
         skips.append(h)
-    h = _res(model.middle.res1, h, temb_act, cond_act)
+    h = _res(model.middle.res1, h, temb_act, cond_act, t_sel)
     h = _attn(model.middle.attn, h)
-    h = _res(model.middle.res2, h, temb_act, cond_act)
+    h = _res(model.middle.res2, h, temb_act, cond_act, t_sel)
     for m in model.up:
         if isinstance(m, UpBlock):
             h = torch.cat((h, skips.pop()), dim=1)
-            h = _attn(m.attn, _res(m.res, h, temb_act, cond_act))
+            h = _attn(m.attn, _res(m.res, h, temb_act, cond_act, t_sel))
         else:
             h = F.linear(h, m.lin.weight, m.lin.bias)
     return F.linear(ln_swish(h, model.norm), model.final.weight, model.final.bias)

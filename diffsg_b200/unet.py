@@ -195,6 +195,22 @@ class UNet1D(nn.Module):
         return unet_forward(self, x, t, cond, cond_mask)
 
 
+def _forward_steps(self, x, ts, n_steps, cond, cond_mask):
+    """`forward(x, ts / n_steps, cond, cond_mask)` for INTEGER steps `ts` [1, B] or [B]: the training graph
+    evaluates the time path on the n_steps grid values only (diffsg_b200.train); inference is unchanged."""
+    from .engine import unet_forward
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+    if needs_grad and x.is_cuda:
+        from .train import unet_forward_train
+        if x.shape[0] >= 1024:    # below that the step is launch-bound and the 2 x 27 gather / scatter kernels cost more
+            return unet_forward_train(self, x, None, cond, cond_mask, t_index=ts, n_steps=n_steps)
+        return unet_forward_train(self, x, ts / n_steps, cond, cond_mask)
+    return unet_forward(self, x, ts / n_steps, cond, cond_mask)
+
+
+UNet1D.forward_steps = _forward_steps
+
+
 def infer_config_from_state_dict(sd, prefix="model."):
     """Recover UNet1D constructor arguments from a reference checkpoint's tensor shapes.
 
