@@ -156,6 +156,8 @@ class UNetEngine:
         self.refresh()
         x2 = _f32c(x).reshape(-1, self.program.input_dim)
         B = x2.shape[0]
+        if B == 0:      # empty batch: nothing to launch (the reference returns an empty tensor too)
+            return torch.empty(0, self.program.input_dim, dtype=torch.float32, device=self.device)
         cond2 = _f32c(cond).reshape(B, self.program.cond_dim)
         tv = t.detach().reshape(-1).to(torch.float32)
         if tv.numel() == 1 and B > 1:
@@ -181,6 +183,8 @@ class UNetEngine:
                rec_y=None, rec_eps=None):
         """In-place reverse diffusion on `y_init` ([B, M] fp32 CUDA); returns it."""
         _require_cuda(cond, y_init, noise, rec_y, rec_eps)
+        if y_init.shape[0] == 0:
+            return y_init
         self.refresh()
         table = self.step_table(T)
         self._bind(table)
@@ -213,6 +217,8 @@ def unet_forward(model, x, t, cond, cond_mask):
 def philox_normal(B: int, M: int, step: int, seed: int, offset: int, device) -> torch.Tensor:
     """The sampler's own noise stream for (seed, offset, step) as a [B, M] tensor."""
     out = torch.empty(B, M, dtype=torch.float32, device=device)
+    if B == 0:
+        return out
     lib = _lib.load()
     with torch.cuda.device(out.device):
         _lib.check(lib.diffsg_philox_normal(out.data_ptr(), B, M, step, int(seed) & (2**64 - 1),

@@ -508,3 +508,11 @@ def test_degenerate_batches():
     assert eps.shape == (1, M)
     y = ddpm.sample(torch.rand(129, C, device=DEV), 3.0)         # one full tile + one row
     assert y.shape == (129, M) and torch.isfinite(y).all()
+    for precision in ("fp16x2", "fp32"):                          # empty batch: empty result, no launch, no error
+        ddpm.model.precision = precision
+        y = ddpm.sample(torch.rand(0, C, device=DEV), 3.0)
+        assert y.numel() == 0
+        with torch.no_grad():
+            eps = ddpm.model(torch.rand(0, M, device=DEV), torch.zeros(1, 0, device=DEV), torch.rand(0, C, device=DEV),
+                             torch.ones(0, 1, device=DEV))
+        assert eps.shape == (0, M)
