@@ -151,19 +151,27 @@ class UNetEngine:
         return self._tables[key]
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x, t, cond, cond_mask):
-        _require_cuda(x, t, cond, cond_mask)
+    def forward(self, x, t, cond, cond_mask, t_index=None, n_steps=None):
+        """`t` [1, B] arbitrary time values (the distinct ones are found with torch.unique: one host sync), or
+        `t_index` [B] integer steps of an `n_steps` schedule (cached step table, no sync)."""
+        _require_cuda(x, t, cond, cond_mask, t_index)
         self.refresh()
         x2 = _f32c(x).reshape(-1, self.program.input_dim)
         B = x2.shape[0]
         if B == 0:      # empty batch: nothing to launch (the reference returns an empty tensor too)
             return torch.empty(0, self.program.input_dim, dtype=torch.float32, device=self.device)
         cond2 = _f32c(cond).reshape(B, self.program.cond_dim)
-        tv = t.detach().reshape(-1).to(torch.float32)
-        if tv.numel() == 1 and B > 1:
-            tv = tv.expand(B)
-        uniq, inv = torch.unique(tv, return_inverse=True)
-        table = self._time_table(uniq)
+        if t_index is not None:
+            table = self.step_table(int(n_steps))
+            inv = t_index.detach().reshape(-1)
+            if inv.numel() == 1 and B > 1:
+                inv = inv.expand(B)
+        else:
+            tv = t.detach().reshape(-1).to(torch.float32)
+            if tv.numel() == 1 and B > 1:
+                tv = tv.expand(B)
+            uniq, inv = torch.unique(tv, return_inverse=True)
+            table = self._time_table(uniq)
         self._keep = table  # keep alive while bound
         self._bind(table)
         mask = None

@@ -326,6 +326,25 @@ def test_data_parallel_trainer_single_gpu_step_reduces_loss():
     assert torch.isfinite(y0).all()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+def test_forward_steps_inference_matches_forward(precision):
+    """UNet1D.forward_steps without grad = the engine forward on the cached step table (no torch.unique sync):
+    bit-identical to forward(x, ts / T, ...)."""
+    ddpm, cfg = standin_model("nu_like")
+    ddpm = ddpm.to(DEV)
+    ddpm.model.precision = precision
+    B = 300
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, cfg["input_dim"], generator=g).to(DEV)
+    c = torch.rand(B, cfg["cond_dim"], generator=g).to(DEV)
+    ts = torch.randint(0, T, (1, B), generator=g).to(DEV)
+    m = torch.ones(B, 1, device=DEV)
+    with torch.no_grad():
+        a = ddpm.model.forward_steps(x, ts, T, c, m)
+        b = ddpm.model(x, ts / T, c, m)
+    assert torch.equal(a, b)
+
+
 def test_training_time_path_hoisting_is_exact():
     """UNet1D.forward_steps (time path evaluated on the T grid rows, gathered per sample) against the plain
     training graph (per-sample time path, the reference's formulation): same eps, same parameter gradients."""
