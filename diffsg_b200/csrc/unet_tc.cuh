@@ -507,7 +507,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                 case OP_RAW_T: {
                     float4* sk = reinterpret_cast<float4*>(E.scr + P.skip_off[op.slot]) + row;
                     Emitter em;
-                    emit_begin(em, E, np, false);
+                    emit_begin(em, E, np, (flags & kFDefer) != 0);     // deferred when the next GEMM accumulates into this region (attention)
                     for (int g = g0; g < ng; g += G) {
                         load_group_tmem(x, ta + g * 16, bias + g * 16);
                         if (flags & kFPush) store_group_skip(x, sk + (size_t)g * 4 * kRows);

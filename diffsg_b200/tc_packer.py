@@ -13,6 +13,7 @@ Layout decisions made here:
   * `cat(x, skip)` is never materialised: its K-chunks are emitted skip-part first, x-part
     second, and the weight rows are permuted to match;
   * an UpBlock's `lin3(a3) + shortcut(cat(x, skip))` is ONE GEMM group of K = D + 2D;
+  * a single-token AttentionBlock is ONE accumulate stage with the fused matrix output.weight @ V.weight;
   * weights are fp16 core-matrix images ([n/8][k/8][n%8][8], one image per <=64-wide K-chunk)
     streamed by 1-D bulk TMA; with nterms == 3 a second image holds the fp16 residual of W;
   * every fp32 side parameter a stage's epilogue needs (bias, LayerNorm gamma/beta) is packed
@@ -30,7 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .unet import DownBlock, ResidualBlock, UNet1D, UpBlock
+from .unet import AttentionBlock, DownBlock, ResidualBlock, UNet1D, UpBlock
 
 CHUNK_K = _lib.TC_VARIANT["chunk"]      # K columns per operand chunk (must match the library build)
 MAX_W = _lib.TC_VARIANT["region"]       # widest vector = TMEM columns per accumulator region
@@ -68,8 +69,6 @@ def supported(model: UNet1D) -> str | None:
         return f"internal widths must be powers of two in [8, {MAX_W}]"
     if model.input_dim > MAX_W or model.cond_dim > 128:
         return f"input_dim > {MAX_W} or cond_dim > 128"
-    if any(model.is_attn) or model.middle_attn:
-        return "attention blocks"
     return None
 
 
@@ -206,7 +205,7 @@ class TcProgram:
             if not b["has_gemm"]:
                 continue
             for o in self.epis[a["epi_begin"]:a["epi_begin"] + a["n_epi"]]:
-                if o["kind"] == OP_LN and o["region"] == b["region"]:
+                if o["kind"] in (OP_LN, OP_RAW_T) and o["region"] == b["region"]:
                     o["flags"] |= F_DEFER
 
     # ---- arrays for the C-ABI
@@ -271,17 +270,38 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
     p = TcProgram(input_dim=model.input_dim, cond_dim=model.cond_dim, nterms=nterms)
     M, C = model.input_dim, model.cond_dim
 
-    # flat module sequence with look-ahead ("what consumes x next?")
-    seq = []
+    # flat module sequence with look-ahead ("what consumes x next?"); `push`: the module's output is a skip
+    seq, pushes = [], []
+
+    def add(kind, mod, push=False):
+        seq.append((kind, mod))
+        pushes.append(push)
+
+    def add_res(kind, stage_mod, res, push):
+        att = getattr(stage_mod, "attn", None)
+        if isinstance(att, AttentionBlock):     # single-token attention = x + output(V(x)): one more accumulate stage
+            add(kind, res)
+            add("attn", att, push)
+        else:
+            add(kind, res, push)
+
     for m in model.down:
-        seq.append(("down_res", m.res) if isinstance(m, DownBlock) else ("lin", m.lin))
-    seq += [("mid_res", model.middle.res1), ("mid_res", model.middle.res2)]
+        if isinstance(m, DownBlock):
+            add_res("down_res", m, m.res, True)
+        else:
+            add("lin", m.lin, True)
+    add_res("mid_res", model.middle, model.middle.res1, False)
+    add("mid_res", model.middle.res2)
     for m in model.up:
-        seq.append(("up_res", m.res) if isinstance(m, UpBlock) else ("lin", m.lin))
-    seq.append(("final", None))
+        if isinstance(m, UpBlock):
+            add_res("up_res", m, m.res, False)
+        else:
+            add("lin", m.lin)
+    add("final", None)
 
     # skip slots are pushed after feature_proj and after every `down` module, popped LIFO by UpBlocks
     n_push = 1 + len(model.down)
+    assert sum(pushes) == len(model.down)
     pops = [i for i, (k, _) in enumerate(seq) if k == "up_res"]
     assert len(pops) == n_push
     pop_slot = {idx: n_push - 1 - j for j, idx in enumerate(pops)}
@@ -290,7 +310,7 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
         k, mod = seq[i]
         if k in ("down_res", "mid_res"):
             return ("res", mod)
-        if k == "lin":
+        if k in ("lin", "attn"):
             return ("raw",)
         if k == "up_res":
             return ("up", mod, pop_slot[i])
@@ -321,7 +341,6 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
     _emit_next(p, consumer_plan(0), xr, xoff, width)
     p.end_stage()
     slot += 1
-    n_down = len(model.down)
 
     for i, (kind, mod) in enumerate(seq):
         nxt = consumer_plan(i + 1) if i + 1 < len(seq) else None
@@ -335,7 +354,29 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             xb = [lambda lin=lin: lin.bias]
             xoff = p.vec(sum_fn(xb), width, pad16(width))
             p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
-            if i < n_down:
+            if pushes[i]:
+                p.skip_widths.append(pad16(width))
+                p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
+                slot += 1
+            _emit_next(p, nxt, xr, xoff, width)
+            p.end_stage()
+        elif kind == "attn":
+            # x' = x + output(V(x)) (the reference's length-1 sequence makes softmax == 1, UNetCF.py:123-157):
+            # ONE accumulate stage with the host-fused matrix output.weight . V.weight, bias folded into xb
+            att = mod
+            dk, nh = att.d_k, att.n_heads
+
+            def v_rows(att=att, dk=dk, nh=nh):
+                return torch.cat([torch.arange(h * 3 * dk + 2 * dk, (h + 1) * 3 * dk) for h in range(nh)])
+
+            p.begin_stage(width, xr, True)
+            p.add_k_segment(lambda att=att, vr=v_rows: att.output.weight.double().matmul(att.projection.weight[vr()].double()).float(),
+                            width, width)
+            xb = xb + [lambda att=att, vr=v_rows: (att.output.weight.double().matmul(att.projection.bias[vr()].double())
+                                                   + att.output.bias.double()).float()]
+            xoff = p.vec(sum_fn(xb), width, pad16(width))
+            p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
+            if pushes[i]:
                 p.skip_widths.append(pad16(width))
                 p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
                 slot += 1
@@ -397,7 +438,7 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             width = dout
             xoff = p.vec(sum_fn(xb), width, dp)
             p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
-            if kind == "down_res" and i < n_down:
+            if pushes[i]:
                 p.skip_widths.append(dp)
                 p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
                 slot += 1

@@ -26,7 +26,7 @@ def cuda(a):
 
 # engine -> (per-pass eps tolerance, tolerance on a well-conditioned final y)
 PRECISIONS = {"fp32": (2e-5, 5e-4), "fp16x3": (2e-5, 5e-4), "fp16x2": (1e-3, 5e-3)}
-ENGINE_CASES = [(n, p) for n in CONFIGS for p in PRECISIONS if not (n == "attn" and p != "fp32")]
+ENGINE_CASES = [(n, p) for n in CONFIGS for p in PRECISIONS]
 
 
 def with_precision(ddpm, precision):
@@ -49,11 +49,13 @@ def test_unet_forward_matches_reference(name, precision):
 def test_auto_precision_picks_tensor_cores_when_supported():
     ddpm, _ = standin_model("msr80c", DEV)
     assert ddpm.model.engine().precision == "fp16x2" and ddpm.model.engine().tc is not None
-    ddpm, _ = standin_model("attn", DEV)
-    assert ddpm.model.engine().precision == "fp32"
-    ddpm.model.precision = "fp16x3"
+    ddpm, _ = standin_model("attn", DEV)           # attention lowers to one accumulate stage per block
+    assert ddpm.model.engine().precision == "fp16x2" and ddpm.model.engine().tc is not None
+    odd = D.UNet1D(input_dim=4, proj_dim=24, cond_dim=4, dims=(12, 6), is_attn=(False, False), n_blocks=1).to(DEV)
+    assert odd.engine().precision == "fp32"        # widths outside the tensor-core engine: exact-fp32 engine
+    odd.precision = "fp16x3"
     with pytest.raises(_lib.DiffsgError):
-        ddpm.model.engine()
+        odd.engine()
 
 
 @pytest.mark.parametrize("precision", list(PRECISIONS))
@@ -486,7 +488,7 @@ def test_objective_parity_on_trained_standin(kind):
             assert abs(ratio - 1) < 5e-3, (kind, omega, precision, ratio)
 
 
-@pytest.mark.parametrize("name,precision", [("attn", "fp32"), ("nu_like", "fp16x3"), ("nu_like", "fp32")])
+@pytest.mark.parametrize("name,precision", [("attn", "fp32"), ("attn", "fp16x3"), ("nu_like", "fp16x3"), ("nu_like", "fp32")])
 def test_short_schedule_every_step_renormalised(name, precision):
     """T = 3 < 5: the reference's `i > T - 5` makes EVERY step (including the last) re-normalise over the
     batch, and no step draws noise except i = 2 (`i > 1`)."""

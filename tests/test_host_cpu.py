@@ -218,7 +218,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.Op) == 48 and ctypes.sizeof(_lib.Cfg) == 64 and ctypes.sizeof(_lib.SampleArgs) == 96
 
 
-@pytest.mark.parametrize("name", ["nu_like", "msr3c", "msr80c", "co"])
+@pytest.mark.parametrize("name", ["nu_like", "msr3c", "msr80c", "co", "attn"])
 def test_tc_program_matches_oracle(name):
     """tc_packer: stage/chunk/epilogue lowering, fp16 weight images (x3 -> ~fp32), cumulative biases,
     cat-free UpBlocks, merged lin3+shortcut GEMM groups — interpreted on the CPU."""
@@ -237,7 +237,11 @@ def test_tc_program_matches_oracle(name):
     assert ch.dtype.itemsize == 8 and ep.dtype.itemsize == 8
     assert len(st) <= 128 and len(ch) <= 224 and len(ep) <= 384 and st.dtype.itemsize == 16
     expect = {"msr3c": (546688, 3768), "msr80c": (566400, 100480), "co": (329024, 11736), "nu_like": (60864, 2736)}
-    assert prog.gemm_macs() == expect[name]
+    if name in expect:
+        assert prog.gemm_macs() == expect[name]
+    else:   # attention (UNetCF.py:123-157) = one accumulate stage per block whose raw operand is published deferred
+        raw_t = [e for e in prog.epis if e["kind"] == tc_packer.OP_RAW_T and e["flags"] & tc_packer.F_DEFER]
+        assert len(raw_t) == sum(isinstance(m, D.unet.AttentionBlock) for m in ddpm.model.modules()) > 0
     # fp16x2 mode: same program, weights rounded to fp16 once
     prog2 = tc_packer.lower_tc(ddpm.model, nterms=2)
     hi2, lo2, params2 = tc_packer.pack_tc_weights(prog2, "cpu")
@@ -248,10 +252,6 @@ def test_tc_program_matches_oracle(name):
 
 def test_tc_engine_rejects_unsupported_topologies():
     from diffsg_b200 import tc_packer
-    ddpm, _ = standin_model("attn")
-    assert tc_packer.supported(ddpm.model) == "attention blocks"
-    with pytest.raises(ValueError):
-        tc_packer.lower_tc(ddpm.model)
     wide = D.UNet1D(input_dim=4, proj_dim=256, cond_dim=4, dims=(64, 32), is_attn=(False, False), n_blocks=1)
     assert tc_packer.supported(wide) is not None
     odd = D.UNet1D(input_dim=4, proj_dim=24, cond_dim=4, dims=(12, 6), is_attn=(False, False), n_blocks=1)
