@@ -65,8 +65,8 @@ def pad16(n: int) -> int:
 def supported(model: UNet1D) -> str | None:
     """None if the tensor-core engine can run this topology, else the reason it cannot."""
     widths = [model.proj_dim, *model.dims]
-    if any(w > MAX_W or w < 8 or (w & (w - 1)) for w in widths):
-        return f"internal widths must be powers of two in [8, {MAX_W}]"
+    if any(w > MAX_W or w < 1 for w in widths):     # any width: vectors are padded to multiples of 16 with exact zeros
+        return f"internal widths must be in [1, {MAX_W}]"
     if model.input_dim > MAX_W or model.cond_dim > 128:
         return f"input_dim > {MAX_W} or cond_dim > 128"
     return None

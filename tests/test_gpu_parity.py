@@ -51,11 +51,44 @@ def test_auto_precision_picks_tensor_cores_when_supported():
     assert ddpm.model.engine().precision == "fp16x2" and ddpm.model.engine().tc is not None
     ddpm, _ = standin_model("attn", DEV)           # attention lowers to one accumulate stage per block
     assert ddpm.model.engine().precision == "fp16x2" and ddpm.model.engine().tc is not None
-    odd = D.UNet1D(input_dim=4, proj_dim=24, cond_dim=4, dims=(12, 6), is_attn=(False, False), n_blocks=1).to(DEV)
-    assert odd.engine().precision == "fp32"        # widths outside the tensor-core engine: exact-fp32 engine
-    odd.precision = "fp16x3"
+    wide = D.UNet1D(input_dim=200, proj_dim=32, cond_dim=4, dims=(16, 8), is_attn=(False, False), n_blocks=1).to(DEV)
+    assert wide.engine().precision == "fp32"       # rows wider than a TMEM region: exact-fp32 engine
+    wide.precision = "fp16x3"
     with pytest.raises(_lib.DiffsgError):
-        odd.engine()
+        wide.engine()
+
+
+@pytest.mark.parametrize("cfg", [dict(input_dim=4, proj_dim=24, cond_dim=5, dims=(12, 6), is_attn=(False, True), middle_attn=True, n_blocks=1),
+                                 dict(input_dim=7, proj_dim=40, cond_dim=3, dims=(40, 20, 10), is_attn=(False,) * 3, middle_attn=False, n_blocks=2),
+                                 dict(input_dim=3, proj_dim=100, cond_dim=9, dims=(72, 36), is_attn=(False,) * 2, middle_attn=False, n_blocks=1)],
+                         ids=lambda c: "x".join(map(str, (c["proj_dim"],) + tuple(c["dims"]))))
+def test_tensor_core_engine_odd_widths(cfg):
+    """Widths that are neither powers of two nor multiples of 16 on the tcgen05 engine: forward against the CPU
+    oracle, sampler against the exact-fp32 engine (same injected noise)."""
+    from oracle.standin import make_state_dict
+    model = D.UNet1D(**cfg)
+    sd = make_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=7)
+    model.load_state_dict(sd)
+    M = cfg["input_dim"]
+    ddpm = D.msr.DDPM(T, model, M, 10.0, 1.0 - D.generate_cosine_schedule(T), DEV, (1, M), {}).to(DEV)
+    B = 300
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, M, generator=g)
+    c = torch.rand(B, cfg["cond_dim"], generator=g)
+    ts = torch.randint(0, T, (1, B), generator=g)
+    m = (torch.rand(B, 1, generator=g) > 0.3).float()
+    want = O.unet_forward({"model." + k: v for k, v in sd.items()}, x, ts / T, c, m)
+    y_T, steps = O.draw_noise(B, (1, M), T, 3)
+    outs = {}
+    for precision in ("fp32", "fp16x3", "fp16x2"):
+        with_precision(ddpm, precision)
+        assert (ddpm.model.engine().tc is not None) == (precision != "fp32")
+        with torch.no_grad():
+            eps = ddpm.model(x.to(DEV), ts.to(DEV) / T, c.to(DEV), m.to(DEV))
+        assert rel_l2(eps.cpu(), want) < PRECISIONS[precision][0], precision
+        outs[precision] = ddpm.sample(c.to(DEV), 3.0, y_init=y_T.reshape(B, M), noise=torch.stack(steps).reshape(T - 2, B, M)).cpu()
+    assert rel_l2(outs["fp16x3"], outs["fp32"]) < 5e-4
+    assert rel_l2(outs["fp16x2"], outs["fp32"]) < 3e-2
 
 
 @pytest.mark.parametrize("precision", list(PRECISIONS))

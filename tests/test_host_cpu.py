@@ -255,4 +255,34 @@ def test_tc_engine_rejects_unsupported_topologies():
     wide = D.UNet1D(input_dim=4, proj_dim=256, cond_dim=4, dims=(64, 32), is_attn=(False, False), n_blocks=1)
     assert tc_packer.supported(wide) is not None
     odd = D.UNet1D(input_dim=4, proj_dim=24, cond_dim=4, dims=(12, 6), is_attn=(False, False), n_blocks=1)
-    assert "powers of two" in tc_packer.supported(odd)
+    assert tc_packer.supported(odd) is None          # any width <= 128 (padded to multiples of 16)
+    assert tc_packer.supported(D.UNet1D(input_dim=200, proj_dim=32, cond_dim=4, dims=(16, 8), is_attn=(False, False), n_blocks=1))
+
+
+ODD_NETS = [dict(input_dim=4, proj_dim=24, cond_dim=5, dims=(12, 6), is_attn=(False, True), middle_attn=True, n_blocks=1),
+            dict(input_dim=7, proj_dim=40, cond_dim=3, dims=(40, 20, 10), is_attn=(False,) * 3, middle_attn=False, n_blocks=2),
+            dict(input_dim=3, proj_dim=100, cond_dim=9, dims=(72, 36), is_attn=(False,) * 2, middle_attn=False, n_blocks=1)]
+
+
+@pytest.mark.parametrize("cfg", ODD_NETS, ids=lambda c: "x".join(map(str, (c["proj_dim"],) + tuple(c["dims"]))))
+def test_tc_program_odd_widths_match_oracle(cfg):
+    """Widths that are not multiples of 16 (nor powers of two): padded columns are exact zeros end to end."""
+    from diffsg_b200 import tc_packer
+    from oracle.standin import make_state_dict
+    from tc_interp import run_tc_program
+    model = D.UNet1D(**cfg)
+    sd = make_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=7)
+    model.load_state_dict(sd)
+    B = 33
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, cfg["input_dim"], generator=g)
+    c = torch.rand(B, cfg["cond_dim"], generator=g)
+    ts = torch.randint(0, T, (1, B), generator=g)
+    m = (torch.rand(B, 1, generator=g) > 0.3).float()
+    want = O.unet_forward({"model." + k: v for k, v in sd.items()}, x, ts / T, c, m)
+    for nterms, emulate, tol in ((3, False, 5e-6), (2, True, 1e-3)):
+        prog = tc_packer.lower_tc(model, nterms=nterms)
+        hi, lo, params = tc_packer.pack_tc_weights(prog, "cpu")
+        table = tc_packer.time_table_tc(model, prog, torch.arange(T) / T)
+        eps = run_tc_program(prog, hi, lo, params, table, x, ts.reshape(-1), c, m, emulate_fp16=emulate)
+        assert rel_l2(eps, want) < tol
