@@ -180,9 +180,10 @@ int diffsg_plan_set_tc_weights(diffsg_plan* plan, const void* w_hi_dev, const vo
 /* Select the engine used by diffsg_unet_forward / diffsg_sample. */
 int diffsg_plan_set_engine(diffsg_plan* plan, int32_t engine);
 
-/* Introspection: what = 0 engine, 1 tensor-core CTAs resident per SM (occupancy API), 2 its dynamic
- * shared memory per CTA (bytes), 3 its maximum grid, 4 nterms, 5 warps per CTA of the fp32 engine.
- * Returns -1 when not applicable. */
+/* Introspection: what = 0 engine, 1 tensor-core CTAs resident per SM, 2 its dynamic shared memory per CTA
+ * (bytes), 3 its maximum grid, 4 nterms, 5 warps per CTA of the fp32 engine, 6 / 7 the K columns per operand
+ * chunk and the TMEM columns per accumulator region this library was BUILT for (the program handed to
+ * diffsg_plan_attach_tc must be lowered for the same values).  Returns -1 when not applicable. */
 int diffsg_plan_query(const diffsg_plan* plan, int32_t what);
 
 /* Number of kernel launches issued by this library (process-wide) since the last reset
