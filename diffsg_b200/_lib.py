@@ -94,6 +94,8 @@ SYMBOLS = {
     "diffsg_lnsw_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "diffsg_lnsw_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P]),
     "diffsg_plan_query": (C.c_int, [_P, _I32]),
+    "diffsg_sample_steps": (C.c_int, [_P, C.POINTER(SampleArgs), _I32, _I32, _I32, _P]),
+    "diffsg_sample_renorm": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     "diffsg_debug_tc_gemm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, C.c_uint32, C.c_uint32, _I32, _P]),
 }
 

@@ -172,10 +172,10 @@ sample_simt_kernel(PlanDev P, SampleDev S) {
 
 // y = (y - mean) / sqrt(var_unbiased) with the scalars of one step (reference :136-137)
 __global__ void renorm_kernel(float* __restrict__ y, float* __restrict__ rec, const double* __restrict__ st,
-                              int64_t n) {
+                              int64_t n, int64_t n_stat) {
     const double s = st[0], q = st[1];
-    const double mean = s / (double)n;
-    const double var = (q - s * mean) / (double)(n - 1);
+    const double mean = s / (double)n_stat;
+    const double var = (q - s * mean) / (double)(n_stat - 1);
     const float mf = (float)mean, sd = sqrtf((float)var);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = (y[i] - mf) / sd;
@@ -383,20 +383,24 @@ int diffsg_unet_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, co
     return DIFFSG_OK;
 }
 
-int diffsg_sample(diffsg_plan* p, const diffsg_sample_args* a, void* stream) {
-    if (!p || !a || !a->cond_dev || !a->y_dev || !a->coef_host || !a->stat_ws_dev) { set_error("sample: null argument"); return DIFFSG_E_INVALID; }
-    if (p->engine != DIFFSG_ENGINE_TC && !p->have_weights) { set_error("sample before set_weights"); return DIFFSG_E_STATE; }
-    if (a->T <= 0 || a->T > 64) { set_error("T=%d outside [1,64]", a->T); return DIFFSG_E_UNSUPPORTED; }
-    if (a->norm_steps < 0) { set_error("norm_steps < 0"); return DIFFSG_E_INVALID; }
-    if (a->B <= 0) return DIFFSG_OK;
-    DIFFSG_CUDA_OK(cudaSetDevice(p->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p->engine == DIFFSG_ENGINE_TC) return tc::tc_sample(p, a, st);
-    if (a->T > p->tt_rows) { set_error("time table has %d rows, T=%d", p->tt_rows, a->T); return DIFFSG_E_INVALID; }
-    const int T = a->T;
-    const int norm_steps = a->norm_steps > T ? T : a->norm_steps;
+// y <- (y - mean) / sd with the two scalars of one step; shared by both engines and diffsg_sample_renorm
+static int launch_renorm(float* y, float* rec, const double* stats, int64_t n, int64_t n_stat, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int rb = (int)((n + 1023) / 1024);
+    if (rb > sms * 8) rb = sms * 8;
+    if (rb < 1) rb = 1;
+    renorm_kernel<<<rb, 256, 0, st>>>(y, rec, stats, n, n_stat);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+static int simt_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps, int hi, int lo, cudaStream_t st) {
     SampleDev S;
     memset(&S, 0, sizeof(S));
+    const int T = a->T;
     S.cond = a->cond_dev; S.y = a->y_dev; S.noise = a->noise_dev;
     S.rec_y = a->rec_y_dev; S.rec_eps = a->rec_eps_dev; S.stats = a->stat_ws_dev;
     S.B = a->B; S.T = T; S.norm_steps = norm_steps; S.omega = a->omega;
@@ -406,29 +410,60 @@ int diffsg_sample(diffsg_plan* p, const diffsg_sample_args* a, void* stream) {
         S.c_rs[i] = a->coef_host[T + i];
         S.c_noise[i] = a->coef_host[2 * T + i];
     }
-    DIFFSG_CUDA_OK(cudaMemsetAsync(a->stat_ws_dev, 0, sizeof(double) * 2 * T, st));
-    const int grid = grid_for(p, a->B);
-    const int64_t n = a->B * (int64_t)p->cfg.input_dim;
-    const int64_t plane = n;
-    int i = T - 1;
-    // phase A: steps whose output is re-normalised over the whole batch -> one launch each
-    for (int k = 0; k < norm_steps; ++k, --i) {
-        S.step_hi = S.step_lo = i;
-        sample_simt_kernel<<<grid, p->warps * 32, p->smem_bytes, st>>>(p->dev, S);
-        int rb = (int)((n + 1023) / 1024);
-        if (rb > p->sm_count * 8) rb = p->sm_count * 8;
-        renorm_kernel<<<rb, 256, 0, st>>>(a->y_dev, a->rec_y_dev ? a->rec_y_dev + (int64_t)(T - 1 - i) * plane : nullptr,
-                                         a->stat_ws_dev + 2 * i, n);
-        count_launch(2);
-    }
-    // phase B: remaining steps, rows are independent -> one persistent launch
-    if (i >= 0) {
-        S.step_hi = i; S.step_lo = 0;
-        sample_simt_kernel<<<grid, p->warps * 32, p->smem_bytes, st>>>(p->dev, S);
-        count_launch();
-    }
+    S.step_hi = hi; S.step_lo = lo;
+    sample_simt_kernel<<<grid_for(p, a->B), p->warps * 32, p->smem_bytes, st>>>(p->dev, S);
+    count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
     return DIFFSG_OK;
+}
+
+int diffsg_sample_steps(diffsg_plan* p, const diffsg_sample_args* a, int32_t step_hi, int32_t step_lo, int32_t renorm,
+                        void* stream) {
+    if (!p || !a || !a->cond_dev || !a->y_dev || !a->coef_host || !a->stat_ws_dev) { set_error("sample: null argument"); return DIFFSG_E_INVALID; }
+    if (p->engine != DIFFSG_ENGINE_TC && !p->have_weights) { set_error("sample before set_weights"); return DIFFSG_E_STATE; }
+    if (a->T <= 0 || a->T > 64) { set_error("T=%d outside [1,64]", a->T); return DIFFSG_E_UNSUPPORTED; }
+    if (a->norm_steps < 0) { set_error("norm_steps < 0"); return DIFFSG_E_INVALID; }
+    const int T = a->T;
+    if (step_lo < 0 || step_hi >= T || step_lo > step_hi) { set_error("sample_steps: steps %d..%d outside [0,%d)", step_hi, step_lo, T); return DIFFSG_E_INVALID; }
+    const int norm_steps = a->norm_steps > T ? T : a->norm_steps;
+    const int first_plain = T - 1 - norm_steps;          // highest step that is NOT re-normalised
+    if (!renorm && step_hi > first_plain && step_hi != step_lo) {
+        set_error("sample_steps: with renorm == 0 a re-normalised step (%d) must be the only step of the call", step_hi);
+        return DIFFSG_E_INVALID;
+    }
+    if (a->B <= 0) return DIFFSG_OK;
+    DIFFSG_CUDA_OK(cudaSetDevice(p->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_engine = p->engine == DIFFSG_ENGINE_TC;
+    if (tc_engine) { if (int rc = tc::tc_sample_check(p, a)) return rc; }
+    else if (T > p->tt_rows) { set_error("time table has %d rows, T=%d", p->tt_rows, T); return DIFFSG_E_INVALID; }
+    const int64_t n = a->B * (int64_t)p->cfg.input_dim;
+    int i = step_hi;
+    // re-normalised steps: the statistics are over the whole batch -> one launch each, grid-wide sums, then renorm
+    for (; i >= step_lo && i > first_plain; --i) {
+        DIFFSG_CUDA_OK(cudaMemsetAsync(a->stat_ws_dev + 2 * i, 0, sizeof(double) * 2, st));
+        if (int rc = tc_engine ? tc::tc_sample_launch(p, a, norm_steps, i, i, st) : simt_sample_launch(p, a, norm_steps, i, i, st)) return rc;
+        if (renorm) {
+            if (int rc = launch_renorm(a->y_dev, a->rec_y_dev ? a->rec_y_dev + (int64_t)(T - 1 - i) * n : nullptr,
+                                       a->stat_ws_dev + 2 * i, n, n, st)) return rc;
+        }
+    }
+    // remaining steps: rows are independent -> one persistent launch
+    if (i >= step_lo) {
+        if (int rc = tc_engine ? tc::tc_sample_launch(p, a, norm_steps, i, step_lo, st) : simt_sample_launch(p, a, norm_steps, i, step_lo, st)) return rc;
+    }
+    return DIFFSG_OK;
+}
+
+int diffsg_sample(diffsg_plan* p, const diffsg_sample_args* a, void* stream) {
+    if (!a) { set_error("sample: null argument"); return DIFFSG_E_INVALID; }
+    return diffsg_sample_steps(p, a, a->T - 1, 0, 1, stream);
+}
+
+int diffsg_sample_renorm(float* y, float* rec, const double* stats, int64_t n_local, int64_t n_stat, void* stream) {
+    if (!y || !stats || n_local < 0 || n_stat < 2 || n_stat < n_local) { set_error("sample_renorm: bad argument"); return DIFFSG_E_INVALID; }
+    if (n_local == 0) return DIFFSG_OK;
+    return launch_renorm(y, rec, stats, n_local, n_stat, (cudaStream_t)stream);
 }
 
 int diffsg_plan_attach_tc(diffsg_plan* p, const diffsg_tc_program* prog) { return tc::tc_attach(p, prog); }

@@ -29,7 +29,8 @@ int tc_set_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_
                    size_t n_params, const float* tt, int tt_rows);
 int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond, const float* mask,
                float* eps, int64_t B, cudaStream_t st);
-int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st);
+int tc_sample_check(diffsg_plan* p, const diffsg_sample_args* a);
+int tc_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps, int step_hi, int step_lo, cudaStream_t st);
 void tc_destroy(diffsg_plan* p);
 int tc_query(const diffsg_plan* p, int what);
 }  // namespace tc

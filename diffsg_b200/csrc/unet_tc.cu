@@ -353,23 +353,15 @@ int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float
     return tc_mark_launch(p, st);
 }
 
-__global__ void tc_renorm_kernel(float* __restrict__ y, float* __restrict__ rec, const double* __restrict__ stt, int64_t n) {
-    const double s = stt[0], q = stt[1];
-    const double mean = s / (double)n;
-    const double var = (q - s * mean) / (double)(n - 1);
-    const float mf = (float)mean, sd = sqrtf((float)var);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = (y[i] - mf) / sd;
-        y[i] = v;
-        if (rec) rec[i] = v;
-    }
+int tc_sample_check(diffsg_plan* p, const diffsg_sample_args* a) {
+    if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
+    if (a->T > p->tc->tt_rows) { set_error("tensor-core time table has %d rows, T=%d", p->tc->tt_rows, a->T); return DIFFSG_E_INVALID; }
+    return DIFFSG_OK;
 }
 
-int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
-    if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
+// one launch: reverse steps step_hi .. step_lo of every tile (a re-normalised step is launched alone)
+int tc_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps, int step_hi, int step_lo, cudaStream_t st) {
     const int T = a->T;
-    if (T > p->tc->tt_rows) { set_error("tensor-core time table has %d rows, T=%d", p->tc->tt_rows, T); return DIFFSG_E_INVALID; }
-    const int norm_steps = a->norm_steps > T ? T : a->norm_steps;
     if (int rc = tc_activate(p, st)) return rc;
     RunArgs R;
     memset(&R, 0, sizeof(R));
@@ -377,24 +369,9 @@ int tc_sample(diffsg_plan* p, const diffsg_sample_args* a, cudaStream_t st) {
     R.stats = a->stat_ws_dev; R.B = a->B; R.T = T; R.norm_steps = norm_steps; R.omega = a->omega;
     R.seed = a->philox_seed; R.offset = a->philox_offset;
     for (int i = 0; i < T; ++i) { R.c_eps[i] = a->coef_host[i]; R.c_rs[i] = a->coef_host[T + i]; R.c_noise[i] = a->coef_host[2 * T + i]; }
-    DIFFSG_CUDA_OK(cudaMemsetAsync(a->stat_ws_dev, 0, sizeof(double) * 2 * T, st));
-    const int grid = tc_grid(p, a->B);
-    const int64_t n = a->B * (int64_t)p->cfg.input_dim;
-    int i = T - 1;
-    for (int k = 0; k < norm_steps; ++k, --i) {
-        R.step_hi = R.step_lo = i;
-        tc_unet_kernel<true><<<grid, kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
-        int rb = (int)((n + 1023) / 1024);
-        if (rb > p->sm_count * 8) rb = p->sm_count * 8;
-        tc_renorm_kernel<<<rb, 256, 0, st>>>(a->y_dev, a->rec_y_dev ? a->rec_y_dev + (int64_t)(T - 1 - i) * n : nullptr,
-                                            a->stat_ws_dev + 2 * i, n);
-        count_launch(2);
-    }
-    if (i >= 0) {
-        R.step_hi = i; R.step_lo = 0;
-        tc_unet_kernel<true><<<grid, kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
-        count_launch();
-    }
+    R.step_hi = step_hi; R.step_lo = step_lo;
+    tc_unet_kernel<true><<<tc_grid(p, a->B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+    count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
     if (int rc = tc_mark_launch(p, st)) return rc;
 #ifdef DIFFSG_TC_TIMING

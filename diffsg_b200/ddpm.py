@@ -108,11 +108,14 @@ class DDPMBase(nn.Module):
         noise = torch.stack(steps).reshape(len(steps), B, M) if steps else torch.empty(0, B, M)
         return y_T.reshape(B, M), noise
 
-    def sample(self, cond, omega=1.0, *, y_init=None, noise=None):
+    def sample(self, cond, omega=1.0, *, y_init=None, noise=None, stats_group=None):
         """y_0 = reverse diffusion with classifier-free guidance (reference MSR.py:114-155).
 
         `y_init` [B, M] / `noise` [T-2, B, M] inject the random draws (parity mode); otherwise
-        they come from `self.noise_mode`.
+        they come from `self.noise_mode`.  `stats_group`: a torch.distributed process group whose ranks each
+        hold a row shard of ONE logical batch: the four re-normalised steps then use the statistics of the whole
+        batch (one 3-double all-reduce each), exactly as the un-sharded reference call would; default: each
+        call normalises over its own rows (the reference's per-call semantics).  A callable is accepted too.
         """
         dev = self.betas.device
         if dev.type != "cuda":
@@ -137,9 +140,17 @@ class DDPMBase(nn.Module):
             if self.record_denoise_path:
                 rec_y = torch.empty(T, B, M, dtype=torch.float32, device=dev)
                 rec_eps = torch.empty(T, B, M, dtype=torch.float32, device=dev)
+            reduce_fn = None
+            if callable(stats_group):
+                reduce_fn = stats_group
+            elif stats_group is not None:
+                import torch.distributed as dist
+                if dist.get_world_size(stats_group) > 1:
+                    reduce_fn = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=stats_group)
             self.model.engine().sample(cond, y, self.step_coefficients(), T, omega, noise=noise,
                                        seed=self.philox_seed, offset=self.philox_offset,
-                                       norm_steps=min(self.NORM_STEPS, T), rec_y=rec_y, rec_eps=rec_eps)
+                                       norm_steps=min(self.NORM_STEPS, T), rec_y=rec_y, rec_eps=rec_eps,
+                                       stats_reduce=reduce_fn)
             if noise is None:
                 self.philox_offset += B  # fresh stream for the next call
             if self.record_denoise_path:

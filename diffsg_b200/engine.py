@@ -188,15 +188,21 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ sampler
     def sample(self, cond, y_init, coef, T, omega, *, noise=None, seed=0, offset=0, norm_steps=4,
-               rec_y=None, rec_eps=None):
-        """In-place reverse diffusion on `y_init` ([B, M] fp32 CUDA); returns it."""
+               rec_y=None, rec_eps=None, stats_reduce=None):
+        """In-place reverse diffusion on `y_init` ([B, M] fp32 CUDA); returns it.
+
+        `stats_reduce(t)`: optional callable that sums the fp64 tensor t = [sum y, sum y^2, count] in place over
+        all shards of ONE logical batch (e.g. `dist.all_reduce`).  The re-normalised steps then use whole-batch
+        statistics — the reference's semantics for the un-sharded call — at the cost of one tiny collective per
+        re-normalised step; without it each shard normalises over its own rows."""
         _require_cuda(cond, y_init, noise, rec_y, rec_eps)
-        if y_init.shape[0] == 0:
+        if y_init.shape[0] == 0 and stats_reduce is None:
             return y_init
         self.refresh()
         table = self.step_table(T)
         self._bind(table)
         B = y_init.shape[0]
+        M = self.program.input_dim
         if self._stat_ws is None or self._stat_ws.numel() < 2 * T:
             self._stat_ws = torch.zeros(2 * max(T, 64), dtype=torch.float64, device=self.device)
         coef_arr = (C.c_float * (3 * T))(*[float(v) for v in coef])
@@ -208,7 +214,26 @@ class UNetEngine:
                                coef_host=C.cast(coef_arr, C.c_void_p), B=B, T=T, norm_steps=norm_steps,
                                omega=float(omega), pad_=0, philox_seed=int(seed) & (2**64 - 1),
                                philox_offset=int(offset) & (2**64 - 1))
-        _lib.check(self.lib.diffsg_sample(self.handle, C.byref(args), _lib.stream_ptr()), "diffsg_sample")
+        if stats_reduce is None:
+            _lib.check(self.lib.diffsg_sample(self.handle, C.byref(args), _lib.stream_ptr()), "diffsg_sample")
+            return y_init
+        # whole-batch statistics over several shards: step-wise through the same kernels
+        n_norm = min(norm_steps, T)
+        cnt = torch.tensor([0.0, 0.0, float(B * M)], dtype=torch.float64, device=self.device)
+        stats_reduce(cnt)
+        n_stat = int(round(float(cnt[2])))                  # element count of the logical batch (the one host sync)
+        for i in range(T - 1, T - 1 - n_norm, -1):
+            tot = torch.zeros(3, dtype=torch.float64, device=self.device)
+            if B > 0:
+                _lib.check(self.lib.diffsg_sample_steps(self.handle, C.byref(args), i, i, 0, _lib.stream_ptr()), "diffsg_sample_steps")
+                tot[:2] = self._stat_ws[2 * i:2 * i + 2]
+            stats_reduce(tot)
+            if B > 0:
+                plane = rec_y[T - 1 - i] if rec_y is not None else None
+                _lib.check(self.lib.diffsg_sample_renorm(y_init.data_ptr(), plane.data_ptr() if plane is not None else None,
+                                                         tot.data_ptr(), B * M, n_stat, _lib.stream_ptr()), "diffsg_sample_renorm")
+        if B > 0 and T - 1 - n_norm >= 0:
+            _lib.check(self.lib.diffsg_sample_steps(self.handle, C.byref(args), T - 1 - n_norm, 0, 1, _lib.stream_ptr()), "diffsg_sample_steps")
         return y_init
 
 

@@ -152,6 +152,23 @@ static_assert(sizeof(diffsg_op) == 48 && sizeof(diffsg_cfg) == 64 && sizeof(diff
 
 int diffsg_sample(diffsg_plan* plan, const diffsg_sample_args* args, void* stream);
 
+/* A slice of diffsg_sample, for callers that shard ONE batch over several GPUs and want the reference's
+ * whole-batch statistics in the re-normalised steps (the reference normalises over the batch of the call,
+ * classifier_free_MSR.py:136-137): runs reverse steps step_hi .. step_lo (inclusive, descending).
+ *   renorm != 0: re-normalised steps use this shard's own statistics (what diffsg_sample does);
+ *   renorm == 0: a re-normalised step only ACCUMULATES (sum y, sum y^2) of its un-normalised output into
+ *                stat_ws_dev[2*step .. 2*step+1] (zeroed by this call); it must be the only step of the call
+ *                (step_hi == step_lo).  The caller sums the two doubles over all ranks (NCCL all-reduce)
+ *                and calls diffsg_sample_renorm with the global element count.
+ * diffsg_sample == diffsg_sample_steps(T-1, 0, renorm = 1). */
+int diffsg_sample_steps(diffsg_plan* plan, const diffsg_sample_args* args, int32_t step_hi, int32_t step_lo,
+                        int32_t renorm, void* stream);
+/* y = (y - mean) / sqrt(var_unbiased) over n_local elements with mean / var from stats_dev = {sum y, sum y^2}
+ * taken over n_stat elements (n_stat = n_local for per-shard statistics); rec_y_plane_dev: NULL or the
+ * [B][M] record plane of that step, which receives the normalised values as well. */
+int diffsg_sample_renorm(float* y_dev, float* rec_y_plane_dev, const double* stats_dev, int64_t n_local,
+                         int64_t n_stat, void* stream);
+
 /* ---- tensor-core program (engine DIFFSG_ENGINE_TC) ------------------------------------
  * Second lowering of the same network for the tcgen05 engine (diffsg_b200/tc_packer.py):
  * stages = GEMM groups accumulating in TMEM, each followed by an epilogue micro-program.

@@ -550,6 +550,58 @@ def test_short_schedule_every_step_renormalised(name, precision):
     assert abs(float(y0.mean())) < 1e-4 and abs(float(y0.var()) - 1.0) < 1e-3
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+def test_sharded_sampling_with_whole_batch_statistics(precision):
+    """`sample(..., stats_group=...)`: two row shards of ONE batch (two plans driven from two threads, the
+    all-reduce emulated with a barrier) reproduce the un-sharded call, whose four re-normalised steps use the
+    statistics of the whole batch (reference MSR.py:136-137); without it the shards would normalise separately."""
+    import copy
+    import threading
+    ddpm, cfg = standin_model("nu_like", DEV)
+    with_precision(ddpm, precision)
+    M, Cd = cfg["input_dim"], cfg["cond_dim"]
+    B, cut = 700, 300                                   # ragged shards
+    g = torch.Generator().manual_seed(21)
+    cond = torch.rand(B, Cd, generator=g)
+    y_T = torch.randn(B, M, generator=g)
+    noise = torch.randn(T - 2, B, M, generator=g)
+    full = ddpm.sample(cond.to(DEV), 3.0, y_init=y_T, noise=noise).cpu()
+    sep = torch.cat([ddpm.sample(cond[s].to(DEV), 3.0, y_init=y_T[s], noise=noise[:, s]).cpu()
+                     for s in (slice(0, cut), slice(cut, B))])
+    assert rel_l2(sep, full) > 1e-3                      # per-shard statistics really are a different computation
+
+    shards = [slice(0, cut), slice(cut, B)]
+    barrier, slots, outs, errs = threading.Barrier(2), [None, None], [None, None], []
+
+    def make_reduce(rank):
+        def reduce(t):
+            torch.cuda.synchronize()
+            slots[rank] = t.clone()
+            barrier.wait()
+            total = slots[0] + slots[1]
+            barrier.wait()
+            t.copy_(total)
+        return reduce
+
+    def work(rank):
+        try:
+            torch.cuda.set_device(0)
+            m = copy.deepcopy(ddpm)
+            m.model.precision = precision
+            s = shards[rank]
+            outs[rank] = m.sample(cond[s].to(DEV), 3.0, y_init=y_T[s], noise=noise[:, s], stats_group=make_reduce(rank)).cpu()
+        except Exception as e:                           # pragma: no cover
+            errs.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in threads]
+    [t.join(timeout=120) for t in threads]
+    assert not errs, errs
+    got = torch.cat(outs)
+    assert rel_l2(got, full) < (1e-5 if precision == "fp32" else 1e-4)
+
+
 def test_degenerate_batches():
     ddpm, cfg = standin_model("nu_like", DEV)
     M, C = cfg["input_dim"], cfg["cond_dim"]
