@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=2048, help="rows per step of the CPU reference arm")
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of the in-run cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-stats", action="store_true",
+                    help="N > 1: treat the shards as ONE batch (whole-batch statistics, one 24-byte all-reduce per re-normalised step)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16x2", "fp16x3"])
     args = ap.parse_args()
 
@@ -191,6 +193,7 @@ def main():
     cond_host = torch.rand(B, Cd, generator=g).pin_memory()     # U(0,1) = min-max scaled gains
     cond = cond_host.to(dev, non_blocking=True)
     out_host = torch.empty(B, M).pin_memory()
+    stats_group = dist.group.WORLD if (args.global_stats and world > 1) else None
     engine = ddpm.model.engine()
     x_macs, c_macs = engine.program.gemm_macs()
     engine_name = {"fp32": "simt-fp32 (CUDA cores)", "fp16x2": "tcgen05 fp16x2 (A hi+lo, W fp16, fp32 accum)",
@@ -198,11 +201,11 @@ def main():
     f_alg = T * 2 * 2 * x_macs + 2 * c_macs                     # 45.51 MFLOP for 80c
 
     def step_resident():
-        return ddpm.sample(cond, OMEGA)
+        return ddpm.sample(cond, OMEGA, stats_group=stats_group)
 
     def step_e2e():
         c = cond_host.to(dev, non_blocking=True)
-        y = ddpm.sample(c, OMEGA)
+        y = ddpm.sample(c, OMEGA, stats_group=stats_group)
         out_host.copy_(y.reshape(B, M), non_blocking=True)
         return y
 
@@ -252,7 +255,8 @@ def main():
                 "config": {"workload": "BASELINE configs[1]: MSR 80c CFG-DDPM sampling (assumed UNet1D 80/128/80/(64,32,16,8)/2, "
                                        "init_weights N(0,0.01) seed 0), synthetic rand(B,80) conditions, rows sharded per GPU, no collective",
                            "rows_per_gpu": B, "T": T, "omega": OMEGA, "noise": "in-kernel Philox4x32-10",
-                           "batch_stats": "per shard (reference per-call semantics)",
+                           "batch_stats": "whole batch (all-reduce of 2 doubles per re-normalised step)" if stats_group is not None
+                           else "per shard (reference per-call semantics)",
                            "l2": f"inputs+state per step {2 * B * M * 4 / 2**20:.0f} MiB > 126 MB L2; no explicit flush",
                            "engine": engine_name, "engine_info": engine.info()},
                 "clocks": clk.summary(),
