@@ -267,7 +267,8 @@ def main():
                              "frac": ach_tf / peak_tf, "traffic": traffic,
                              "traffic_note": "bytes per step per GPU = ncu dram read+write per (row, reverse step) of the phase-B launch "
                                              "(profiles/r01_traffic_tc.json) x rows x T; not measured in this run",
-                             "kernel": "sample_*_kernel (all launches of one sample() call)",
+                             "kernel": ("sample_simt_kernel" if engine.precision == "fp32" else "tc_unet_kernel<true>")
+                                       + " (the 5 launches of one sample() call; 99.8 % of the step's GPU time, profiles/r01_ncu_launches_tc.csv)",
                              "flop_per_solution": f_alg, "peak_source": f"{pk_kind} bf16 sustained"}}
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v.detach().cpu().clone() for k, v in ddpm.state_dict().items()}
