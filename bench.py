@@ -203,11 +203,39 @@ def main():
     def step_resident():
         return ddpm.sample(cond, OMEGA, stats_group=stats_group)
 
-    def step_e2e():
-        c = cond_host.to(dev, non_blocking=True)
-        y = ddpm.sample(c, OMEGA, stats_group=stats_group)
-        out_host.copy_(y.reshape(B, M), non_blocking=True)
-        return y
+    copy_stream = torch.cuda.Stream(device=dev)
+    cond_bufs = [torch.empty(B, Cd, device=dev) for _ in range(2)]
+
+    def run_e2e(n):
+        """n steps through the public API with HOST buffers in and out, as a serving loop would run them: the
+        pinned-host -> device copy of step k+1 and the device -> host read of step k's result are issued on a copy
+        stream while step k / k+1 computes (double-buffered inputs).  Every byte still moves inside the timed region."""
+        cur = torch.cuda.current_stream(dev)
+        h2d = [torch.cuda.Event() for _ in range(n)]
+        done = [None, None]
+
+        def issue_h2d(k):
+            with torch.cuda.stream(copy_stream):
+                if done[k % 2] is not None:
+                    copy_stream.wait_event(done[k % 2])           # the step that read this buffer has finished
+                cond_bufs[k % 2].copy_(cond_host, non_blocking=True)
+                h2d[k].record(copy_stream)
+
+        copy_stream.wait_stream(cur)
+        issue_h2d(0)
+        for k in range(n):
+            if k + 1 < n:
+                issue_h2d(k + 1)
+            cur.wait_event(h2d[k])
+            y = ddpm.sample(cond_bufs[k % 2], OMEGA, stats_group=stats_group)
+            ev_done = torch.cuda.Event()
+            ev_done.record(cur)
+            done[k % 2] = ev_done
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_done)
+                out_host.copy_(y.reshape(B, M), non_blocking=True)
+                y.record_stream(copy_stream)
+        cur.wait_stream(copy_stream)
 
     for _ in range(args.warmup):
         step_resident()
@@ -223,12 +251,11 @@ def main():
     launches = _lib.launch_count()
     ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
     # end to end through the public API, host buffers in and out
-    step_e2e()
+    run_e2e(1)
     barrier()
     ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev2[0].record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     ev2[1].record()
     barrier()
     ms2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], device=dev, dtype=torch.float64)
