@@ -4,7 +4,7 @@
  * The reference (qiyu3816/DiffSG) is pure Python/PyTorch and has no FFI; its public
  * surface for this path is the nn.Module API.  Every entry point below names the
  * reference interface it replaces (paths relative to the reference repo root).  The
- * Python host side (diffsg_b200/*.py) keeps the reference's constructor arguments,
+ * Python host side (the modules under diffsg_b200/) keeps the reference's constructor arguments,
  * state_dict layout and sample()/forward() signatures and binds these symbols through
  * ctypes (INTEGRATION.md shows the stub).
  *
