@@ -26,8 +26,8 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
         return hi + (a - hi).half().float()
 
     def emit(vec, dp):
-        for k0 in range(0, dp, 64):
-            queue.append(split(vec[:, k0:min(dp, k0 + 64)].clone()))
+        for k0 in range(0, dp, T.CHUNK_K):
+            queue.append(split(vec[:, k0:min(dp, k0 + T.CHUNK_K)].clone()))
 
     def do_stats(dt, flags):
         if flags & T.STATS_RESET:
