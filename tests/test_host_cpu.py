@@ -2,6 +2,7 @@
 lowering + packing + hoisting), C-ABI library surface.  No GPU needed."""
 import ctypes
 import re
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -286,3 +287,20 @@ def test_tc_program_odd_widths_match_oracle(cfg):
         table = tc_packer.time_table_tc(model, prog, torch.arange(T) / T)
         eps = run_tc_program(prog, hi, lo, params, table, x, ts.reshape(-1), c, m, emulate_fp16=emulate)
         assert rel_l2(eps, want) < tol
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) prints ONE JSON line with the
+    contract's keys; it must run without a GPU."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-rows", "32"], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "solutions/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
