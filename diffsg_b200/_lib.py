@@ -17,21 +17,14 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libdiffsg_b200.so"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 SOURCES = ("diffsg.cu", "side_kernels.cu", "unet_tc.cu")
-# Build variant of the tensor-core engine (diffsg_b200/csrc/unet_tc.cuh): K columns per operand chunk, A-ring
-# depth, TMEM columns per accumulator region (= widest vector), co-resident CTAs per SM.  One variant per
-# build; DIFFSG_TC_VARIANT="chunk=32,aslots=3,region=64,ctas=3" overrides it for experiments.
+# Tensor-core engine geometry (diffsg_b200/csrc/unet_tc.cuh): K columns per operand chunk, TMEM columns per
+# accumulator region (= widest vector), co-resident CTAs per SM.
 TC_VARIANT = dict(chunk=64, aslots=2, region=128, ctas=2)
-for _kv in filter(None, os.environ.get("DIFFSG_TC_VARIANT", "").split(",")):
-    _k, _v = _kv.split("=")
-    if _k not in TC_VARIANT:
-        raise ValueError(f"DIFFSG_TC_VARIANT: unknown key {_k!r}")
-    TC_VARIANT[_k] = int(_v)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared",
-              f"-DDIFFSG_TC_CHUNK={TC_VARIANT['chunk']}", f"-DDIFFSG_TC_ASLOTS={TC_VARIANT['aslots']}",
-              f"-DDIFFSG_TC_REGION={TC_VARIANT['region']}", f"-DDIFFSG_TC_CTAS={TC_VARIANT['ctas']}")
+              "-Xcompiler", "-fPIC", "-shared")
+EXTRA_FLAGS = tuple(filter(None, os.environ.get("DIFFSG_NVCC_FLAGS", "").split()))   # experiments: -DDIFFSG_TC_TIMING ...
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OP_GEMM, OP_LNSW, OP_PUSH, OP_POP = 1, 2, 3, 4
 F_ACC, F_TIME, F_NOBIAS = 1, 2, 4
 BUF_COND, N_BUF = 4, 4
@@ -89,7 +82,8 @@ SYMBOLS = {
     "diffsg_decode_co": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "diffsg_cost_co": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "diffsg_plan_attach_tc": (C.c_int, [_P, C.POINTER(TcProgramC)]),
-    "diffsg_plan_set_tc_weights": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _I32]),
+    "diffsg_plan_set_tc_weights": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _I32, _P, _I32, _I64]),
+    "diffsg_plan_status": (C.c_int, [_P, C.POINTER(_I32), _I32, _P]),
     "diffsg_plan_set_engine": (C.c_int, [_P, _I32]),
     "diffsg_lnsw_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "diffsg_lnsw_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P]),
@@ -122,7 +116,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB_PATH
     srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(INCLUDE_DIR), *srcs, "-o", str(LIB_PATH)]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *EXTRA_FLAGS, "-I", str(INCLUDE_DIR), *srcs, "-o", str(LIB_PATH)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

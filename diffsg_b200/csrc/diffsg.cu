@@ -469,8 +469,13 @@ int diffsg_sample_renorm(float* y, float* rec, const double* stats, int64_t n_lo
 int diffsg_plan_attach_tc(diffsg_plan* p, const diffsg_tc_program* prog) { return tc::tc_attach(p, prog); }
 
 int diffsg_plan_set_tc_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_bytes, const float* params,
-                               size_t n_params, const float* tt, int32_t tt_rows) {
-    return tc::tc_set_weights(p, w_hi, w_lo, w_bytes, params, n_params, tt, tt_rows);
+                               size_t n_params, const float* tt, int32_t tt_rows, const void* tt_img, int32_t img_rows,
+                               int64_t img_stride) {
+    return tc::tc_set_weights(p, w_hi, w_lo, w_bytes, params, n_params, tt, tt_rows, tt_img, img_rows, img_stride);
+}
+
+int diffsg_plan_status(diffsg_plan* p, int32_t* flags, int32_t reset, void* stream) {
+    return tc::tc_status(p, flags, reset, (cudaStream_t)stream);
 }
 
 int diffsg_plan_set_engine(diffsg_plan* p, int32_t engine) {

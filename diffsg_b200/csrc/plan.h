@@ -26,7 +26,8 @@ namespace tc {
 // implemented in unet_tc.cu
 int tc_attach(diffsg_plan* p, const diffsg_tc_program* prog);
 int tc_set_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_bytes, const float* params,
-                   size_t n_params, const float* tt, int tt_rows);
+                   size_t n_params, const float* tt, int tt_rows, const void* tt_img, int img_rows, int64_t img_stride);
+int tc_status(diffsg_plan* p, int32_t* flags, int reset, cudaStream_t st);
 int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond, const float* mask,
                float* eps, int64_t B, cudaStream_t st);
 int tc_sample_check(diffsg_plan* p, const diffsg_sample_args* a);

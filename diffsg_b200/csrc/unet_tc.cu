@@ -165,10 +165,11 @@ struct TcHost {
     std::vector<Epi> epis;
     uint64_t serial = 0;
     float* d_scratch = nullptr;
+    int* d_status = nullptr;
     int grid_max = 0;
     int occupancy = 0;
     size_t smem_bytes = 0;
-    int tt_rows = 0;
+    int tt_rows = 0, img_rows = 0;
     bool have_weights = false;
 };
 
@@ -180,6 +181,7 @@ void tc_destroy(diffsg_plan* p) {
         if (g_resident[p->cfg.device & 63] == h->serial) g_resident[p->cfg.device & 63] = 0;
     }
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_status) cudaFree(h->d_status);
     delete h;
     p->tc = nullptr;
 }
@@ -200,17 +202,25 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     const Epi* ep = (const Epi*)g->epis;
     for (int i = 0; i < g->n_stages; ++i) {
         if (st[i].chunk_begin + st[i].n_chunks > g->n_chunks || st[i].epi_begin + st[i].n_epi > g->n_epi ||
-            st[i].n16 < 1 || st[i].n16 * 16 > kRegionCols || (st[i].pkg_f4 + st[i].tt_f4) * 4 > kPkgFloats) {
+            st[i].n16 < 1 || st[i].n16 * 16 > kRegionCols || st[i].pkg_f4 * 4 > kPkgFloats) {
             set_error("attach_tc: stage %d malformed", i); return DIFFSG_E_INVALID;
         }
     }
     for (int i = 0; i < g->n_chunks; ++i)
-        if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16) { set_error("attach_tc: chunk %d kw=%d", i, ch[i].kw); return DIFFSG_E_INVALID; }
+        if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16 || ((ch[i].flags & kChunkBias) && ch[i].kw != kBiasK) ||
+            ((ch[i].flags & kChunkTime) && !(ch[i].flags & kChunkBias))) {
+            set_error("attach_tc: chunk %d kw=%d flags=%d", i, ch[i].kw, ch[i].flags); return DIFFSG_E_INVALID;
+        }
+    for (int i = 0; i < g->n_stages; ++i) {      // the bias chunk must be the LAST chunk of its GEMM group (see unet_tc.cuh)
+        for (int c = st[i].chunk_begin; c + 1 < st[i].chunk_begin + st[i].n_chunks; ++c)
+            if (ch[c].flags & kChunkBias) { set_error("attach_tc: stage %d: bias chunk is not last", i); return DIFFSG_E_INVALID; }
+    }
     for (int i = 0; i < g->n_epi; ++i) {
         const Epi& e = ep[i];
         const bool skip = e.kind == OP_CATLN || e.kind == OP_RAW_S || ((e.misc >> 1) & kFPush);
+        const bool ln = e.kind == OP_LN || e.kind == OP_CATLN;
         if (e.kind < OP_LN || e.kind > OP_OUT || e.np * 8 > kRegionCols || (e.np & 1) || e.np == 0 || e.dt > e.np * 8 || e.dt == 0 ||
-            (skip && e.slot >= g->n_skip)) {
+            (skip && e.slot >= g->n_skip) || (ln && (e.off1 * 4 + e.np * 8 * (e.kind == OP_CATLN ? 4 : 2)) > kPkgFloats)) {
             set_error("attach_tc: epilogue op %d malformed", i); return DIFFSG_E_INVALID;
         }
     }
@@ -232,6 +242,7 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     }
     D.stash_off = (int)off; off += (size_t)D.Mp * kRows;
     D.cond_off = (int)off;  off += (size_t)D.Cp * kRows;      // 2 images x Cp x 128 fp16 = Cp*128 floats
+    D.stats_off = (int)off; off += (size_t)(g->n_skip > 0 ? g->n_skip : 1) * kRows * 4;   // (s1, s2, shift, -) per pushed row
     D.scratch_floats = (off + 31) & ~size_t(31);
     const int w_terms = g->nterms == 3 ? 2 : 1;
     h->smem_bytes = 128 + ((sizeof(SmemLayout) + 127) & ~size_t(127)) + (size_t)kWStages * w_terms * kWStageBytes;
@@ -250,6 +261,9 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     }
     DIFFSG_CUDA_OK(cudaMemset(h->d_scratch, 0, sizeof(float) * D.scratch_floats * p->sm_count * kCtasPerSm));
     D.scratch = h->d_scratch;
+    DIFFSG_CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
+    DIFFSG_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
+    D.status = h->d_status;
     DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -287,15 +301,33 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
 }
 
 int tc_set_weights(diffsg_plan* p, const void* w_hi, const void* w_lo, size_t w_bytes, const float* params,
-                   size_t n_params, const float* tt, int tt_rows) {
+                   size_t n_params, const float* tt, int tt_rows, const void* tt_img, int img_rows, int64_t img_stride) {
     if (!p || !p->tc) { set_error("set_tc_weights: no tensor-core program attached"); return DIFFSG_E_STATE; }
-    if (!w_hi || !params || !tt || tt_rows <= 0 || (p->tc->dev.nterms == 3 && !w_lo)) { set_error("set_tc_weights: null argument"); return DIFFSG_E_INVALID; }
-    if (((uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)params | (uintptr_t)tt) & 15) { set_error("set_tc_weights: blobs must be 16-byte aligned"); return DIFFSG_E_INVALID; }
+    if (!w_hi || !params || (p->tc->dev.nterms == 3 && !w_lo)) { set_error("set_tc_weights: null argument"); return DIFFSG_E_INVALID; }
+    if ((!tt || tt_rows <= 0) && (!tt_img || img_rows <= 0)) { set_error("set_tc_weights: neither a time table nor step images given"); return DIFFSG_E_INVALID; }
+    if (((uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)params | (uintptr_t)tt | (uintptr_t)tt_img | (uintptr_t)img_stride) & 15) {
+        set_error("set_tc_weights: blobs must be 16-byte aligned"); return DIFFSG_E_INVALID;
+    }
+    if (img_stride < 0 || img_stride > 0x7fffffff) { set_error("set_tc_weights: image stride"); return DIFFSG_E_INVALID; }
     (void)w_bytes; (void)n_params;
     TcDev& D = p->tc->dev;
-    D.w_hi = (const uint8_t*)w_hi; D.w_lo = (const uint8_t*)w_lo; D.params = params; D.tt = tt;
-    p->tc->tt_rows = tt_rows;
+    D.w_hi = (const uint8_t*)w_hi; D.w_lo = (const uint8_t*)w_lo; D.params = params;
+    D.tt = tt; D.tt_img = (const uint8_t*)tt_img; D.tt_img_stride = (int)img_stride;
+    p->tc->tt_rows = tt ? tt_rows : 0;
+    p->tc->img_rows = tt_img ? img_rows : 0;
     p->tc->have_weights = true;
+    return DIFFSG_OK;
+}
+
+// kStatus* bits raised by the kernels of this plan since the last reset.  Synchronises `st`.
+int tc_status(diffsg_plan* p, int32_t* flags, int reset, cudaStream_t st) {
+    if (!p || !p->tc || !flags) { set_error("plan_status: no tensor-core program attached"); return DIFFSG_E_STATE; }
+    DIFFSG_CUDA_OK(cudaSetDevice(p->cfg.device));
+    int h = 0;
+    DIFFSG_CUDA_OK(cudaMemcpyAsync(&h, p->tc->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (reset) DIFFSG_CUDA_OK(cudaMemsetAsync(p->tc->d_status, 0, sizeof(int), st));
+    DIFFSG_CUDA_OK(cudaStreamSynchronize(st));
+    *flags = h;
     return DIFFSG_OK;
 }
 
@@ -308,6 +340,7 @@ int tc_query(const diffsg_plan* p, int what) {
         case 4: return p->tc->dev.nterms;
         case 6: return kChunkK;
         case 7: return kRegionCols;
+        case 8: return (int)(p->tc->dev.scratch_floats * sizeof(float));
         default: return -1;
     }
 }
@@ -342,7 +375,7 @@ static int tc_grid(const diffsg_plan* p, int64_t B) {
 
 int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float* cond, const float* mask,
                float* eps, int64_t B, cudaStream_t st) {
-    if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
+    if (!p->tc || !p->tc->have_weights || !p->tc->tt_rows) { set_error("tensor-core engine selected but not initialised (forward needs the fp32 time table)"); return DIFFSG_E_STATE; }
     if (int rc = tc_activate(p, st)) return rc;
     RunArgs R;
     memset(&R, 0, sizeof(R));
@@ -355,7 +388,7 @@ int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float
 
 int tc_sample_check(diffsg_plan* p, const diffsg_sample_args* a) {
     if (!p->tc || !p->tc->have_weights) { set_error("tensor-core engine selected but not initialised"); return DIFFSG_E_STATE; }
-    if (a->T > p->tc->tt_rows) { set_error("tensor-core time table has %d rows, T=%d", p->tc->tt_rows, a->T); return DIFFSG_E_INVALID; }
+    if (a->T > p->tc->img_rows) { set_error("tensor-core step images cover %d steps, T=%d", p->tc->img_rows, a->T); return DIFFSG_E_INVALID; }
     return DIFFSG_OK;
 }
 
@@ -382,7 +415,7 @@ int tc_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps
         cudaStreamSynchronize(st);
         long long h[12];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[12] = {"acc_wait", "pkg_wait", "ln_pass1", "exchange", "ln_pass2", "a_empty_wait", "publish", "cond", "catln", "out", "total", "raw"};
+        const char* names[12] = {"acc_wait", "pkg_wait", "ln_pass1", "ln_pass2", "catln", "raw", "cond", "out", "total", "-", "-", "-"};
         fprintf(stderr, "[tc timing, cycles of thread 0 / CTA 0, previous launch]");
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
         fprintf(stderr, "\n");

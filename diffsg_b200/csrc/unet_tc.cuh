@@ -1,18 +1,22 @@
 // Tensor-core engine: one CTA carries a 128-row tile through the whole UNet1D stage program;
 // two CTAs are co-resident per SM (fp16x2) so one tile's MMAs overlap the other's epilogue.
 //
-//   warp 0        bulk-TMA producer: streams fp16 weight K-chunk images into the W ring and the
-//                 per-stage fp32 parameter package (bias / LayerNorm gamma, beta / time-bias slice)
-//                 into the package ring
-//   warp 1        MMA issuer: one thread issues tcgen05.mma (A, W from shared memory, fp32
-//                 accumulators in TMEM) and commits completion to mbarriers
-//   warps 2-5     epilogue / operand producers: thread == row == TMEM lane.  Every epilogue op STREAMS
-//                 its source (the TMEM accumulator, a skip vector, the input row) in groups of 16
-//                 columns: pass 1 accumulates the LayerNorm statistics, pass 2 re-reads the
-//                 accumulator, normalises, applies Swish in fp32, splits into fp16 (hi, lo) and writes
-//                 the next GEMM's A operand as core-matrix K-chunks.  Only one 16-column group lives
-//                 in registers, so the epilogue is a handful of small loops that stay in the
-//                 instruction cache (the unrolled row-in-registers version was instruction-fetch bound).
+//   warps 0-3     epilogue / operand producers: thread == row == TMEM lane, one warp per SM sub-partition.
+//                 Every epilogue op STREAMS its source (the TMEM accumulator, a skip vector, the input row)
+//                 in groups of 16 columns held as 8 packed f32x2 register pairs: pass 1 accumulates the
+//                 shifted LayerNorm moments, pass 2 re-reads the accumulator, normalises, applies Swish,
+//                 splits into fp16 (hi, lo) and writes the next GEMM's A operand as core-matrix K-chunks.
+//                 All per-element arithmetic is packed (FFMA2 / FADD2 / FMUL2); the only scalar ops are the
+//                 two MUFU of Swish, the fp16 unpack and the operand stores.
+//   warp 4        bulk-TMA producer: streams fp16 weight K-chunk images (and the bias chunk images: static
+//                 ones from the weight blob, the per-step time-bias ones from the step image table) into the
+//                 W ring, and the per-stage LayerNorm gamma / beta package into the package ring
+//   warp 5        MMA issuer: one thread issues tcgen05.mma (A, W from shared memory, fp32 accumulators in
+//                 TMEM) and commits completion to mbarriers
+//
+// Biases never touch the CUDA cores: every GEMM group ends with a K = 16 "bias chunk" whose A operand is a
+// constant tile of ones (columns 0..2) and whose W rows hold the bias as three fp16 terms (hi, mid, lo), so
+// the accumulator already contains `x = W a + b` when the epilogue reads it.
 //
 // Program format: diffsg_b200/tc_packer.py.  Reference semantics: ddpm_opt/UNetCF.py:83-95,
 // :318-356; sampler: ddpm_opt/classifier_free_MSR.py:124-137.
@@ -23,73 +27,35 @@
 namespace diffsg {
 namespace tc {
 
-// Build variant (diffsg_b200/_lib.py TC_VARIANT): K columns per operand chunk, A-ring depth, TMEM columns per
-// accumulator region and the number of co-resident CTAs (tiles) per SM the resources are budgeted for.
-#ifndef DIFFSG_TC_CHUNK
-#define DIFFSG_TC_CHUNK 64
-#endif
-#ifndef DIFFSG_TC_ASLOTS
-#define DIFFSG_TC_ASLOTS 2
-#endif
-#ifndef DIFFSG_TC_REGION
-#define DIFFSG_TC_REGION 128
-#endif
-#ifndef DIFFSG_TC_CTAS
-#define DIFFSG_TC_CTAS 2
-#endif
 constexpr int kRows = 128;
-constexpr int kChunkK = DIFFSG_TC_CHUNK;
-constexpr int kGroupsPerChunk = kChunkK / 16, kPiecesPerChunk = kChunkK / 8;
-constexpr int kSlotBytes = kRows * kChunkK * 2;      // one fp16 A chunk (16 KB at 64 columns)
-constexpr int kASlots = DIFFSG_TC_ASLOTS;
+constexpr int kChunkK = 64;                          // K columns per operand chunk
+constexpr int kSlotBytes = kRows * kChunkK * 2;      // one fp16 A chunk (16 KB)
+constexpr int kASlots = 2;
 constexpr int kWStages = 2;
-constexpr int kRegionCols = DIFFSG_TC_REGION;        // widest vector the engine carries
+constexpr int kRegionCols = 128;                     // widest vector the engine carries
 constexpr int kWStageBytes = kRegionCols * kChunkK * 2;   // one fp16 W chunk (N <= kRegionCols)
-static_assert(kChunkK == 32 || kChunkK == 64, "chunk width");
-static_assert(kRegionCols == 64 || kRegionCols == 128, "region width");
-#ifndef DIFFSG_TC_SETS
-#define DIFFSG_TC_SETS 1
-#endif
-// Epilogue warp sets: set s owns the 16-column groups g == s (mod kEpiSets) of every vector, so with
-// two sets eight warps (two per TMEM lane quarter) share one tile's epilogue.
-constexpr int kEpiSets = DIFFSG_TC_SETS;
-constexpr int kEpiThreads = 128 * kEpiSets;
-constexpr int kCtasPerSm = DIFFSG_TC_CTAS;
-// Register split (setmaxnreg): needed for > 2 CTAs per SM or two epilogue sets.  setmaxnreg is a WARPGROUP
-// instruction (4 aligned warps execute the same one), so the split build pads the producer side to a full
-// warpgroup: warps 0-3 = producers (TMA lane, MMA lane, two idle warps), epilogue from warp 4.
-#ifndef DIFFSG_TC_SPLITREGS
-#define DIFFSG_TC_SPLITREGS (kEpiSets == 2 || kCtasPerSm > 2)
-#endif
-constexpr bool kSplitRegs = DIFFSG_TC_SPLITREGS;
-constexpr int kEpiWarp0 = kSplitRegs ? 4 : 2;        // no split: warps 2..5 are the epilogue
-constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 192 (default) / 256 / 384
-// Launch budget L per thread: the register file is 4 x 16384 (one bank per scheduler), a scheduler hosts
-// ceil(CTAs x warps / 4) warps, L is that share rounded down to 8 (what ptxas derives from __launch_bounds__).
-// The producer warpgroup keeps kRegsProducer, the epilogue threads get everything that frees.
-constexpr int kWarpsPerScheduler = (kCtasPerSm * (kThreads / 32) + 3) / 4;
-constexpr int kRegsLaunch = (16384 / (kWarpsPerScheduler * 32)) / 8 * 8;
-constexpr int kRegsProducer = 24;
-constexpr int kRegsEpilogue = (kRegsLaunch + (kRegsLaunch - kRegsProducer) * (kEpiWarp0 * 32) / kEpiThreads) / 8 * 8;
-static_assert(!kSplitRegs || (kRegsProducer * kEpiWarp0 * 32 + kRegsEpilogue * kEpiThreads <= kRegsLaunch * kThreads && kRegsEpilogue <= 232),
-              "setmaxnreg split exceeds the CTA's register allocation");
+constexpr int kBiasK = 16;                           // K of a bias chunk (one MMA)
+constexpr int kOnesBytes = kRows * kBiasK * 2;       // the constant A tile of the bias chunks
+constexpr int kCtasPerSm = 2;
+constexpr int kEpiWarps = 4, kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = kEpiThreads + 64;           // + TMA warp + MMA warp
 constexpr int kTmemCols = 2 * kRegionCols;           // two accumulator regions
-constexpr int kMaxStages = 256, kMaxChunks = 512, kMaxEpi = 1024;   // program lives in __constant__ memory (16 KB)
-constexpr int kPkgFloats = 640, kPSlots = 2;
+constexpr int kMaxStages = 256, kMaxChunks = 640, kMaxEpi = 512;   // program lives in __constant__ memory
+constexpr int kPkgFloats = 512, kPSlots = 2;         // gamma | beta (x2 for a cat LayerNorm) of one stage
 
 // streaming epilogue ops (diffsg_b200/tc_packer.py)
 enum : int { OP_LN = 1, OP_CATLN, OP_RAW_T, OP_RAW_S, OP_RAW_IN, OP_OUT };
-constexpr int kChunkCond = 1;
+constexpr int kChunkCond = 1, kChunkBias = 2, kChunkTime = 4;
 constexpr int kFTime = 1, kFCond = 2, kFPush = 4, kFDefer = 8;
+constexpr int kStatusOverflow = 1;                   // a raw fp16 operand exceeded the fp16 range
 
-struct __align__(8) Epi { uint8_t kind, np, dt, misc, slot, off0, off1, off2; };   // misc: region | flags << 1
+struct __align__(8) Epi { uint8_t kind, np, dt, misc, slot, off1; uint16_t tt_src4; };   // misc: region | flags << 1
 struct __align__(8) Chunk { uint16_t kw, flags; uint32_t w_off16; };
 struct __align__(16) Stage {
     uint16_t chunk_begin, epi_begin;
-    uint8_t n_chunks, n_epi, n16, bits;          // bits: region | accumulate << 1 | has_gemm << 2 | has_time << 3
+    uint8_t n_chunks, n_epi, n16, bits;          // bits: region | accumulate << 1 | has_gemm << 2
     uint32_t pkg_off4;
-    uint16_t tt_src4;
-    uint8_t pkg_f4, tt_f4;
+    uint16_t pkg_f4, pad_;
 };
 static_assert(sizeof(Epi) == 8 && sizeof(Chunk) == 8 && sizeof(Stage) == 16, "program record layout");
 
@@ -101,21 +67,24 @@ __constant__ Epi c_epis[kMaxEpi];
 struct TcDev {
     int n_stages, n_chunks, n_epi;
     const uint8_t* w_hi; const uint8_t* w_lo;     // fp16 weight images (lo: nterms == 3 only)
-    const float* params; const float* tt;
-    int tt_stride, nterms;
+    const float* params;                           // LayerNorm gamma / beta packages
+    const float* tt;                               // fp32 time table [rows][tt_stride] (forward mode)
+    const uint8_t* tt_img;                         // fp16 bias-chunk images of the time table, one row per step
+    int tt_stride, tt_img_stride, nterms;          // tt_img_stride in bytes
     int M, Mp, C, Cp;
     long long* debug;
-    float* scratch;                                 // per CTA: skip stack + eps stash + cond image
-    size_t scratch_floats;                          // per CTA
-    int skip_off[kMaxSkip];                         // float offset of each skip slot inside the CTA scratch
-    int stash_off, cond_off;                        // float offsets (cond image: hi then lo, fp16)
+    int* status;                                   // kStatus* bits (atomicOr)
+    float* scratch;                                // per CTA: skip stack + eps stash + cond image + skip moments
+    size_t scratch_floats;                         // per CTA
+    int skip_off[kMaxSkip];                        // float offset of each skip slot inside the CTA scratch
+    int stash_off, cond_off, stats_off;            // float offsets (cond image: hi then lo, fp16)
 };
 
 struct SmemLayout {
     uint8_t a_hi[kASlots][kSlotBytes];
     uint8_t a_lo[kASlots][kSlotBytes];
+    uint8_t ones[kOnesBytes];
     float pkg[kPSlots][kPkgFloats];
-    float2 xch[2][kEpiSets == 2 ? 256 : 1];         // per-row moment exchange between the two sets
     uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], p_full[kPSlots],
         p_empty[kPSlots], acc_full;
     uint32_t tmem_base, pad_;
@@ -135,32 +104,60 @@ struct RunArgs {
     float c_eps[64], c_rs[64], c_noise[64];
 };
 
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (relative error ~3e-7; correct limits at +-inf)
-__device__ __forceinline__ float swish_f(float x) {
-    return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
-}
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer)); }
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue)); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+// ------------------------------------------------------------------------------------------ packed fp32
+typedef unsigned long long f2;      // two fp32 in one 64-bit register pair (FFMA2 / FADD2 / FMUL2 operands)
+__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2 pku(uint32_t a, uint32_t b) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// (lo, hi) -> packed fp16x2, round to nearest, saturating at +-65504 instead of producing inf
+__device__ __forceinline__ uint32_t cvt_h2(float lo, float hi) {
     uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    return __uint_as_float(r);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
-__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+__device__ __forceinline__ f2 h2_to_f2(uint32_t h) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    return pk(f.x, f.y);
+}
+// v (two fp32) -> fp16 hi pair and fp16 residual pair: v ~= hi + lo to 22 significant bits
+__device__ __forceinline__ void split2(f2 v, uint32_t& hi, uint32_t& lo) {
+    float a, b;
+    upk(v, a, b);
+    hi = cvt_h2(a, b);
+    upk(sub2(v, h2_to_f2(hi)), a, b);
+    lo = cvt_h2(a, b);
+}
+// x * sigmoid(x), two lanes: one MUFU.EX2 and one MUFU.RCP per lane (relative error ~3e-7)
+__device__ __forceinline__ f2 swish2(f2 u) {
+    float e0, e1;
+    upk(mul2(u, pk(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
+    upk(add2(pk(ex2_approx(e0), ex2_approx(e1)), pk(1.0f, 1.0f)), e0, e1);
+    return mul2(u, pk(rcp_approx(e0), rcp_approx(e1)));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+
+// ------------------------------------------------------------------------------------------ TMEM
+// 16 consecutive columns of this thread's lane; results are valid after tmem_wait16 on the same registers
+// (the wait takes them as in/out operands so no consumer can be scheduled ahead of it).
+__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 }
 
 #ifdef DIFFSG_TC_TIMING
@@ -170,235 +167,207 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
 #define TCT_BEGIN(v)
 #define TCT_END(v, slot)
 #endif
+
 // Per-thread epilogue context
 struct EpiCtx {
 #ifdef DIFFSG_TC_TIMING
-    long long tacc[12];   // 0 acc wait, 1 pkg wait, 2 LN pass 1, 3 exchange, 4 LN pass 2 (incl 5, 6), 5 a_empty wait, 6 publish, 7 cond, 8 catln, 9 out, 10 total, 11 raw ops
+    long long tacc[12];   // 0 acc wait, 1 pkg wait, 2 LN pass 1, 3 LN pass 2, 4 cat-LN, 5 raw ops, 6 cond, 7 out, 8 total
 #endif
-    int row, set, et;
-    uint32_t xpar;          // parity of the moment-exchange buffer
+    int row, lane;
     uint32_t tmem_row;      // TMEM address of this thread's lane, column 0
     uint32_t aseq;          // A-ring sequence number (chunks published so far by the tile)
+    uint32_t fresh;         // chunks published since the last accumulator wait (the first kASlots need no slot wait)
+    uint32_t a_row;         // byte offset of this row inside an 8-row core-matrix group: (row & 7) * 16
+    uint32_t a_hi0;         // shared-memory address of a_hi[0]
+    float amax;             // largest |raw operand| seen (fp16 range check)
     float* scr;             // this CTA's global scratch
     int64_t grow;           // global row
     bool valid;
 };
 
-// ---- A-operand ring (producer side): one vector of `np` 8-column pieces -> ceil(np / 8) K-chunks.
-// Group g (pieces 2g, 2g+1) is written by set g % kEpiSets; EVERY epilogue thread arrives once per
-// chunk (after waiting for the slot), whether or not it wrote into it.
+// ---- A-operand ring (producer side): one vector of `np` 8-column pieces -> ceil(np / 8) K-chunks of up to four
+// 16-column groups.  Slot-free wait: every MMA issued before the last accumulator wait has completed, so the first
+// kASlots chunks published after it find their slot free; later ones wait for the MMA that read the slot.
 struct Emitter {
-    uint32_t seq0;
+    uint32_t seq0, base;
     int np, ng;
     bool defer;
 };
 __device__ __forceinline__ void emit_begin(Emitter& em, const EpiCtx& E, int np, bool defer) {
-    em.seq0 = E.aseq; em.np = np; em.ng = np >> 1; em.defer = defer;
+    em.seq0 = E.aseq; em.np = np; em.ng = np >> 1; em.defer = defer; em.base = 0;
 }
-#ifdef DIFFSG_TC_TIMING
-#define emit_wait_slot(S, sq) { TCT_BEGIN(_tw); mbar_wait(&(S).a_empty[(sq) % kASlots], ((((sq)) / kASlots) & 1) ^ 1); TCT_END(_tw, 5); }
-#define emit_publish(S, sq) { TCT_BEGIN(_tp); fence_proxy_async_smem(); tcgen05_fence_before(); mbar_arrive(&(S).a_full[(sq) % kASlots]); TCT_END(_tp, 6); }
-#else
-__device__ __forceinline__ void emit_wait_slot(SmemLayout& S, uint32_t sq) {
-    mbar_wait(&S.a_empty[sq % kASlots], ((sq / kASlots) & 1) ^ 1);
-}
-__device__ __forceinline__ void emit_publish(SmemLayout& S, uint32_t sq) {
+__device__ __forceinline__ void emit_publish(SmemLayout& S, const EpiCtx& E, uint32_t sq) {
     fence_proxy_async_smem();
     tcgen05_fence_before();
-    mbar_arrive(&S.a_full[sq % kASlots]);
+    __syncwarp();
+    if (E.lane == 0) mbar_arrive(&S.a_full[sq % kASlots]);
 }
-#endif
-// first / last group of chunk c owned by set `set` (first > last: none)
-__device__ __forceinline__ void my_groups(const Emitter& em, int c, int set, int& first, int& last) {
-    const int lo = kGroupsPerChunk * c, hi = min(kGroupsPerChunk * c + kGroupsPerChunk - 1, em.ng - 1);
-    first = lo + ((set - lo) & (kEpiSets - 1));
-    last = hi - ((hi - set) & (kEpiSets - 1));
+// shared-memory address (a_hi image) where group g of the vector goes; opens the chunk when g is its first group
+__device__ __forceinline__ uint32_t emit_addr(SmemLayout& S, EpiCtx& E, Emitter& em, int g) {
+    if ((g & 3) == 0) {
+        const int c = g >> 2;
+        const uint32_t sq = em.seq0 + c, sl = sq % kASlots;
+        if (E.fresh >= kASlots) mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
+        ++E.fresh;
+        const int cnt = min(8, em.np - 8 * c);                      // 8-column pieces in chunk c
+        em.base = E.a_hi0 + sl * kSlotBytes + (uint32_t)(E.row >> 3) * (uint32_t)(cnt * 128) + E.a_row;
+    }
+    return em.base + (g & 3) * 256;
 }
-__device__ __forceinline__ void emit_group(SmemLayout& S, EpiCtx& E, const Emitter& em, int g, const float (&x)[16]) {
-    const int c = g / kGroupsPerChunk;
-    const uint32_t sq = em.seq0 + c;
-    const uint32_t sl = sq % kASlots;
-    int first, last;
-    my_groups(em, c, E.set, first, last);
-    if (g == first) emit_wait_slot(S, sq);
-    const int cnt = min(kPiecesPerChunk, em.np - kPiecesPerChunk * c);         // pieces in chunk c
-    const uint32_t off = (uint32_t)(E.row >> 3) * (cnt * 128) + ((g % kGroupsPerChunk) * 2) * 128 + (E.row & 7) * 16;
-    uint4 hi, lo;
-    split_pack8(*reinterpret_cast<const float(*)[8]>(&x[0]), hi, lo);
-    *reinterpret_cast<uint4*>(S.a_hi[sl] + off) = hi;
-    *reinterpret_cast<uint4*>(S.a_lo[sl] + off) = lo;
-    split_pack8(*reinterpret_cast<const float(*)[8]>(&x[8]), hi, lo);
-    *reinterpret_cast<uint4*>(S.a_hi[sl] + off + 128) = hi;
-    *reinterpret_cast<uint4*>(S.a_lo[sl] + off + 128) = lo;
-    if (!em.defer && g == last) emit_publish(S, sq);
+__device__ __forceinline__ void emit_done(SmemLayout& S, const EpiCtx& E, const Emitter& em, int g) {
+    if (!em.defer && ((g & 3) == 3 || g == em.ng - 1)) emit_publish(S, E, em.seq0 + (g >> 2));
 }
 __device__ __forceinline__ void emit_end(SmemLayout& S, EpiCtx& E, const Emitter& em) {
-    const int nch = (em.np + kPiecesPerChunk - 1) / kPiecesPerChunk;
-    for (int c = 0; c < nch; ++c) {
-        int first, last;
-        my_groups(em, c, E.set, first, last);
-        const bool mine = first <= last;
-        if (!mine) emit_wait_slot(S, em.seq0 + c);          // no group of this chunk is mine: still take part
-        if (!mine || em.defer) emit_publish(S, em.seq0 + c);
-    }
+    const int nch = (em.np + 7) >> 3;
+    if (em.defer)
+        for (int c = 0; c < nch; ++c) emit_publish(S, E, em.seq0 + c);
     E.aseq += nch;
 }
+constexpr uint32_t kLoOff = kASlots * kSlotBytes;     // a_lo[s] = a_hi[s] + kLoOff
 
-// ---- group sources --------------------------------------------------------------------------
-// accumulator columns [16g, 16g+16) of `region` + bias (bias: shared-memory package, or the row's
-// time-table slice in global memory for forward mode)
-__device__ __forceinline__ void load_group_tmem(float (&x)[16], uint32_t ta, const float* bias) {
-    tmem_ld16(ta, x);
-    float4 b[4];
+// one group: raw values -> fp16 (hi, lo) operand pieces
+__device__ __forceinline__ void store_split(uint32_t addr, const f2 (&v)[8]) {
+    uint32_t h[8], l[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(bias + q * 4);
-    tmem_ld_wait();
+    for (int j = 0; j < 8; ++j) split2(v[j], h[j], l[j]);
+    sts128(addr, h[0], h[1], h[2], h[3]);
+    sts128(addr + 128, h[4], h[5], h[6], h[7]);
+    sts128(addr + kLoOff, l[0], l[1], l[2], l[3]);
+    sts128(addr + kLoOff + 128, l[4], l[5], l[6], l[7]);
+}
+// t = x * sc + sh for one group straight out of the TMEM registers (which are then free for the next load)
+__device__ __forceinline__ void normalise16(const uint32_t (&r)[16], f2 sc, f2 sh, f2 (&t)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = fma2(pku(r[2 * j], r[2 * j + 1]), sc, sh);
+}
+// one group: swish(t * gamma + beta) -> operand pieces.  Pad columns have gamma = beta = 0 -> exact zeros.
+__device__ __forceinline__ void store_ln_swish(uint32_t addr, const f2 (&t)[8], const float4* gamma, const float4* beta) {
+    f2 v[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        x[q * 4 + 0] += b[q].x; x[q * 4 + 1] += b[q].y; x[q * 4 + 2] += b[q].z; x[q * 4 + 3] += b[q].w;
+        const float4 g = gamma[q], b = beta[q];
+        v[2 * q] = swish2(fma2(t[2 * q], pk(g.x, g.y), pk(b.x, b.y)));
+        v[2 * q + 1] = swish2(fma2(t[2 * q + 1], pk(g.z, g.w), pk(b.z, b.w)));
+    }
+    store_split(addr, v);
+}
+// shifted one-pass moments of one group: d = x - shift (computed straight out of the TMEM registers, which are
+// then free for the next load), s1 += d, s2 += d^2 (two packed accumulators each)
+__device__ __forceinline__ void centre16(const uint32_t (&r)[16], f2 shift, f2 (&d)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = sub2(pku(r[2 * j], r[2 * j + 1]), shift);
+}
+__device__ __forceinline__ void moments16(const f2 (&d)[8], f2 (&s1)[2], f2 (&s2)[2]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s1[j & 1] = add2(s1[j & 1], d[j]);
+        s2[j & 1] = fma2(d[j], d[j], s2[j & 1]);
     }
 }
-// Software-pipelined walk over the accumulator: the raw TMEM load of group g+1 is in flight while
-// group g is processed.  `raw` holds the prefetched group (no bias yet).
-struct TmemWalk {
-    float raw[16];
-};
-__device__ __forceinline__ void walk_begin(TmemWalk& w, uint32_t ta) {
-    tmem_ld16(ta, w.raw);
-    tmem_ld_wait();
+__device__ __forceinline__ void pack16(const uint32_t (&r)[16], f2 (&x)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = pku(r[2 * j], r[2 * j + 1]);
 }
-// x = prefetched group + bias; start fetching the next group (if any); caller must call walk_sync()
-// before the next walk_next()
-__device__ __forceinline__ void walk_next(TmemWalk& w, float (&x)[16], const float* bias, bool more, uint32_t ta_next) {
+__device__ __forceinline__ void fold_moments(const f2 (&s1)[2], const f2 (&s2)[2], float& a, float& q) {
+    float a0, a1, q0, q1;
+    upk(add2(s1[0], s1[1]), a0, a1);
+    upk(add2(s2[0], s2[1]), q0, q1);
+    a = a0 + a1;
+    q = q0 + q1;
+}
+__device__ __forceinline__ void track_amax(EpiCtx& E, const uint32_t (&r)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) E.amax = fmaxf(E.amax, fabsf(__uint_as_float(r[j])));
+}
+__device__ __forceinline__ void store_group_skip(const uint32_t (&r)[16], uint4* sk) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sk[q * kRows] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+}
+// forward mode only: add this row's slice of the fp32 time table (lin1.bias + time embedding) to a group
+__device__ __forceinline__ void add_time16(uint32_t (&r)[16], const float* tt) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
-        x[q * 4 + 0] = w.raw[q * 4 + 0] + b.x; x[q * 4 + 1] = w.raw[q * 4 + 1] + b.y;
-        x[q * 4 + 2] = w.raw[q * 4 + 2] + b.z; x[q * 4 + 3] = w.raw[q * 4 + 3] + b.w;
+        const float4 b = *reinterpret_cast<const float4*>(tt + q * 4);
+        r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + b.x);
+        r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + b.y);
+        r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + b.z);
+        r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + b.w);
     }
-    if (more) tmem_ld16(ta_next, w.raw);
-}
-__device__ __forceinline__ void walk_sync() { tmem_ld_wait(); }
-__device__ __forceinline__ void load_group_skip(float (&x)[16], const float4* sk) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 t = sk[q * kRows];
-        x[q * 4 + 0] = t.x; x[q * 4 + 1] = t.y; x[q * 4 + 2] = t.z; x[q * 4 + 3] = t.w;
-    }
-}
-__device__ __forceinline__ void store_group_skip(const float (&x)[16], float4* sk) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) sk[q * kRows] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
 }
 
-// Walk a skip vector (global scratch slab, L2 / HBM resident, ~1 us latency) in batches of two groups:
-// all 8 16-byte loads of a batch are issued back to back, so the latency is paid once per batch
-// instead of once per group.  (Loads are NOT kept in flight across body(): the operand-publish fence
-// inside emit_group would wait for them.)
+// Walk a skip vector (global scratch slab, L2 / HBM resident) in batches of two groups: all 8 16-byte loads of a
+// batch are issued back to back, so the latency is paid once per batch.  (Loads are NOT kept in flight across
+// body(): the operand-publish fence would wait for them.)
 template <typename F>
-__device__ __forceinline__ void skip_walk2(const float4* sk, int g0, int G, int ng, F body) {
-    for (int gb = g0; gb < ng; gb += 2 * G) {
-        const bool two = gb + G < ng;
-        const float4* p0 = sk + (size_t)gb * 4 * kRows;
-        const float4* p1 = sk + (size_t)(two ? gb + G : gb) * 4 * kRows;
-        const float4 a0 = p0[0], a1 = p0[kRows], a2 = p0[2 * kRows], a3 = p0[3 * kRows];
-        const float4 c0 = p1[0], c1 = p1[kRows], c2 = p1[2 * kRows], c3 = p1[3 * kRows];
-        float x[16];
-        x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
-        x[8] = a2.x; x[9] = a2.y; x[10] = a2.z; x[11] = a2.w; x[12] = a3.x; x[13] = a3.y; x[14] = a3.z; x[15] = a3.w;
-        body(gb, x);
+__device__ __forceinline__ void skip_walk2(const uint4* sk, int ng, F body) {
+    for (int gb = 0; gb < ng; gb += 2) {
+        const bool two = gb + 1 < ng;
+        const uint4* p0 = sk + (size_t)gb * 4 * kRows;
+        const uint4* p1 = p0 + (two ? 4 * kRows : 0);
+        const uint4 a0 = p0[0], a1 = p0[kRows], a2 = p0[2 * kRows], a3 = p0[3 * kRows];
+        const uint4 c0 = p1[0], c1 = p1[kRows], c2 = p1[2 * kRows], c3 = p1[3 * kRows];
+        {
+            const uint32_t r[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+            body(gb, r);
+        }
         if (two) {
-            x[0] = c0.x; x[1] = c0.y; x[2] = c0.z; x[3] = c0.w; x[4] = c1.x; x[5] = c1.y; x[6] = c1.z; x[7] = c1.w;
-            x[8] = c2.x; x[9] = c2.y; x[10] = c2.z; x[11] = c2.w; x[12] = c3.x; x[13] = c3.y; x[14] = c3.z; x[15] = c3.w;
-            body(gb + G, x);
+            const uint32_t r[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+            body(gb + 1, r);
         }
     }
 }
 
-// shifted one-pass moments: s1 += (x - shift), s2 += (x - shift)^2 over the first `nval` columns
-__device__ __forceinline__ void moments_group(const float (&x)[16], int nval, float shift, float& s1, float& s2) {
-    float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
-    if (nval >= 16) {
+// Shifted moments of a TMEM vector (pass 1 of a LayerNorm); optionally spills the vector to a skip slot.
+// Returns shift, s1 = sum(x - shift), s2 = sum((x - shift)^2) over the first dt columns.
+template <bool kSampler>
+__device__ __forceinline__ void tmem_moments(uint32_t ta, int ng, int dt, const float* tt_row, uint4* sk_push,
+                                             float& shift, float& s1o, float& s2o) {
+    uint32_t r[16];
+    f2 x[8], s1[2] = {0ull, 0ull}, s2[2] = {0ull, 0ull}, sh2 = 0ull;
+    shift = 0.f;
+    tmem_ld16u(ta, r);
+    for (int g = 0; g < ng; ++g) {
+        tmem_wait16(r);
+        if (!kSampler && tt_row) add_time16(r, tt_row + g * 16);
+        if (g == 0) { shift = __uint_as_float(r[0]); sh2 = pk(shift, shift); }
+        if (sk_push) store_group_skip(r, sk_push + (size_t)g * 4 * kRows);
+        if (g == ng - 1 && dt < ng * 16) {           // pad columns (exact zeros) must not enter the moments
+            const int nval = dt - g * 16;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            const float d0 = x[j] - shift, d1 = x[j + 1] - shift;
-            a0 += d0; a1 += d1;
-            q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+            for (int j = 0; j < 16; ++j) if (j >= nval) r[j] = __float_as_uint(shift);
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float d = j < nval ? x[j] - shift : 0.f;
-            a0 += d;
-            q0 = fmaf(d, d, q0);
-        }
+        centre16(r, sh2, x);
+        if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
+        moments16(x, s1, s2);
     }
-    s1 += a0 + a1;
-    s2 += q0 + q1;
-}
-// x <- swish((x * a_scale + a_shift) * gamma + beta), zero beyond nval
-__device__ __forceinline__ void ln_swish_group(float (&x)[16], int nval, float a_scale, float a_shift,
-                                               const float* gamma, const float* beta) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 g = *reinterpret_cast<const float4*>(gamma + q * 4);
-        const float4 b = *reinterpret_cast<const float4*>(beta + q * 4);
-        x[q * 4 + 0] = swish_f(fmaf(fmaf(x[q * 4 + 0], a_scale, a_shift), g.x, b.x));
-        x[q * 4 + 1] = swish_f(fmaf(fmaf(x[q * 4 + 1], a_scale, a_shift), g.y, b.y));
-        x[q * 4 + 2] = swish_f(fmaf(fmaf(x[q * 4 + 2], a_scale, a_shift), g.z, b.z));
-        x[q * 4 + 3] = swish_f(fmaf(fmaf(x[q * 4 + 3], a_scale, a_shift), g.w, b.w));
-    }
-    if (nval < 16) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j >= nval) x[j] = 0.f;
-    }
-}
-__device__ __forceinline__ void finish_moments(float s1, float s2, float shift, float n, float& a_scale, float& a_shift) {
-    const float md = s1 / n;
-    const float var = fmaxf(s2 / n - md * md, 0.f);
-    const float rstd = rsqrtf(var + kLnEps);
-    a_scale = rstd;
-    a_shift = -(shift + md) * rstd;
-}
-
-// sum the partial moments of the two sets of a row
-__device__ __forceinline__ void exchange_moments(SmemLayout& S, EpiCtx& E, float& s1, float& s2) {
-    if (kEpiSets == 2) {
-        S.xch[E.xpar][E.et] = make_float2(s1, s2);
-        epi_bar_sync();
-        const float2 o = S.xch[E.xpar][E.et ^ 128];
-        E.xpar ^= 1;
-        s1 += o.x;
-        s2 += o.y;
-    }
+    fold_moments(s1, s2, s1o, s2o);
 }
 
 __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P) {
-    const uint4* img = reinterpret_cast<const uint4*>(E.scr + P.cond_off);
+    const uint4* img = reinterpret_cast<const uint4*>(E.scr + P.cond_off) + E.row;
     const int nkc = P.Cp / 8;                      // 16-byte K pieces per row
-    for (int c0 = 0; c0 < nkc; c0 += kPiecesPerChunk) {
-        const int nk = min(kPiecesPerChunk, nkc - c0);
+    for (int c0 = 0; c0 < nkc; c0 += 8) {
+        const int nk = min(8, nkc - c0);
         const uint32_t sq = E.aseq, sl = sq % kASlots;
-        mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
-        const uint32_t base = (uint32_t)(E.row >> 3) * (nk * 128) + (E.row & 7) * 16;
-        for (int k0 = E.set; k0 < nk; k0 += 4 * kEpiSets) {   // 8 independent 16-byte loads in flight; piece k -> set k % kEpiSets
+        if (E.fresh >= kASlots) mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
+        ++E.fresh;
+        const uint32_t base = E.a_hi0 + sl * kSlotBytes + (uint32_t)(E.row >> 3) * (uint32_t)(nk * 128) + E.a_row;
+        for (int k0 = 0; k0 < nk; k0 += 4) {       // 8 independent 16-byte loads in flight
             uint4 h[4], l[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k0 + k * kEpiSets < nk) {
-                    h[k] = img[(size_t)(c0 + k0 + k * kEpiSets) * kRows + E.row];
-                    l[k] = img[(size_t)(nkc + c0 + k0 + k * kEpiSets) * kRows + E.row];
+                if (k0 + k < nk) {
+                    h[k] = img[(size_t)(c0 + k0 + k) * kRows];
+                    l[k] = img[(size_t)(nkc + c0 + k0 + k) * kRows];
                 }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k0 + k * kEpiSets < nk) {
-                    *reinterpret_cast<uint4*>(S.a_hi[sl] + base + (k0 + k * kEpiSets) * 128) = h[k];
-                    *reinterpret_cast<uint4*>(S.a_lo[sl] + base + (k0 + k * kEpiSets) * 128) = l[k];
+                if (k0 + k < nk) {
+                    sts128(base + (k0 + k) * 128, h[k].x, h[k].y, h[k].z, h[k].w);
+                    sts128(base + kLoOff + (k0 + k) * 128, l[k].x, l[k].y, l[k].z, l[k].w);
                 }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&S.a_full[sl]);
+        emit_publish(S, E, sq);
         ++E.aseq;
     }
 }
@@ -415,128 +384,183 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             mbar_wait(&S.acc_full, acc_phase);
             acc_phase ^= 1;
             tcgen05_fence_after();
+            E.fresh = 0;
             TCT_END(_ta, 0);
         }
-        const bool has_pkg = (sg.pkg_f4 | sg.tt_f4) != 0;
+        const bool has_pkg = sg.pkg_f4 != 0;
         const uint32_t psl = pseq % kPSlots;
         if (has_pkg) { TCT_BEGIN(_tk); mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1); TCT_END(_tk, 1); }
-        const float* pk = S.pkg[psl];
+        const float* pk_ = S.pkg[psl];
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
             const Epi op = c_epis[ei];
-            const int np = op.np, ng = np >> 1, dt = op.dt;
+            const int np = op.np, ng = np >> 1, dt = op.dt, dp = np * 8;
             const int region = op.misc & 1, flags = op.misc >> 1;
             const uint32_t ta = E.tmem_row + region * kRegionCols;
-            const float* bias = pk + op.off0 * 4;
-            if (!kSampler && (flags & kFTime)) bias = P.tt + (size_t)trow * P.tt_stride + sg.tt_src4 * 4;
-            float x[16];
-            constexpr int G = kEpiSets;       // group stride: this thread owns groups set, set + G, ...
-            const int g0 = E.set;
+            const float* tt_row = (!kSampler && (flags & kFTime)) ? P.tt + (size_t)trow * P.tt_stride + op.tt_src4 * 4 : nullptr;
+            uint32_t r[16];
+            f2 x[8];
             switch (op.kind) {
                 case OP_LN: {
-                    float4* sk = reinterpret_cast<float4*>(E.scr + P.skip_off[op.slot]) + row;
-                    // shift for the one-pass moments: column 0 of the (bias-added) vector
-                    float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                    if (G == 2 && g0 != 0) shift = tmem_ld1(ta) + bias[0];
-                    TmemWalk w;
+                    // ---- pass 1: moments (and the skip push)
                     TCT_BEGIN(_t1);
-                    if (g0 < ng) walk_begin(w, ta + g0 * 16);
-                    for (int g = g0; g < ng; g += G) {
-                        walk_next(w, x, bias + g * 16, g + G < ng, ta + (g + G) * 16);
-                        if (flags & kFPush) store_group_skip(x, sk + (size_t)g * 4 * kRows);
-                        if (g == 0) shift = x[0];
-                        moments_group(x, dt - g * 16, shift, s1, s2);
-                        walk_sync();
-                    }
+                    uint4* sk = (flags & kFPush) ? reinterpret_cast<uint4*>(E.scr + P.skip_off[op.slot]) + row : nullptr;
+                    float shift, s1, s2;
+                    tmem_moments<kSampler>(ta, ng, dt, tt_row, sk, shift, s1, s2);
+                    if (flags & kFPush)
+                        reinterpret_cast<float4*>(E.scr + P.stats_off)[op.slot * kRows + row] = make_float4(s1, s2, shift, 0.f);
+                    const float inv_n = 1.0f / (float)dt;
+                    const float md = s1 * inv_n;
+                    const float rstd = rsqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + kLnEps);
+                    const f2 sc = pk(rstd, rstd), sh = pk(-(shift + md) * rstd, -(shift + md) * rstd);
                     TCT_END(_t1, 2);
+                    // ---- pass 2: normalise, Swish, split, publish
                     TCT_BEGIN(_t2);
-                    exchange_moments(S, E, s1, s2);
-                    TCT_END(_t2, 3);
-                    TCT_BEGIN(_t3);
-                    float a_scale, a_shift;
-                    finish_moments(s1, s2, shift, (float)dt, a_scale, a_shift);
+                    const float4* pg = reinterpret_cast<const float4*>(pk_ + op.off1 * 4);
+                    const float4* pb = pg + np * 2;
                     Emitter em;
                     emit_begin(em, E, np, (flags & kFDefer) != 0);
-                    const float* pg = pk + op.off1 * 4;
-                    const float* pb = pk + op.off2 * 4;
-                    if (g0 < ng) walk_begin(w, ta + g0 * 16);
-                    for (int g = g0; g < ng; g += G) {
-                        walk_next(w, x, bias + g * 16, g + G < ng, ta + (g + G) * 16);
-                        ln_swish_group(x, dt - g * 16, a_scale, a_shift, pg + g * 16, pb + g * 16);
-                        emit_group(S, E, em, g, x);
-                        walk_sync();
+                    tmem_ld16u(ta, r);
+                    for (int g = 0; g < ng; ++g) {
+                        const uint32_t addr = emit_addr(S, E, em, g);
+                        tmem_wait16(r);
+                        if (!kSampler && tt_row) add_time16(r, tt_row + g * 16);
+                        normalise16(r, sc, sh, x);
+                        if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
+                        store_ln_swish(addr, x, pg + g * 4, pb + g * 4);
+                        emit_done(S, E, em, g);
                     }
                     emit_end(S, E, em);
-                    TCT_END(_t3, 4);
-                    if ((flags & kFCond) && use_cond) { TCT_BEGIN(_t4); emit_cond(S, E, P); TCT_END(_t4, 7); }
+                    TCT_END(_t2, 3);
+                    if ((flags & kFCond) && use_cond) { TCT_BEGIN(_t4); emit_cond(S, E, P); TCT_END(_t4, 6); }
                     break;
                 }
                 case OP_CATLN: {
                     TCT_BEGIN(_t5);
-                    // LayerNorm over cat(x, skip): statistics over both, operands: skip part, then x part
-                    const float4* sk = reinterpret_cast<const float4*>(E.scr + P.skip_off[op.slot]) + row;
-                    float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                    if (G == 2 && g0 != 0) shift = tmem_ld1(ta) + bias[0];
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_tmem(x, ta + g * 16, bias + g * 16);
-                        if (g == 0) shift = x[0];
-                        moments_group(x, dt - g * 16, shift, s1, s2);
-                    }
-                    skip_walk2(sk, g0, G, ng, [&](int g, const float (&xg)[16]) { moments_group(xg, dt - g * 16, shift, s1, s2); });
-                    exchange_moments(S, E, s1, s2);
-                    float a_scale, a_shift;
-                    finish_moments(s1, s2, shift, (float)(2 * dt), a_scale, a_shift);
-                    const float* pgx = pk + op.off1 * 4;            // gamma_x | beta_x | gamma_s | beta_s
-                    const int dp = np * 8;
+                    // LayerNorm over cat(x, skip): the skip part's moments were stored when it was pushed;
+                    // operands: skip part, then x part
+                    const uint4* sk = reinterpret_cast<const uint4*>(E.scr + P.skip_off[op.slot]) + row;
+                    const float4 ss = reinterpret_cast<const float4*>(E.scr + P.stats_off)[op.slot * kRows + row];
+                    float shift, s1, s2;
+                    tmem_moments<kSampler>(ta, ng, dt, nullptr, nullptr, shift, s1, s2);
+                    const float n = (float)dt, inv_n = 1.0f / n;
+                    const float mx = shift + s1 * inv_n, ms = ss.z + ss.x * inv_n;
+                    const float m2 = (s2 - s1 * s1 * inv_n) + (ss.y - ss.x * ss.x * inv_n) + (mx - ms) * (mx - ms) * (0.5f * n);
+                    const float mean = 0.5f * (mx + ms);
+                    const float rstd = rsqrtf(fmaxf(m2 * (0.5f * inv_n), 0.f) + kLnEps);
+                    const f2 sc = pk(rstd, rstd), sh = pk(-mean * rstd, -mean * rstd);
+                    const float4* pgx = reinterpret_cast<const float4*>(pk_ + op.off1 * 4);   // gamma_x | beta_x | gamma_s | beta_s
+                    const int d4 = np * 2;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    skip_walk2(sk, g0, G, ng, [&](int g, float (&xg)[16]) {
-                        ln_swish_group(xg, dt - g * 16, a_scale, a_shift, pgx + 2 * dp + g * 16, pgx + 3 * dp + g * 16);
-                        emit_group(S, E, em, g, xg);
+                    skip_walk2(sk, ng, [&](int g, const uint32_t (&rs)[16]) {
+                        const uint32_t addr = emit_addr(S, E, em, g);
+                        f2 xs[8];
+                        normalise16(rs, sc, sh, xs);
+                        store_ln_swish(addr, xs, pgx + 2 * d4 + g * 4, pgx + 3 * d4 + g * 4);
+                        emit_done(S, E, em, g);
                     });
                     emit_end(S, E, em);
                     emit_begin(em, E, np, false);
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_tmem(x, ta + g * 16, bias + g * 16);
-                        ln_swish_group(x, dt - g * 16, a_scale, a_shift, pgx + g * 16, pgx + dp + g * 16);
-                        emit_group(S, E, em, g, x);
+                    tmem_ld16u(ta, r);
+                    for (int g = 0; g < ng; ++g) {
+                        const uint32_t addr = emit_addr(S, E, em, g);
+                        tmem_wait16(r);
+                        normalise16(r, sc, sh, x);
+                        if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
+                        store_ln_swish(addr, x, pgx + g * 4, pgx + d4 + g * 4);
+                        emit_done(S, E, em, g);
                     }
                     emit_end(S, E, em);
-                    TCT_END(_t5, 8);
+                    TCT_END(_t5, 4);
                     break;
                 }
                 case OP_RAW_T: {
-                    float4* sk = reinterpret_cast<float4*>(E.scr + P.skip_off[op.slot]) + row;
+                    TCT_BEGIN(_t6);
+                    // raw TMEM vector as an operand (Down/Upsample, shortcut, attention); when pushed, its moments
+                    // are stored for the cat LayerNorm that pops it
+                    const bool push = (flags & kFPush) != 0;
+                    uint4* sk = reinterpret_cast<uint4*>(E.scr + P.skip_off[push ? op.slot : 0]) + row;
+                    f2 s1[2] = {0ull, 0ull}, s2[2] = {0ull, 0ull}, sh2 = 0ull;
+                    float shift = 0.f;
                     Emitter em;
-                    emit_begin(em, E, np, (flags & kFDefer) != 0);     // deferred when the next GEMM accumulates into this region (attention)
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_tmem(x, ta + g * 16, bias + g * 16);
-                        if (flags & kFPush) store_group_skip(x, sk + (size_t)g * 4 * kRows);
-                        emit_group(S, E, em, g, x);                  // pad columns are exact zeros (zero W rows, zero bias)
+                    emit_begin(em, E, np, (flags & kFDefer) != 0);     // deferred when the next GEMM accumulates into this region
+                    tmem_ld16u(ta, r);
+                    for (int g = 0; g < ng; ++g) {
+                        const uint32_t addr = emit_addr(S, E, em, g);
+                        tmem_wait16(r);
+                        track_amax(E, r);
+                        pack16(r, x);                                // pad columns are exact zeros (zero W rows, zero bias)
+                        store_split(addr, x);
+                        if (push) {
+                            if (g == 0) { shift = __uint_as_float(r[0]); sh2 = pk(shift, shift); }
+                            store_group_skip(r, sk + (size_t)g * 4 * kRows);
+                            if (g == ng - 1 && dt < ng * 16) {
+                                const int nval = dt - g * 16;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) if (j >= nval) r[j] = __float_as_uint(shift);
+                            }
+                            centre16(r, sh2, x);
+                            moments16(x, s1, s2);
+                        }
+                        if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
+                        emit_done(S, E, em, g);
                     }
                     emit_end(S, E, em);
+                    if (push) {
+                        float a, q;
+                        fold_moments(s1, s2, a, q);
+                        reinterpret_cast<float4*>(E.scr + P.stats_off)[op.slot * kRows + row] = make_float4(a, q, shift, 0.f);
+                    }
+                    TCT_END(_t6, 5);
                     break;
                 }
                 case OP_RAW_S: {
-                    const float4* sk = reinterpret_cast<const float4*>(E.scr + P.skip_off[op.slot]) + row;
+                    TCT_BEGIN(_t7);
+                    const uint4* sk = reinterpret_cast<const uint4*>(E.scr + P.skip_off[op.slot]) + row;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    skip_walk2(sk, g0, G, ng, [&](int g, const float (&xg)[16]) { emit_group(S, E, em, g, xg); });
+                    skip_walk2(sk, ng, [&](int g, const uint32_t (&rs)[16]) {
+                        const uint32_t addr = emit_addr(S, E, em, g);
+                        track_amax(E, rs);
+                        f2 xs[8];
+                        pack16(rs, xs);
+                        store_split(addr, xs);
+                        emit_done(S, E, em, g);
+                    });
                     emit_end(S, E, em);
+                    TCT_END(_t7, 5);
                     break;
                 }
                 case OP_RAW_IN: {
+                    TCT_BEGIN(_t8);
                     const float* src = (kSampler ? R.y : R.x) + E.grow * P.M;
+                    const bool vec4 = (P.M & 3) == 0;
                     Emitter em;
                     emit_begin(em, E, np, false);
-                    for (int g = g0; g < ng; g += G) {
+                    for (int g = 0; g < ng; ++g) {
+                        const uint32_t addr = emit_addr(S, E, em, g);
+                        if (vec4) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) x[j] = (E.valid && g * 16 + j < dt) ? src[g * 16 + j] : 0.f;
-                        emit_group(S, E, em, g, x);
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                                if (E.valid && g * 16 + q * 4 < dt) t = *reinterpret_cast<const uint4*>(src + g * 16 + q * 4);
+                                r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r[j] = (E.valid && g * 16 + j < dt) ? __float_as_uint(src[g * 16 + j]) : 0u;
+                        }
+                        track_amax(E, r);
+                        pack16(r, x);
+                        store_split(addr, x);
+                        emit_done(S, E, em, g);
                     }
                     emit_end(S, E, em);
+                    TCT_END(_t8, 5);
                     break;
                 }
                 case OP_OUT: {
+                    TCT_BEGIN(_t9);
                     float4* stash = reinterpret_cast<float4*>(E.scr + P.stash_off) + row;
                     const float w1 = 1.0f + R.omega, w0 = R.omega;
                     const float ce = R.c_eps[step], crs = R.c_rs[step], cn = R.c_noise[step];
@@ -544,18 +568,24 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const bool want_stats = step > R.T - 1 - R.norm_steps;
                     const int64_t plane = R.B * (int64_t)P.M;
                     const int64_t pidx = (int64_t)(R.T - 1 - step) * plane;
-                    for (int g = g0; g < ng; g += G) {
-                        load_group_tmem(x, ta + g * 16, bias + g * 16);
+                    for (int g = 0; g < ng; ++g) {
+                        tmem_ld16u(ta + g * 16, r);
+                        tmem_wait16(r);
+                        float xv[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xv[j] = __uint_as_float(r[j]);
                         if (!kSampler) {
                             if (E.valid) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
-                                    if (g * 16 + j < dt) R.eps[E.grow * P.M + g * 16 + j] = x[j];
+                                    if (g * 16 + j < dt) R.eps[E.grow * P.M + g * 16 + j] = xv[j];
                             }
                             continue;
                         }
                         if (pass == 0) {           // unconditional pass: park eps_0
-                            store_group_skip(x, stash + (size_t)g * 4 * kRows);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                stash[(size_t)(g * 4 + q) * kRows] = make_float4(xv[q * 4], xv[q * 4 + 1], xv[q * 4 + 2], xv[q * 4 + 3]);
                             continue;
                         }
                         // conditional pass: guidance mix + posterior update (classifier_free_MSR.py:132-134)
@@ -588,7 +618,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                             }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                ev[j] = w1 * x[q * 4 + j] - w0 * e0a[j];
+                                ev[j] = w1 * xv[q * 4 + j] - w0 * e0a[j];
                                 yn[j] = (yo[j] - ce * ev[j]) * crs;
                                 if (add_noise) yn[j] += cn * z[j];
                                 if (want_stats && c0 + j < dt) { st_s += (double)yn[j]; st_q += (double)yn[j] * (double)yn[j]; }
@@ -608,6 +638,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                             }
                         }
                     }
+                    TCT_END(_t9, 7);
                     break;
                 }
                 default:
@@ -615,10 +646,20 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             }
         }
         if (has_pkg) {
-            mbar_arrive(&S.p_empty[psl]);
+            __syncwarp();
+            if (E.lane == 0) mbar_arrive(&S.p_empty[psl]);
             ++pseq;
         }
     }
+}
+
+// Which chunks of a stage are issued in this pass: cond chunks only in a conditional pass; time-bias chunks
+// (images of the step table) only by the sampler -- forward mode adds the row's own time slice in the epilogue.
+template <bool kSampler>
+__device__ __forceinline__ bool chunk_active(const Chunk& ch, bool use_cond) {
+    if ((ch.flags & kChunkCond) && !use_cond) return false;
+    if ((ch.flags & kChunkTime) && !kSampler) return false;
+    return true;
 }
 
 template <bool kSampler>
@@ -632,13 +673,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kASlots; ++i) { mbar_init(&S.a_full[i], kEpiThreads); mbar_init(&S.a_empty[i], 1); }
+        for (int i = 0; i < kASlots; ++i) { mbar_init(&S.a_full[i], kEpiWarps); mbar_init(&S.a_empty[i], 1); }
         for (int i = 0; i < kWStages; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
-        for (int i = 0; i < kPSlots; ++i) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], kEpiThreads); }
+        for (int i = 0; i < kPSlots; ++i) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], kEpiWarps); }
         mbar_init(&S.acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) { tmem_alloc(&S.tmem_base, kTmemCols); tmem_relinquish(); }
+    if (threadIdx.x < kRows) {
+        // constant A tile of the bias chunks: K columns 0..2 = 1 (the three fp16 terms of the bias), rest 0;
+        // core-matrix layout [row / 8][k / 8][row % 8][8]
+        const uint32_t rr = threadIdx.x;
+        uint4* o = reinterpret_cast<uint4*>(S.ones + (rr >> 3) * 256 + (rr & 7) * 16);
+        o[0] = make_uint4(0x3C003C00u, 0x00003C00u, 0u, 0u);
+        o[8] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
+    if (warp == kEpiWarps) { tmem_alloc(&S.tmem_base, kTmemCols); tmem_relinquish(); }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -647,10 +697,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
     const int n_pass = kSampler ? 2 : 1;
     const int step_hi = kSampler ? R.step_hi : 0, step_lo = kSampler ? R.step_lo : 0;
 
-    if (warp < kEpiWarp0) {
-      if (kSplitRegs) setmaxnreg_dec();
-      if (warp == 0) {
-        // =========================== TMA producer: parameter packages + weight chunks
+    if (warp == kEpiWarps) {
+        // =========================== TMA producer: parameter packages + weight / bias chunks
         if (lane == 0) {
             uint32_t wseq = 0, pseq = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -659,39 +707,38 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                         const bool use_cond = kSampler ? (pass == 1) : true;
                         for (int si = 0; si < P.n_stages; ++si) {
                             const Stage sg = c_stages[si];
-                            if (sg.pkg_f4 | sg.tt_f4) {
+                            if (sg.pkg_f4) {
                                 const uint32_t sl = pseq % kPSlots;
-                                const bool tma_time = kSampler && sg.tt_f4;
-                                const uint32_t tt_bytes = (uint32_t)sg.tt_f4 * 16u, st_bytes = (uint32_t)sg.pkg_f4 * 16u;
+                                const uint32_t bytes = (uint32_t)sg.pkg_f4 * 16u;
                                 mbar_wait_parked(&S.p_empty[sl], ((pseq / kPSlots) & 1) ^ 1);
-                                mbar_arrive_expect_tx(&S.p_full[sl], st_bytes + (tma_time ? tt_bytes : 0u));
-                                if (tma_time)
-                                    tma_load_1d(S.pkg[sl], P.tt + (size_t)step * P.tt_stride + (size_t)sg.tt_src4 * 4, tt_bytes, &S.p_full[sl]);
-                                if (st_bytes)
-                                    tma_load_1d(S.pkg[sl] + sg.tt_f4 * 4, P.params + (size_t)sg.pkg_off4 * 4, st_bytes, &S.p_full[sl]);
+                                mbar_arrive_expect_tx(&S.p_full[sl], bytes);
+                                tma_load_1d(S.pkg[sl], P.params + (size_t)sg.pkg_off4 * 4, bytes, &S.p_full[sl]);
                                 ++pseq;
                             }
                             if (!(sg.bits & 4)) continue;
                             for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
                                 const Chunk ch = c_chunks[ci];
-                                if ((ch.flags & kChunkCond) && !use_cond) continue;
+                                if (!chunk_active<kSampler>(ch, use_cond)) continue;
                                 const uint32_t st = wseq % kWStages, ph = (wseq / kWStages) & 1;
                                 const uint32_t bytes = (uint32_t)sg.n16 * 16u * ch.kw * 2u;
+                                const bool bias = (ch.flags & kChunkBias) != 0;
+                                const uint8_t* src = (ch.flags & kChunkTime) ? P.tt_img + (size_t)step * P.tt_img_stride : P.w_hi;
                                 mbar_wait_parked(&S.w_empty[st], ph ^ 1);
-                                mbar_arrive_expect_tx(&S.w_full[st], bytes * w_terms);
+                                mbar_arrive_expect_tx(&S.w_full[st], bytes * (bias ? 1 : w_terms));
                                 uint8_t* dst = w_ring + (size_t)st * w_terms * kWStageBytes;
-                                tma_load_1d(dst, P.w_hi + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
-                                if (w_terms == 2)
+                                tma_load_1d(dst, src + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
+                                if (w_terms == 2 && !bias)
                                     tma_load_1d(dst + kWStageBytes, P.w_lo + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
                                 ++wseq;
                             }
                         }
                     }
         }
-      } else if (warp == 1) {
+    } else if (warp == kEpiWarps + 1) {
         // =========================== MMA issuer
         if (lane == 0) {
             uint32_t wseq = 0, aseq = 0;
+            const uint64_t d_ones = make_smem_desc(smem_u32(S.ones), 128, 256, 0);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int step = step_hi; step >= step_lo; --step)
                     for (int pass = 0; pass < n_pass; ++pass) {
@@ -704,17 +751,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                             uint32_t acc = (sg.bits >> 1) & 1;
                             for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
                                 const Chunk ch = c_chunks[ci];
-                                if ((ch.flags & kChunkCond) && !use_cond) continue;
+                                if (!chunk_active<kSampler>(ch, use_cond)) continue;
                                 const uint32_t st = wseq % kWStages, wph = (wseq / kWStages) & 1;
+                                const uint32_t sbo = (uint32_t)ch.kw * 16u;
+                                const uint8_t* wst = w_ring + (size_t)st * w_terms * kWStageBytes;
+                                const uint64_t dw_hi = make_smem_desc(smem_u32(wst), 128, sbo, 0);
+                                if (ch.flags & kChunkBias) {
+                                    // accumulator += 1 . [b_hi, b_mid, b_lo]: the constant ones tile is the A operand
+                                    mbar_wait_parked(&S.w_full[st], wph);
+                                    tcgen05_fence_after();
+                                    umma_f16(d_tmem, d_ones, dw_hi, idesc, acc);
+                                    acc = 1;
+                                    umma_commit(&S.w_empty[st]);
+                                    ++wseq;
+                                    continue;
+                                }
                                 const uint32_t sl = aseq % kASlots, aph = (aseq / kASlots) & 1;
                                 mbar_wait_parked(&S.a_full[sl], aph);
                                 mbar_wait_parked(&S.w_full[st], wph);
                                 tcgen05_fence_after();
-                                const uint32_t sbo = (uint32_t)ch.kw * 16u;
-                                const uint8_t* wst = w_ring + (size_t)st * w_terms * kWStageBytes;
                                 const uint64_t da_hi = make_smem_desc(smem_u32(S.a_hi[sl]), 128, sbo, 0);
                                 const uint64_t da_lo = make_smem_desc(smem_u32(S.a_lo[sl]), 128, sbo, 0);
-                                const uint64_t dw_hi = make_smem_desc(smem_u32(wst), 128, sbo, 0);
                                 const uint64_t dw_lo = make_smem_desc(smem_u32(wst + kWStageBytes), 128, sbo, 0);
                                 for (uint32_t ks = 0; ks < ch.kw / 16u; ++ks) {
                                     const uint64_t adv = (uint64_t)(ks * 16u);      // 256 bytes >> 4
@@ -731,17 +788,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                         }
                     }
         }
-      }
     } else {
         // =========================== epilogue / operand producers (thread == row == TMEM lane)
-        if (kSplitRegs) setmaxnreg_inc();
         EpiCtx E;
-        E.et = threadIdx.x - kEpiWarp0 * 32;
-        E.set = E.et >> 7;
-        E.row = 32 * (warp & 3) + lane;
-        E.tmem_row = S.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        E.lane = lane;
+        E.row = threadIdx.x;
+        E.tmem_row = S.tmem_base + ((uint32_t)(32 * warp) << 16);
         E.aseq = 0;
-        E.xpar = 0;
+        E.fresh = 0;
+        E.a_row = (uint32_t)(E.row & 7) * 16u;
+        E.a_hi0 = smem_u32(S.a_hi[0]);
+        E.amax = 0.f;
 #ifdef DIFFSG_TC_TIMING
         for (int i = 0; i < 12; ++i) E.tacc[i] = 0;
 #endif
@@ -753,20 +810,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
             E.valid = E.grow < R.B;
             // cond image: swish(cond * mask) as fp16 (hi, lo) 16-byte K pieces (thread-private scratch)
             {
-                uint4* img = reinterpret_cast<uint4*>(E.scr + P.cond_off);
+                uint4* img = reinterpret_cast<uint4*>(E.scr + P.cond_off) + E.row;
                 const int nkc = P.Cp / 8;
                 const float mk = (!kSampler && R.mask && E.valid) ? R.mask[E.grow] : 1.0f;
-                for (int kc = E.set; kc < nkc; kc += kEpiSets) {
-                    float x[8];
+                for (int kc = 0; kc < nkc; ++kc) {
+                    float xc[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int c = kc * 8 + j;
-                        x[j] = (E.valid && c < P.C) ? swish_exact(R.cond[E.grow * P.C + c] * mk) : 0.f;
+                        xc[j] = (E.valid && c < P.C) ? swish_exact(R.cond[E.grow * P.C + c] * mk) : 0.f;
                     }
                     uint4 hi, lo;
-                    split_pack8(x, hi, lo);
-                    img[(size_t)kc * kRows + E.row] = hi;
-                    img[(size_t)(nkc + kc) * kRows + E.row] = lo;
+                    split2(pk(xc[0], xc[1]), hi.x, lo.x);
+                    split2(pk(xc[2], xc[3]), hi.y, lo.y);
+                    split2(pk(xc[4], xc[5]), hi.z, lo.z);
+                    split2(pk(xc[6], xc[7]), hi.w, lo.w);
+                    img[(size_t)kc * kRows] = hi;
+                    img[(size_t)(nkc + kc) * kRows] = lo;
                 }
             }
             const int trow_fwd = (!kSampler && E.valid) ? R.t_idx[E.grow] : 0;
@@ -776,13 +836,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                     TCT_BEGIN(_tt);
                     run_epilogue<kSampler>(S, P, R, E, kSampler ? step : trow_fwd, use_cond, pass, step, acc_phase,
                                            pseq, st_s, st_q);
-                    TCT_END(_tt, 10);
+                    TCT_END(_tt, 8);
                 }
         }
 #ifdef DIFFSG_TC_TIMING
-        if (blockIdx.x == 0 && E.et == 0 && P.debug)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && P.debug)
             for (int i = 0; i < 12; ++i) P.debug[i] = E.tacc[i];
 #endif
+        if (E.amax > 65504.0f && P.status) atomicOr(P.status, kStatusOverflow);
         if (kSampler && R.step_hi > R.T - 1 - R.norm_steps) {
             st_s = warp_sum(st_s);
             st_q = warp_sum(st_q);
@@ -794,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(S.tmem_base, kTmemCols);
+    if (warp == kEpiWarps) tmem_dealloc(S.tmem_base, kTmemCols);
 }
 
 }  // namespace tc

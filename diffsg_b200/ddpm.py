@@ -60,6 +60,10 @@ class DDPMBase(nn.Module):
         self.noise_mode = "reference"
         self.philox_seed = 0
         self.philox_offset = 0
+        # sample() ends with a check of the engine's fp16 range flag (one 4-byte read, synchronises the stream) and
+        # raises if an un-normalised operand left the fp16 range; set False to keep sample() fully asynchronous
+        # (the flag stays sticky: `model.engine().check_status()` reads it later).
+        self.range_check = True
 
     # ------------------------------------------------------------------ training loss
     def forward(self, y, cond):
@@ -153,6 +157,8 @@ class DDPMBase(nn.Module):
                                        stats_reduce=reduce_fn)
             if noise is None:
                 self.philox_offset += B  # fresh stream for the next call
+            if getattr(self, "range_check", True):
+                self.model.engine().check_status()
             if self.record_denoise_path:
                 self._store_records(rec_y, rec_eps)
         return torch.squeeze(y.reshape(B, *self.data_size))

@@ -88,7 +88,7 @@ class UNetEngine:
         self._sig = None
         self._blob = None
         self._tc_blobs = None
-        self._tables = {}       # key -> (t_values tuple / T) -> table tensor
+        self._tables = {}       # key -> (fp32 time table, fp16 step image table or None)
         self._bound_table = None
         self._stat_ws = None
 
@@ -123,7 +123,8 @@ class UNetEngine:
             self._bound_table = None
             self._sig = sig
 
-    def _bind(self, table: torch.Tensor):
+    def _bind(self, table: torch.Tensor, images: torch.Tensor | None = None):
+        """Bind the packed weights plus one time table (and, for the tensor-core sampler, its step images)."""
         if self._bound_table is not table:
             if self.tc is None:
                 _lib.check(self.lib.diffsg_plan_set_weights(self.handle, self._blob.data_ptr(), self._blob.numel(),
@@ -133,8 +134,11 @@ class UNetEngine:
                 hi, lo, params = self._tc_blobs
                 _lib.check(self.lib.diffsg_plan_set_tc_weights(
                     self.handle, hi.data_ptr(), lo.data_ptr() if lo is not None else None, hi.numel() * 2,
-                    params.data_ptr(), params.numel(), table.data_ptr(), table.shape[0]), "diffsg_plan_set_tc_weights")
+                    params.data_ptr(), params.numel(), table.data_ptr(), table.shape[0],
+                    images.data_ptr() if images is not None else None, images.shape[0] if images is not None else 0,
+                    images.shape[1] * 2 if images is not None else 0), "diffsg_plan_set_tc_weights")
             self._bound_table = table
+            self._bound_keep = (table, images)
 
     def _time_table(self, t_values):
         with _fp32_matmul():
@@ -142,13 +146,46 @@ class UNetEngine:
                 return time_table(self.model, self.program, t_values)
             return tc_packer.time_table_tc(self.model, self.tc, t_values)
 
-    def step_table(self, T: int) -> torch.Tensor:
-        """Time-bias table for the sampler: row i <-> t = i / T (reference MSR.py:126)."""
+    def step_table(self, T: int):
+        """Time-bias table for the sampler: row i <-> t = i / T (reference MSR.py:126).  -> (fp32 table, fp16 step
+        images or None): the tensor-core sampler streams the images as bias chunks, forward reads the fp32 rows."""
         key = ("steps", T)
         if key not in self._tables:
             t = torch.arange(T, device=self.device) / T
-            self._tables[key] = self._time_table(t)
+            table = self._time_table(t)
+            self._tables[key] = (table, tc_packer.time_images(self.tc, table) if self.tc is not None else None)
         return self._tables[key]
+
+    def check_status(self, reset=True):
+        """Raise if a tensor-core kernel of this plan flagged a raw operand outside the fp16 range since the last
+        check (the fp16-split engines saturate it: the call's results are not within tolerance of fp32).
+        Synchronises the current stream."""
+        if self.tc is None:
+            return
+        flags = C.c_int32(0)
+        _lib.check(self.lib.diffsg_plan_status(self.handle, C.byref(flags), 1 if reset else 0, _lib.stream_ptr()),
+                   "diffsg_plan_status")
+        if flags.value & 1:
+            raise _lib.DiffsgError(
+                f"precision {self.precision!r}: an un-normalised operand (y_t or the residual stream) exceeded the fp16 range "
+                "(|x| > 65504); the fp16-split tensor-core engine saturates such values, so this call's results are not "
+                "within tolerance of the fp32 reference.  Re-run with model.precision = 'fp32'.")
+
+    def _table_for(self, tv: torch.Tensor):
+        """fp32 time table for arbitrary time values `tv` [B] -> (table, row index per element).  The distinct values
+        are found with torch.unique (one host sync, needed to size the table); the table itself is cached per
+        distinct-value set, so repeated calls on the same time grid (a sampling loop, a training schedule) reuse it."""
+        uniq, inv = torch.unique(tv, return_inverse=True)
+        if uniq.numel() <= 4096:
+            key = ("values", tuple(uniq.tolist()))
+            if key not in self._tables:
+                if sum(1 for k in self._tables if k[0] == "values") >= 64:      # bound the cache
+                    for k in [k for k in self._tables if k[0] == "values"]:
+                        if self._tables[k][0] is not self._bound_table:
+                            del self._tables[k]
+                self._tables[key] = (self._time_table(uniq), None)
+            return self._tables[key][0], inv
+        return self._time_table(uniq), inv
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, t, cond, cond_mask, t_index=None, n_steps=None):
@@ -161,8 +198,9 @@ class UNetEngine:
         if B == 0:      # empty batch: nothing to launch (the reference returns an empty tensor too)
             return torch.empty(0, self.program.input_dim, dtype=torch.float32, device=self.device)
         cond2 = _f32c(cond).reshape(B, self.program.cond_dim)
+        images = None
         if t_index is not None:
-            table = self.step_table(int(n_steps))
+            table, images = self.step_table(int(n_steps))
             inv = t_index.detach().reshape(-1)
             if inv.numel() == 1 and B > 1:
                 inv = inv.expand(B)
@@ -170,10 +208,8 @@ class UNetEngine:
             tv = t.detach().reshape(-1).to(torch.float32)
             if tv.numel() == 1 and B > 1:
                 tv = tv.expand(B)
-            uniq, inv = torch.unique(tv, return_inverse=True)
-            table = self._time_table(uniq)
-        self._keep = table  # keep alive while bound
-        self._bind(table)
+            table, inv = self._table_for(tv)
+        self._bind(table, images)
         mask = None
         if cond_mask is not None:
             mask = _f32c(cond_mask).reshape(-1)
@@ -199,8 +235,8 @@ class UNetEngine:
         if y_init.shape[0] == 0 and stats_reduce is None:
             return y_init
         self.refresh()
-        table = self.step_table(T)
-        self._bind(table)
+        table, images = self.step_table(T)
+        self._bind(table, images)
         B = y_init.shape[0]
         M = self.program.input_dim
         if self._stat_ws is None or self._stat_ws.numel() < 2 * T:

@@ -16,9 +16,13 @@ Layout decisions made here:
   * a single-token AttentionBlock is ONE accumulate stage with the fused matrix output.weight @ V.weight;
   * weights are fp16 core-matrix images ([n/8][k/8][n%8][8], one image per <=64-wide K-chunk)
     streamed by 1-D bulk TMA; with nterms == 3 a second image holds the fp16 residual of W;
-  * every fp32 side parameter a stage's epilogue needs (bias, LayerNorm gamma/beta) is packed
-    into ONE contiguous per-stage package that the TMA warp streams into shared memory ahead
-    of the epilogue; the hoisted time bias (+ lin1.bias) comes from the per-step table row;
+  * biases ride on the tensor cores: every GEMM group ends with a K = 16 "bias chunk" whose A operand is the
+    kernel's constant tile of ones (K columns 0..2) and whose W image holds the bias as three fp16 terms
+    (hi, mid, lo; exact to 2^-33).  Static biases live in the weight blob; the hoisted time bias
+    (lin1.bias + time_emb(Swish(TimeEmbedding(t)))) is one image row per reverse step (`time_images`).
+    `UNet1D.forward` (rows with arbitrary t) skips the time chunks and adds the row's fp32 table slice instead;
+  * the LayerNorm gamma / beta a stage's epilogue needs are packed into ONE contiguous per-stage package that
+    the TMA warp streams into shared memory ahead of the epilogue;
   * widths are padded to multiples of 16 (UMMA K / N granularity); pad rows/cols are zero.
 Reference semantics: ddpm_opt/UNetCF.py:83-95, :318-356.
 """
@@ -35,26 +39,20 @@ from .unet import AttentionBlock, DownBlock, ResidualBlock, UNet1D, UpBlock
 
 CHUNK_K = _lib.TC_VARIANT["chunk"]      # K columns per operand chunk (must match the library build)
 MAX_W = _lib.TC_VARIANT["region"]       # widest vector = TMEM columns per accumulator region
-PKG_MAX_FLOATS = 640
+PKG_MAX_FLOATS = 512
+BIAS_K = 16                             # K of a bias chunk; K columns 0..2 carry the three fp16 terms
 
-# primitive micro-ops emitted by the lowering below (an intermediate form; `_select_ops` turns each
-# stage's primitive sequence into the streaming ops the kernel implements)
-TE_LOAD, TE_LOAD_SKIP, TE_LOAD_INPUT, TE_STORE_SKIP, TE_STORE_OUT = 1, 2, 3, 4, 5
-TE_STATS, TE_EMIT_LN, TE_EMIT_RAW, TE_EMIT_COND = 6, 7, 8, 9
-STATS_RESET, STATS_FINISH = 1, 2
 # streaming epilogue ops (mirror diffsg_b200/csrc/unet_tc.cuh).  Each walks its source in groups of
 # 16 columns; nothing but the current group lives in registers.
 OP_LN, OP_CATLN, OP_RAW_T, OP_RAW_S, OP_RAW_IN, OP_OUT = 1, 2, 3, 4, 5, 6
 F_TIME, F_COND, F_PUSH, F_DEFER = 1, 2, 4, 8
-NONE8 = 255
 
-EPI_DT = np.dtype([("kind", "u1"), ("np", "u1"), ("dt", "u1"), ("misc", "u1"), ("slot", "u1"), ("off0", "u1"),
-                   ("off1", "u1"), ("off2", "u1")])
+EPI_DT = np.dtype([("kind", "u1"), ("np", "u1"), ("dt", "u1"), ("misc", "u1"), ("slot", "u1"), ("off1", "u1"),
+                   ("tt_src4", "u2")])
 CHUNK_DT = np.dtype([("kw", "u2"), ("flags", "u2"), ("w_off16", "u4")])          # w_off16: offset / 16 bytes
 STAGE_DT = np.dtype([("chunk_begin", "u2"), ("epi_begin", "u2"), ("n_chunks", "u1"), ("n_epi", "u1"),
-                     ("n16", "u1"), ("bits", "u1"), ("pkg_off4", "u4"), ("tt_src4", "u2"), ("pkg_f4", "u1"),
-                     ("tt_f4", "u1")])
-CHUNK_COND = 1
+                     ("n16", "u1"), ("bits", "u1"), ("pkg_off4", "u4"), ("pkg_f4", "u2"), ("pad_", "u2")])
+CHUNK_COND, CHUNK_BIAS, CHUNK_TIME = 1, 2, 4
 assert EPI_DT.itemsize == 8 and CHUNK_DT.itemsize == 8 and STAGE_DT.itemsize == 16
 
 
@@ -78,128 +76,94 @@ class TcProgram:
     chunks: list = field(default_factory=list)
     epis: list = field(default_factory=list)
     wpieces: list = field(default_factory=list)     # (byte offset, n, npad, k, kw, fn -> [n, k] fp32 weight slice)
-    ppieces: list = field(default_factory=list)     # (float offset, n, fn -> flat fp32)
+    bpieces: list = field(default_factory=list)     # (byte offset, n, npad, fn -> [n] fp32 bias): static bias chunks
+    ppieces: list = field(default_factory=list)     # (float offset, n, fn -> flat fp32): LayerNorm gamma / beta
     w_bytes: int = 0
     n_params: int = 0
     skip_widths: list = field(default_factory=list)  # padded widths
-    time_blocks: list = field(default_factory=list)  # (t_off, time_emb Linear, lin1 Linear)
-    tt_stride: int = 0
+    time_blocks: list = field(default_factory=list)  # (t_off floats, img_off bytes, npad, time_emb Linear, lin1 Linear)
+    tt_stride: int = 0                               # floats per row of the fp32 time table
+    img_stride: int = 0                              # bytes per row of the step image table
     input_dim: int = 0
     cond_dim: int = 0
     nterms: int = 2
     _open: dict | None = None
 
-    # ---- per-stage parameter package
+    # ---- per-stage parameter package (LayerNorm gamma / beta)
     def vec(self, fn, n: int, npad: int) -> int:
         """Append a vector to the open stage's package; returns its float4 offset inside the package."""
         st = self._open
-        off = st["pkg_floats"]                      # offset inside the static (blob-resident) part
+        off = st["pkg_floats"]
         self.ppieces.append((st["pkg_off"] + off, n, fn))
-        st["pkg_floats"] += (npad + 3) & ~3
-        assert st["tt_floats"] + st["pkg_floats"] <= PKG_MAX_FLOATS, st
-        return (st["tt_floats"] + off) // 4         # shared-memory package = [time slice | static part]
+        st["pkg_floats"] += npad
+        assert npad % 16 == 0 and st["pkg_floats"] <= PKG_MAX_FLOATS, st
+        return off // 4
 
-    def time_slot(self, t_off: int, npad: int) -> int:
-        """Reserve package space that the TMA fills from time_table[step][t_off : t_off + npad]."""
-        st = self._open
-        assert st["tt_src"] is None and st["pkg_floats"] == 0, "the time slice must be the first package entry"
-        st["tt_src"], st["tt_floats"] = t_off, npad
-        return 0
-
-    def weight_chunk(self, fn, n: int, npad: int, k: int, kw: int) -> int:
-        off = self.w_bytes
-        self.wpieces.append((off, n, npad, k, kw, fn))
-        self.w_bytes += npad * kw * 2
+    def ln_params(self, norm_w, norm_b, width: int) -> int:
+        """gamma | beta (each padded with zeros: pad columns then come out of LayerNorm -> Swish as exact zeros)."""
+        dp = pad16(width)
+        off = self.vec(norm_w, width, dp)
+        self.vec(norm_b, width, dp)
         return off
 
     # ---- stage construction
     def begin_stage(self, n_out: int, region: int, accumulate: bool, has_gemm: bool = True):
         assert self._open is None
-        self._open = dict(chunk_begin=len(self.chunks), n16=pad16(n_out) // 16, region=region,
+        self._open = dict(chunk_begin=len(self.chunks), n16=pad16(n_out) // 16, region=region, n_out=n_out,
                           accumulate=int(accumulate), has_gemm=int(has_gemm), epi_begin=len(self.epis),
-                          pkg_off=self.n_params, pkg_floats=0, tt_src=None, tt_floats=0)
+                          pkg_off=self.n_params, pkg_floats=0, has_bias=False)
 
     def add_k_segment(self, weight_fn, n_out: int, k: int, cond: bool = False):
         """Append the K-chunks of one operand segment of width k (weight_fn() -> [n_out, k])."""
+        assert not self._open["has_bias"], "the bias chunk must be the last chunk of a GEMM group"
         npad, kp = pad16(n_out), pad16(k)
         for k0 in range(0, kp, CHUNK_K):
             kw = min(CHUNK_K, kp - k0)
             kreal = max(0, min(k - k0, kw))
-            off = self.weight_chunk(lambda k0=k0, kreal=kreal: weight_fn()[:, k0:k0 + kreal], n_out, npad, kreal, kw)
-            self.chunks.append(dict(kw=kw, flags=CHUNK_COND if cond else 0, w_off16=off // 16))
+            off = self.w_bytes
+            self.wpieces.append((off, n_out, npad, kreal, kw, lambda k0=k0, kreal=kreal: weight_fn()[:, k0:k0 + kreal]))
+            self.w_bytes += npad * kw * 2
+            self.chunks.append(dict(kw=kw, flags=CHUNK_COND if cond else 0, w_off16=off // 16, macs=n_out * kreal))
 
-    def epi(self, kind, width=16, dt=0, region=0, flags=0, slot=0, off0=NONE8, off1=NONE8, off2=NONE8):
-        self.epis.append(dict(kind=kind, np=pad16(width) // 8, dt=dt, region=region, flags=flags, slot=slot,
-                              off0=off0, off1=off1, off2=off2))
+    def add_bias(self, bias_fn):
+        """Close the GEMM group with a static bias chunk (image in the weight blob)."""
+        st = self._open
+        npad = st["n16"] * 16
+        off = self.w_bytes
+        self.bpieces.append((off, st["n_out"], npad, bias_fn))
+        self.w_bytes += npad * BIAS_K * 2
+        self.chunks.append(dict(kw=BIAS_K, flags=CHUNK_BIAS, w_off16=off // 16, macs=0))
+        st["has_bias"] = True
+
+    def add_time_bias(self, time_emb, lin1) -> int:
+        """Close the GEMM group with the per-step bias chunk lin1.bias + time_emb(.): one image per reverse step in
+        the step image table; returns the column offset of the same values in the fp32 time table."""
+        st = self._open
+        npad = st["n16"] * 16
+        t_off, img_off = self.tt_stride, self.img_stride
+        self.time_blocks.append((t_off, img_off, npad, time_emb, lin1))
+        self.tt_stride += npad
+        self.img_stride += npad * BIAS_K * 2
+        self.chunks.append(dict(kw=BIAS_K, flags=CHUNK_BIAS | CHUNK_TIME, w_off16=img_off // 16, macs=0))
+        st["has_bias"] = True
+        return t_off
+
+    def epi(self, kind, width, region=0, flags=0, slot=0, off1=0, tt_src=0):
+        assert 1 <= width <= MAX_W and tt_src % 4 == 0
+        self.epis.append(dict(kind=kind, np=pad16(width) // 8, dt=width, region=region, flags=flags, slot=slot,
+                              off1=off1, tt_src4=tt_src // 4))
 
     def end_stage(self):
         st = self._open
+        assert not st["has_gemm"] or st["has_bias"], "every GEMM group ends with its bias chunk"
         st["n_chunks"] = len(self.chunks) - st["chunk_begin"]
         st["n_epi"] = len(self.epis) - st["epi_begin"]
-        # shared-memory package = [time slice (from the per-step table row) | static part (blob)]
         self.n_params += st["pkg_floats"]
-        self._select_ops(st)
         self.stages.append(st)
         self._open = None
 
-    def _select_ops(self, st):
-        """Rewrite the stage's primitive op sequence into streaming ops."""
-        prim = self.epis[st["epi_begin"]:]
-        out, i = [], 0
-
-        def kind(j):
-            return prim[j]["kind"] if j < len(prim) else None
-
-        def op(k, src, **kw):
-            d = dict(kind=k, np=src["np"], dt=src["dt"], region=src.get("region", 0), flags=0, slot=0,
-                     off0=NONE8, off1=NONE8, off2=NONE8)
-            d.update(kw)
-            out.append(d)
-
-        while i < len(prim):
-            o = prim[i]
-            if o["kind"] == TE_LOAD_INPUT and kind(i + 1) == TE_EMIT_RAW:
-                op(OP_RAW_IN, o)
-                i += 2
-            elif o["kind"] == TE_LOAD_SKIP and kind(i + 1) == TE_EMIT_RAW:
-                op(OP_RAW_S, o, slot=o["slot"])
-                i += 2
-            elif o["kind"] == TE_LOAD:
-                j, flags, slot = i + 1, o["flags"] & F_TIME, 0
-                if kind(j) == TE_STORE_SKIP:
-                    flags, slot, j = flags | F_PUSH, prim[j]["slot"], j + 1
-                if kind(j) == TE_STORE_OUT:
-                    op(OP_OUT, o, off0=o["off0"])
-                    i = j + 1
-                elif kind(j) == TE_EMIT_RAW:
-                    op(OP_RAW_T, o, flags=flags, slot=slot, off0=o["off0"])
-                    i = j + 1
-                elif kind(j) == TE_STATS and prim[j]["flags"] == (STATS_RESET | STATS_FINISH) and kind(j + 1) == TE_EMIT_LN:
-                    ln = prim[j + 1]
-                    j += 2
-                    if kind(j) == TE_EMIT_COND:
-                        flags, j = flags | F_COND, j + 1
-                    op(OP_LN, o, flags=flags, slot=slot, off0=o["off0"], off1=ln["off0"], off2=ln["off1"])
-                    i = j
-                elif (kind(j) == TE_STATS and kind(j + 1) == TE_LOAD_SKIP and kind(j + 2) == TE_STATS
-                      and kind(j + 3) == TE_EMIT_LN and kind(j + 4) == TE_LOAD and kind(j + 5) == TE_EMIT_LN):
-                    sk, ln_s, ln_x = prim[j + 1], prim[j + 3], prim[j + 5]
-                    dp4 = o["np"] * 2
-                    # package order fixed by _emit_next: gamma_x, beta_x, gamma_s, beta_s (contiguous)
-                    assert ln_x["off1"] == ln_x["off0"] + dp4 and ln_s["off0"] == ln_x["off0"] + 2 * dp4 \
-                        and ln_s["off1"] == ln_x["off0"] + 3 * dp4 and sk["np"] == o["np"]
-                    assert not (flags & F_PUSH)
-                    op(OP_CATLN, o, flags=flags, slot=sk["slot"], off0=o["off0"], off1=ln_x["off0"])
-                    i = j + 6
-                else:
-                    raise AssertionError(f"no streaming op for primitive sequence at {i}: {[q['kind'] for q in prim]}")
-            else:
-                raise AssertionError(f"no streaming op for primitive sequence at {i}: {[q['kind'] for q in prim]}")
-        self.epis[st["epi_begin"]:] = out
-        st["n_epi"] = len(out)
-
     def mark_deferred(self):
-        """An LN whose source region is overwritten by the NEXT stage's GEMM must not let that GEMM
+        """An op whose source region is overwritten by the NEXT stage's GEMM must not let that GEMM
         start before the source has been read completely: its operand chunks are published at the end."""
         for a, b in zip(self.stages, self.stages[1:]):
             if not b["has_gemm"]:
@@ -207,58 +171,49 @@ class TcProgram:
             for o in self.epis[a["epi_begin"]:a["epi_begin"] + a["n_epi"]]:
                 if o["kind"] in (OP_LN, OP_RAW_T) and o["region"] == b["region"]:
                     o["flags"] |= F_DEFER
+                assert not (o["kind"] == OP_CATLN and o["region"] == b["region"]), "cat-LN source overwritten by the next GEMM"
 
     # ---- arrays for the C-ABI
     def arrays(self):
         s = np.zeros(len(self.stages), STAGE_DT)
         for i, d in enumerate(self.stages):
             s[i] = (d["chunk_begin"], d["epi_begin"], d["n_chunks"], d["n_epi"], d["n16"],
-                    d["region"] | (d["accumulate"] << 1) | (d["has_gemm"] << 2) | ((d["tt_src"] is not None) << 3),
-                    d["pkg_off"] // 4, (d["tt_src"] or 0) // 4, d["pkg_floats"] // 4, d["tt_floats"] // 4)
+                    d["region"] | (d["accumulate"] << 1) | (d["has_gemm"] << 2),
+                    d["pkg_off"] // 4, d["pkg_floats"] // 4, 0)
         c = np.zeros(len(self.chunks), CHUNK_DT)
         for i, d in enumerate(self.chunks):
             c[i] = (d["kw"], d["flags"], d["w_off16"])
         e = np.zeros(len(self.epis), EPI_DT)
         for i, d in enumerate(self.epis):
-            e[i] = (d["kind"], d["np"], d["dt"], d["region"] | (d["flags"] << 1), d["slot"], d["off0"], d["off1"], d["off2"])
+            e[i] = (d["kind"], d["np"], d["dt"], d["region"] | (d["flags"] << 1), d["slot"], d["off1"], d["tt_src4"])
         return s, c, e
 
     def gemm_macs(self):
-        """(x-path, cond) algorithmic MACs per row-forward from the un-padded shapes."""
-        x = c = 0
-        for (_, n, _, k, _, _), ch in zip(self.wpieces, self.chunks):
-            if ch["flags"] & CHUNK_COND:
-                c += n * k
-            else:
-                x += n * k
+        """(x-path, cond) algorithmic MACs per row-forward from the un-padded shapes (biases are not MACs)."""
+        x = sum(ch["macs"] for ch in self.chunks if not ch["flags"] & CHUNK_COND)
+        c = sum(ch["macs"] for ch in self.chunks if ch["flags"] & CHUNK_COND)
         return x, c
 
 
-def _emit_next(p: TcProgram, plan, xr, xb_off4, width):
-    """Epilogue tail shared by every stage that ends with a finished activation x (in region xr,
-    cumulative bias at package offset xb_off4): what it must EMIT depends on the module that consumes x next."""
-    dp = pad16(width)
+def _emit_next(p: TcProgram, plan, xr, width, push_slot=None):
+    """Epilogue of every stage that ends with a finished activation x (in TMEM region xr, bias included): what it
+    must EMIT depends on the module that consumes x next; `push_slot`: x is also a skip (spilled with its moments)."""
     kind = plan[0]
+    flags = F_PUSH if push_slot is not None else 0
+    slot = push_slot if push_slot is not None else 0
     if kind in ("res", "final"):   # identity-shortcut ResidualBlock / output head: LN -> Swish
         norm = plan[1].norm1 if kind == "res" else plan[1]
-        p.epi(TE_STATS, width=dp, dt=width, flags=STATS_RESET | STATS_FINISH)
-        g = p.vec(lambda: norm.weight, width, dp)
-        b = p.vec(lambda: norm.bias, width, dp)
-        p.epi(TE_EMIT_LN, width=dp, dt=width, off0=g, off1=b)
-    elif kind == "raw":            # Down/Upsample Linear consumes x itself
-        p.epi(TE_EMIT_RAW, width=dp, dt=width)
+        off = p.ln_params(lambda: norm.weight, lambda: norm.bias, width)
+        p.epi(OP_LN, width, region=xr, flags=flags, slot=slot, off1=off)
+    elif kind == "raw":            # Down/Upsample Linear (or the fused attention matrix) consumes x itself
+        p.epi(OP_RAW_T, width, region=xr, flags=flags, slot=slot)
     elif kind == "up":             # UpBlock: LN1 over cat(x, skip); chunks: skip part, then x part
-        blk, slot = plan[1], plan[2]
-        g_x = p.vec(lambda: blk.norm1.weight[:width], width, dp)
-        b_x = p.vec(lambda: blk.norm1.bias[:width], width, dp)
-        g_s = p.vec(lambda: blk.norm1.weight[width:], width, dp)
-        b_s = p.vec(lambda: blk.norm1.bias[width:], width, dp)
-        p.epi(TE_STATS, width=dp, dt=width, flags=STATS_RESET)
-        p.epi(TE_LOAD_SKIP, width=dp, dt=width, slot=slot)
-        p.epi(TE_STATS, width=dp, dt=width, flags=STATS_FINISH)
-        p.epi(TE_EMIT_LN, width=dp, dt=width, off0=g_s, off1=b_s)
-        p.epi(TE_LOAD, width=dp, dt=width, region=xr, off0=xb_off4)
-        p.epi(TE_EMIT_LN, width=dp, dt=width, off0=g_x, off1=b_x)
+        blk, pop = plan[1], plan[2]
+        assert push_slot is None and blk.in_dim == 2 * width and p.skip_widths[pop] == pad16(width), \
+            "cat LayerNorm expects a skip as wide as x"
+        off = p.ln_params(lambda: blk.norm1.weight[:width], lambda: blk.norm1.bias[:width], width)
+        p.ln_params(lambda: blk.norm1.weight[width:], lambda: blk.norm1.bias[width:], width)
+        p.epi(OP_CATLN, width, region=xr, slot=pop, off1=off)
     else:
         raise ValueError(kind)
 
@@ -316,14 +271,22 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             return ("up", mod, pop_slot[i])
         return ("final", model.norm)
 
-    def sum_fn(fns):
-        fns = tuple(fns)
-        return lambda: sum(f() for f in fns)
+    slot = 0
+
+    def finish(i_next, xr, width, push):
+        """Close the stage that produced x: push it if it is a skip, emit what its consumer needs."""
+        nonlocal slot
+        push_slot = None
+        if push:
+            p.skip_widths.append(pad16(width))
+            push_slot = slot
+            slot += 1
+        _emit_next(p, consumer_plan(i_next), xr, width, push_slot)
+        p.end_stage()
 
     # ---- stage 0: operand of feature_proj = the raw input row
     p.begin_stage(16, 0, False, has_gemm=False)
-    p.epi(TE_LOAD_INPUT, width=pad16(M), dt=M)
-    p.epi(TE_EMIT_RAW, width=pad16(M), dt=M)
+    p.epi(OP_RAW_IN, M)
     p.end_stage()
 
     # ---- feature_proj
@@ -332,37 +295,21 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
     xr = 0
     p.begin_stage(width, xr, False)
     p.add_k_segment(lambda: fp.weight, width, M)
-    xb = [lambda: fp.bias]                 # bias terms summed into the cumulative vector of x
-    xoff = p.vec(sum_fn(xb), width, pad16(width))
-    p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
-    slot = 0
-    p.skip_widths.append(pad16(width))
-    p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
-    _emit_next(p, consumer_plan(0), xr, xoff, width)
-    p.end_stage()
-    slot += 1
+    p.add_bias(lambda: fp.bias)
+    finish(0, xr, width, True)
 
     for i, (kind, mod) in enumerate(seq):
-        nxt = consumer_plan(i + 1) if i + 1 < len(seq) else None
         if kind == "lin":
             lin = mod
-            hr = 1 - xr
-            p.begin_stage(lin.out_features, hr, False)
+            xr = 1 - xr
+            p.begin_stage(lin.out_features, xr, False)
             p.add_k_segment(lambda lin=lin: lin.weight, lin.out_features, lin.in_features)
+            p.add_bias(lambda lin=lin: lin.bias)
             width = lin.out_features
-            xr = hr
-            xb = [lambda lin=lin: lin.bias]
-            xoff = p.vec(sum_fn(xb), width, pad16(width))
-            p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
-            if pushes[i]:
-                p.skip_widths.append(pad16(width))
-                p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
-                slot += 1
-            _emit_next(p, nxt, xr, xoff, width)
-            p.end_stage()
+            finish(i + 1, xr, width, pushes[i])
         elif kind == "attn":
             # x' = x + output(V(x)) (the reference's length-1 sequence makes softmax == 1, UNetCF.py:123-157):
-            # ONE accumulate stage with the host-fused matrix output.weight . V.weight, bias folded into xb
+            # ONE accumulate stage with the host-fused matrix output.weight . V.weight and the fused bias
             att = mod
             dk, nh = att.d_k, att.n_heads
 
@@ -372,55 +319,35 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
             p.begin_stage(width, xr, True)
             p.add_k_segment(lambda att=att, vr=v_rows: att.output.weight.double().matmul(att.projection.weight[vr()].double()).float(),
                             width, width)
-            xb = xb + [lambda att=att, vr=v_rows: (att.output.weight.double().matmul(att.projection.bias[vr()].double())
-                                                   + att.output.bias.double()).float()]
-            xoff = p.vec(sum_fn(xb), width, pad16(width))
-            p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
-            if pushes[i]:
-                p.skip_widths.append(pad16(width))
-                p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
-                slot += 1
-            _emit_next(p, nxt, xr, xoff, width)
-            p.end_stage()
+            p.add_bias(lambda att=att, vr=v_rows: (att.output.weight.double().matmul(att.projection.bias[vr()].double())
+                                                   + att.output.bias.double()).float())
+            finish(i + 1, xr, width, pushes[i])
         elif kind in ("down_res", "mid_res", "up_res"):
             blk: ResidualBlock = mod
             dout = blk.out_dim
-            dp = pad16(dout)
             hr = 1 - xr
             is_up = kind == "up_res"
-            t_off = p.tt_stride
-            p.time_blocks.append((t_off, blk.time_emb, blk.lin1))
-            p.tt_stride += dp
-            # ---- G1: h = lin1(a1) + [b1 + time]  (bias = the per-step table slice)
+            # ---- G1: h = lin1(a1) + [b1 + time]  (bias chunk = this step's image of the time table)
             p.begin_stage(dout, hr, False)
             if is_up:   # K order: skip part (cat columns [width:]) then x part (cat columns [:width])
                 p.add_k_segment(lambda blk=blk, w=width: blk.lin1.weight[:, w:], dout, blk.in_dim - width)
                 p.add_k_segment(lambda blk=blk, w=width: blk.lin1.weight[:, :w], dout, width)
             else:
                 p.add_k_segment(lambda blk=blk: blk.lin1.weight, dout, blk.in_dim)
-            p.epi(TE_LOAD, width=dout, dt=dout, region=hr, flags=F_TIME, off0=p.time_slot(t_off, dp))
-            p.epi(TE_STATS, width=dout, dt=dout, flags=STATS_RESET | STATS_FINISH)
-            g = p.vec(lambda blk=blk: blk.norm2.weight, dout, dp)
-            b = p.vec(lambda blk=blk: blk.norm2.bias, dout, dp)
-            p.epi(TE_EMIT_LN, width=dout, dt=dout, off0=g, off1=b)
-            p.epi(TE_EMIT_COND)
+            t_off = p.add_time_bias(blk.time_emb, blk.lin1)
+            off = p.ln_params(lambda blk=blk: blk.norm2.weight, lambda blk=blk: blk.norm2.bias, dout)
+            p.epi(OP_LN, dout, region=hr, flags=F_TIME | F_COND, off1=off, tt_src=t_off)
             p.end_stage()
-            # ---- G2: h = lin2(a2) + b2 + cond_emb(swish(cond))
+            # ---- G2: h = lin2(a2) + b2 + cond_emb(swish(cond))   (uncond pass: Swish(0) = 0 -> the bias alone)
             p.begin_stage(dout, hr, False)
             p.add_k_segment(lambda blk=blk: blk.lin2.weight, dout, dout)
             p.add_k_segment(lambda blk=blk: blk.cond_emb.weight, dout, C, cond=True)
-            b2 = p.vec(lambda blk=blk: blk.lin2.bias + blk.cond_emb.bias, dout, dp)
-            p.epi(TE_LOAD, width=dout, dt=dout, region=hr, off0=b2)
-            p.epi(TE_STATS, width=dout, dt=dout, flags=STATS_RESET | STATS_FINISH)
-            g = p.vec(lambda blk=blk: blk.norm3.weight, dout, dp)
-            b = p.vec(lambda blk=blk: blk.norm3.bias, dout, dp)
-            p.epi(TE_EMIT_LN, width=dout, dt=dout, off0=g, off1=b)
+            p.add_bias(lambda blk=blk: blk.lin2.bias + blk.cond_emb.bias)
+            off = p.ln_params(lambda blk=blk: blk.norm3.weight, lambda blk=blk: blk.norm3.bias, dout)
+            p.epi(OP_LN, dout, region=hr, off1=off)
             if is_up:   # raw operands of the shortcut Linear: x part, then skip part
-                sw = blk.in_dim - width
-                p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=p.vec(sum_fn(xb), width, pad16(width)))
-                p.epi(TE_EMIT_RAW, width=width, dt=width)
-                p.epi(TE_LOAD_SKIP, width=sw, dt=sw, slot=pop_slot[i])
-                p.epi(TE_EMIT_RAW, width=sw, dt=sw)
+                p.epi(OP_RAW_T, width, region=xr)
+                p.epi(OP_RAW_S, blk.in_dim - width, slot=pop_slot[i])
             p.end_stage()
             # ---- G3: x' = lin3(a3) + b3 + shortcut(x)
             if is_up:
@@ -428,37 +355,56 @@ def lower_tc(model: UNet1D, nterms: int = 2) -> TcProgram:
                 p.add_k_segment(lambda blk=blk: blk.lin3.weight, dout, dout)
                 p.add_k_segment(lambda blk=blk, w=width: blk.shortcut.weight[:, :w], dout, width)
                 p.add_k_segment(lambda blk=blk, w=width: blk.shortcut.weight[:, w:], dout, blk.in_dim - width)
+                p.add_bias(lambda blk=blk: blk.lin3.bias + blk.shortcut.bias)
                 xr = hr
-                xb = [lambda blk=blk: blk.lin3.bias, lambda blk=blk: blk.shortcut.bias]
             else:
                 assert isinstance(blk.shortcut, nn.Identity) and blk.in_dim == dout
-                p.begin_stage(dout, xr, True)
+                p.begin_stage(dout, xr, True)      # the residual add is the MMA accumulating into x's own region
                 p.add_k_segment(lambda blk=blk: blk.lin3.weight, dout, dout)
-                xb = xb + [lambda blk=blk: blk.lin3.bias]
+                p.add_bias(lambda blk=blk: blk.lin3.bias)
             width = dout
-            xoff = p.vec(sum_fn(xb), width, dp)
-            p.epi(TE_LOAD, width=width, dt=width, region=xr, off0=xoff)
-            if pushes[i]:
-                p.skip_widths.append(dp)
-                p.epi(TE_STORE_SKIP, width=width, dt=width, slot=slot)
-                slot += 1
-            _emit_next(p, nxt, xr, xoff, width)
-            p.end_stage()
+            finish(i + 1, xr, width, pushes[i])
         elif kind == "final":
             fin = model.final
             hr = 1 - xr
             p.begin_stage(M, hr, False)
             p.add_k_segment(lambda: fin.weight, M, fin.in_features)
-            p.epi(TE_LOAD, width=M, dt=M, region=hr, off0=p.vec(lambda: fin.bias, M, pad16(M)))
-            p.epi(TE_STORE_OUT, width=M, dt=M)
+            p.add_bias(lambda: fin.bias)
+            p.epi(OP_OUT, M, region=hr)
             p.end_stage()
     assert slot == n_push, (slot, n_push)
     p.mark_deferred()
     return p
 
 
+def _w_image(t: torch.Tensor, npad: int, kw: int) -> torch.Tensor:
+    """[npad, kw] -> UMMA K-major no-swizzle core-matrix order [n/8][k/8][n%8][8], flat."""
+    return t.reshape(npad // 8, 8, kw // 8, 8).permute(0, 2, 1, 3).reshape(-1)
+
+
+def split3(b: torch.Tensor):
+    """fp32 -> three fp16 terms with b == h0 + h1 + h2 up to 2^-33 |b| (and >= 2^-25 absolute: fp16 subnormals)."""
+    h0 = b.to(torch.float16)
+    r1 = b - h0.to(torch.float32)
+    h1 = r1.to(torch.float16)
+    h2 = (r1 - h1.to(torch.float32)).to(torch.float16)
+    return h0, h1, h2
+
+
+def bias_image(b: torch.Tensor, npad: int) -> torch.Tensor:
+    """Bias vectors [..., n] -> bias-chunk images [..., npad * 16] fp16: W rows of a K = 16 chunk whose K columns
+    0..2 hold the three fp16 terms (the kernel's constant A tile has ones exactly there)."""
+    lead = b.shape[:-1]
+    v = torch.zeros(*lead, npad, dtype=torch.float32, device=b.device)
+    v[..., :b.shape[-1]] = b.to(torch.float32)
+    img = torch.zeros(*lead, npad // 8, BIAS_K // 8, 8, 8, dtype=torch.float16, device=b.device)
+    for j, h in enumerate(split3(v)):
+        img[..., 0, :, j] = h.reshape(*lead, npad // 8, 8)
+    return img.reshape(*lead, npad * BIAS_K)
+
+
 def pack_tc_weights(p: TcProgram, device):
-    """-> (w_hi fp16 blob, w_lo fp16 blob or None, params fp32 blob) on `device`."""
+    """-> (w_hi fp16 blob incl. the static bias images, w_lo fp16 blob or None, LayerNorm params fp32 blob) on `device`."""
     with torch.no_grad():
         hi = torch.zeros(max(p.w_bytes // 2, 8), dtype=torch.float16, device=device)
         lo = torch.zeros_like(hi) if p.nterms >= 3 else None
@@ -467,10 +413,11 @@ def pack_tc_weights(p: TcProgram, device):
             if k > 0:
                 w[:n, :k] = fn().detach().to(device=device, dtype=torch.float32)
             wh = w.to(torch.float16)
-            img = lambda t: t.reshape(npad // 8, 8, kw // 8, 8).permute(0, 2, 1, 3).reshape(-1)
-            hi[off // 2:off // 2 + npad * kw] = img(wh)
+            hi[off // 2:off // 2 + npad * kw] = _w_image(wh, npad, kw)
             if lo is not None:
-                lo[off // 2:off // 2 + npad * kw] = img((w - wh.to(torch.float32)).to(torch.float16))
+                lo[off // 2:off // 2 + npad * kw] = _w_image((w - wh.to(torch.float32)).to(torch.float16), npad, kw)
+        for off, n, npad, fn in p.bpieces:
+            hi[off // 2:off // 2 + npad * BIAS_K] = bias_image(fn().detach().to(device=device, dtype=torch.float32).reshape(-1), npad)
         params = torch.zeros(max(p.n_params, 4), dtype=torch.float32, device=device)
         for off, n, fn in p.ppieces:
             params[off:off + n] = fn().detach().to(device=device, dtype=torch.float32).reshape(-1)
@@ -488,6 +435,16 @@ def time_table_tc(model: UNet1D, p: TcProgram, t_values: torch.Tensor) -> torch.
         e = F.linear(_swish(F.linear(e, te.lin1.weight, te.lin1.bias)), te.lin2.weight, te.lin2.bias)
         a = _swish(e)
         tab = torch.zeros(a.shape[0], max(p.tt_stride, 4), dtype=torch.float32, device=a.device)
-        for t_off, lin, lin1 in p.time_blocks:
+        for t_off, _, _, lin, lin1 in p.time_blocks:
             tab[:, t_off:t_off + lin.out_features] = F.linear(a, lin.weight, lin.bias) + lin1.bias
     return tab.contiguous()
+
+
+def time_images(p: TcProgram, table: torch.Tensor) -> torch.Tensor:
+    """fp32 time table [R, tt_stride] -> step image table [R, img_stride / 2] fp16: per block the bias-chunk image
+    of that row's slice (what the sampler's TMA warp streams as the last chunk of every lin1 GEMM group)."""
+    with torch.no_grad():
+        img = torch.zeros(table.shape[0], max(p.img_stride // 2, 8), dtype=torch.float16, device=table.device)
+        for t_off, img_off, npad, _, _ in p.time_blocks:
+            img[:, img_off // 2:img_off // 2 + npad * BIAS_K] = bias_image(table[:, t_off:t_off + npad], npad)
+    return img.contiguous()

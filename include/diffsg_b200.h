@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DIFFSG_ABI_VERSION 1
+#define DIFFSG_ABI_VERSION 2
 
 enum {
     DIFFSG_OK = 0,
@@ -178,7 +178,7 @@ enum { DIFFSG_ENGINE_SIMT = 0, DIFFSG_ENGINE_TC = 1 };
 typedef struct diffsg_tc_program {
     const void* stages;        /* n_stages x 16-byte records                                  */
     const void* chunks;        /* n_chunks x  8-byte records                                  */
-    const void* epis;          /* n_epi    x 16-byte records                                  */
+    const void* epis;          /* n_epi    x  8-byte records                                  */
     const int32_t* skip_widths;/* n_skip padded widths (multiples of 16)                      */
     int32_t n_stages, n_chunks, n_epi, n_skip;
     int32_t nterms;            /* 2: (A_hi + A_lo) . W_fp16;  3: + A_hi . W_lo                */
@@ -189,18 +189,32 @@ typedef struct diffsg_tc_program {
 /* Attach the tensor-core program to a plan (fails with DIFFSG_E_UNSUPPORTED if the topology is
  * outside the engine's limits; the plan then keeps running on the fp32 engine). */
 int diffsg_plan_attach_tc(diffsg_plan* plan, const diffsg_tc_program* prog);
-/* fp16 weight images (w_lo_dev may be NULL when nterms == 2), fp32 side parameters and the
- * hoisted time table of the tensor-core program. */
+/* fp16 weight + static bias-chunk images (w_lo_dev may be NULL when nterms == 2), the fp32 LayerNorm
+ * gamma / beta packages, and the hoisted time path of the tensor-core program in two forms:
+ *   time_table_dev  fp32 [tt_rows][tt_stride]: lin1.bias + time embedding per block; read per row by
+ *                   diffsg_unet_forward (rows carry arbitrary time indices).  May be NULL for sampling only.
+ *   time_img_dev    fp16 [img_rows][img_stride_bytes]: the same rows as K = 16 bias-chunk images (three fp16
+ *                   terms per value), streamed by the sampler, row = reverse step.  May be NULL for forward only. */
 int diffsg_plan_set_tc_weights(diffsg_plan* plan, const void* w_hi_dev, const void* w_lo_dev,
                                size_t w_bytes, const float* params_dev, size_t n_params,
-                               const float* time_table_dev, int32_t tt_rows);
+                               const float* time_table_dev, int32_t tt_rows, const void* time_img_dev,
+                               int32_t img_rows, int64_t img_stride_bytes);
+/* Sticky status bits raised on the device by the tensor-core kernels of this plan since the last reset:
+ *   DIFFSG_STATUS_FP16_OVERFLOW  a raw (un-normalised) operand row -- y_t, the residual stream into a Down/Upsample
+ *                                or shortcut Linear -- exceeded the fp16 range (|x| > 65504): the fp16-split engines
+ *                                saturate it, so results of that call are NOT within tolerance of the fp32 reference;
+ *                                re-run with precision "fp32".
+ * This call synchronises `stream` (it reads one word back). */
+#define DIFFSG_STATUS_FP16_OVERFLOW 1
+int diffsg_plan_status(diffsg_plan* plan, int32_t* flags_out, int32_t reset, void* stream);
 /* Select the engine used by diffsg_unet_forward / diffsg_sample. */
 int diffsg_plan_set_engine(diffsg_plan* plan, int32_t engine);
 
 /* Introspection: what = 0 engine, 1 tensor-core CTAs resident per SM, 2 its dynamic shared memory per CTA
  * (bytes), 3 its maximum grid, 4 nterms, 5 warps per CTA of the fp32 engine, 6 / 7 the K columns per operand
  * chunk and the TMEM columns per accumulator region this library was BUILT for (the program handed to
- * diffsg_plan_attach_tc must be lowered for the same values).  Returns -1 when not applicable. */
+ * diffsg_plan_attach_tc must be lowered for the same values), 8 the tensor-core engine's global scratch per
+ * CTA in bytes.  Returns -1 when not applicable. */
 int diffsg_plan_query(const diffsg_plan* plan, int32_t what);
 
 /* Number of kernel launches issued by this library (process-wide) since the last reset

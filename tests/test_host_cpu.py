@@ -221,8 +221,9 @@ def test_c_abi_exports_every_declared_symbol():
 
 @pytest.mark.parametrize("name", ["nu_like", "msr3c", "msr80c", "co", "attn"])
 def test_tc_program_matches_oracle(name):
-    """tc_packer: stage/chunk/epilogue lowering, fp16 weight images (x3 -> ~fp32), cumulative biases,
-    cat-free UpBlocks, merged lin3+shortcut GEMM groups — interpreted on the CPU."""
+    """tc_packer: stage/chunk/epilogue lowering, fp16 weight images (x3 -> ~fp32), biases as K = 16 chunks on a
+    constant ones tile (static images + per-step time images), cat-free UpBlocks with the skip moments stored at
+    push time, merged lin3+shortcut GEMM groups — interpreted on the CPU."""
     from diffsg_b200 import tc_packer
     from tc_interp import run_tc_program
     g = load_golden(f"standin_{name}.npz")
@@ -232,11 +233,26 @@ def test_tc_program_matches_oracle(name):
     table = tc_packer.time_table_tc(ddpm.model, prog, torch.arange(T) / T)
     x, cond, mask = (torch.tensor(g[k]) for k in ("x", "cond", "mask"))
     ts = torch.tensor(g["ts"]).reshape(-1)
-    eps = run_tc_program(prog, hi, lo, params, table, x, ts, cond, mask)
+    eps = run_tc_program(prog, hi, lo, params, table, x, ts, cond, mask)          # forward mode: fp32 table rows
     assert rel_l2(eps, g["eps"]) < 5e-6
+    images = tc_packer.time_images(prog, table)                                    # sampler mode: time-bias chunk images
+    assert images.shape == (T, prog.img_stride // 2) and prog.img_stride % 16 == 0
+    for step in sorted(set(ts.tolist()))[:3]:
+        sel = ts == step
+        eps_s = run_tc_program(prog, hi, lo, params, table, x[sel], ts[sel], cond[sel], mask[sel], images=images)
+        assert rel_l2(eps_s, g["eps"][sel.numpy()]) < 5e-6
     st, ch, ep = prog.arrays()
     assert ch.dtype.itemsize == 8 and ep.dtype.itemsize == 8
-    assert len(st) <= 128 and len(ch) <= 224 and len(ep) <= 384 and st.dtype.itemsize == 16
+    assert len(st) <= 256 and len(ch) <= 640 and len(ep) <= 512 and st.dtype.itemsize == 16      # kMax* of unet_tc.cuh
+    # every GEMM group ends with exactly one bias chunk; the three fp16 terms reproduce the fp32 bias to 2^-30
+    for sdict in prog.stages:
+        fl = [c["flags"] for c in prog.chunks[sdict["chunk_begin"]:sdict["chunk_begin"] + sdict["n_chunks"]]]
+        assert not sdict["has_gemm"] or (fl[-1] & tc_packer.CHUNK_BIAS and not any(f & tc_packer.CHUNK_BIAS for f in fl[:-1]))
+    b = torch.randn(3, 40) * torch.tensor([1e-6, 1.0, 300.0])[:, None]
+    img = tc_packer.bias_image(b, 48).float().reshape(3, 6, 2, 8, 8)
+    back = img[:, :, 0, :, :3].sum(-1).reshape(3, 48)
+    assert torch.all((back[:, :40] - b).abs() <= b.abs() * 2.0 ** -30 + 2.0 ** -25) and torch.all(back[:, 40:] == 0)
+    assert torch.all(img[:, :, 1] == 0) and torch.all(img[:, :, 0, :, 3:] == 0)
     expect = {"msr3c": (546688, 3768), "msr80c": (566400, 100480), "co": (329024, 11736), "nu_like": (60864, 2736)}
     if name in expect:
         assert prog.gemm_macs() == expect[name]
