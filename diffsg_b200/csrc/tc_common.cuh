@@ -42,6 +42,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Tight spin with a short back-off: for the one wait that sits on a tile's critical path (the MMA thread waiting
+// for the operand chunk the epilogue is about to publish).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+}
 // Producer-side wait (TMA / MMA threads): let the hardware park the thread for up to `ns` per probe
 // instead of spinning, so the waiting warp does not steal issue slots from the epilogue warp that
 // shares its scheduler.

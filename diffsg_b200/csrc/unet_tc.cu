@@ -207,13 +207,12 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
         }
     }
     for (int i = 0; i < g->n_chunks; ++i)
-        if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16 || ((ch[i].flags & kChunkBias) && ch[i].kw != kBiasK) ||
-            ((ch[i].flags & kChunkTime) && !(ch[i].flags & kChunkBias))) {
-            set_error("attach_tc: chunk %d kw=%d flags=%d", i, ch[i].kw, ch[i].flags); return DIFFSG_E_INVALID;
-        }
-    for (int i = 0; i < g->n_stages; ++i) {      // the bias chunk must be the LAST chunk of its GEMM group (see unet_tc.cuh)
-        for (int c = st[i].chunk_begin; c + 1 < st[i].chunk_begin + st[i].n_chunks; ++c)
-            if (ch[c].flags & kChunkBias) { set_error("attach_tc: stage %d: bias chunk is not last", i); return DIFFSG_E_INVALID; }
+        if (ch[i].kw == 0 || ch[i].kw > kChunkK || ch[i].kw % 16) { set_error("attach_tc: chunk %d kw=%d", i, ch[i].kw); return DIFFSG_E_INVALID; }
+    for (int i = 0; i < g->n_stages; ++i) {      // a GEMM group needs at least one chunk that is issued in every pass
+        if (!(st[i].bits & 4)) continue;
+        bool any = false;
+        for (int c = st[i].chunk_begin; c < st[i].chunk_begin + st[i].n_chunks; ++c) any = any || !(ch[c].flags & kChunkCond);
+        if (!any) { set_error("attach_tc: stage %d has no unconditional chunk", i); return DIFFSG_E_INVALID; }
     }
     for (int i = 0; i < g->n_epi; ++i) {
         const Epi& e = ep[i];
@@ -245,7 +244,7 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     D.stats_off = (int)off; off += (size_t)(g->n_skip > 0 ? g->n_skip : 1) * kRows * 4;   // (s1, s2, shift, -) per pushed row
     D.scratch_floats = (off + 31) & ~size_t(31);
     const int w_terms = g->nterms == 3 ? 2 : 1;
-    h->smem_bytes = 128 + ((sizeof(SmemLayout) + 127) & ~size_t(127)) + (size_t)kWStages * w_terms * kWStageBytes;
+    h->smem_bytes = 128 + ((sizeof(SmemLayout) + 127) & ~size_t(127)) + (size_t)kWStages * (w_terms * kWStageBytes + kBiasBytes);
     // fp16x2 fits two CTAs (tiles) per SM: 2 x (<= 113 KB smem, 256 TMEM columns, 30 K registers)
     h->grid_max = p->sm_count;
     if ((int)h->smem_bytes > p->max_smem) { set_error("attach_tc: needs %zu B shared memory", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }

@@ -14,9 +14,10 @@
 //   warp 5        MMA issuer: one thread issues tcgen05.mma (A, W from shared memory, fp32 accumulators in
 //                 TMEM) and commits completion to mbarriers
 //
-// Biases never touch the CUDA cores: every GEMM group ends with a K = 16 "bias chunk" whose A operand is a
+// Biases never touch the CUDA cores: every GEMM group ends with one K = 16 "bias MMA" whose A operand is a
 // constant tile of ones (columns 0..2) and whose W rows hold the bias as three fp16 terms (hi, mid, lo), so
-// the accumulator already contains `x = W a + b` when the epilogue reads it.
+// the accumulator already contains `x = W a + b` when the epilogue reads it.  The bias image travels with the
+// group's last weight chunk (same W-ring stage, one barrier).
 //
 // Program format: diffsg_b200/tc_packer.py.  Reference semantics: ddpm_opt/UNetCF.py:83-95,
 // :318-356; sampler: ddpm_opt/classifier_free_MSR.py:124-137.
@@ -34,8 +35,9 @@ constexpr int kASlots = 2;
 constexpr int kWStages = 2;
 constexpr int kRegionCols = 128;                     // widest vector the engine carries
 constexpr int kWStageBytes = kRegionCols * kChunkK * 2;   // one fp16 W chunk (N <= kRegionCols)
-constexpr int kBiasK = 16;                           // K of a bias chunk (one MMA)
-constexpr int kOnesBytes = kRows * kBiasK * 2;       // the constant A tile of the bias chunks
+constexpr int kBiasK = 16;                           // K of the bias MMA
+constexpr int kBiasBytes = kRegionCols * kBiasK * 2; // bias image of one GEMM group (rides behind its last weight chunk)
+constexpr int kOnesBytes = kRows * kBiasK * 2;       // the constant A tile of the bias MMAs
 constexpr int kCtasPerSm = 2;
 constexpr int kEpiWarps = 4, kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = kEpiThreads + 64;           // + TMA warp + MMA warp
@@ -45,7 +47,7 @@ constexpr int kPkgFloats = 512, kPSlots = 2;         // gamma | beta (x2 for a c
 
 // streaming epilogue ops (diffsg_b200/tc_packer.py)
 enum : int { OP_LN = 1, OP_CATLN, OP_RAW_T, OP_RAW_S, OP_RAW_IN, OP_OUT };
-constexpr int kChunkCond = 1, kChunkBias = 2, kChunkTime = 4;
+constexpr int kChunkCond = 1;
 constexpr int kFTime = 1, kFCond = 2, kFPush = 4, kFDefer = 8;
 constexpr int kStatusOverflow = 1;                   // a raw fp16 operand exceeded the fp16 range
 
@@ -53,9 +55,10 @@ struct __align__(8) Epi { uint8_t kind, np, dt, misc, slot, off1; uint16_t tt_sr
 struct __align__(8) Chunk { uint16_t kw, flags; uint32_t w_off16; };
 struct __align__(16) Stage {
     uint16_t chunk_begin, epi_begin;
-    uint8_t n_chunks, n_epi, n16, bits;          // bits: region | accumulate << 1 | has_gemm << 2
-    uint32_t pkg_off4;
-    uint16_t pkg_f4, pad_;
+    uint8_t n_chunks, n_epi, n16, bits;          // bits: region | accumulate << 1 | has_gemm << 2 | time_bias << 3
+    uint16_t pkg_off16;                          // LayerNorm package: offset (x 16 floats) and size (x 4 floats)
+    uint8_t pkg_f4, pad_;
+    uint32_t bias_off16;                         // bias image (x 16 bytes): in the weight blob, or in a step-image row
 };
 static_assert(sizeof(Epi) == 8 && sizeof(Chunk) == 8 && sizeof(Stage) == 16, "program record layout");
 
@@ -88,9 +91,9 @@ struct SmemLayout {
     uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], p_full[kPSlots],
         p_empty[kPSlots], acc_full;
     uint32_t tmem_base, pad_;
-    // followed by the W ring: kWStages * (nterms == 3 ? 2 : 1) * kWStageBytes (dynamic)
+    // followed by the W ring: kWStages x [(nterms == 3 ? 2 : 1) weight images | bias image] (dynamic)
 };
-static_assert((((sizeof(SmemLayout) + 127) & ~size_t(127)) + kWStages * kWStageBytes + 128 + 1024) * kCtasPerSm <= 233472,
+static_assert((((sizeof(SmemLayout) + 127) & ~size_t(127)) + kWStages * (kWStageBytes + kBiasBytes) + 128 + 1024) * kCtasPerSm <= 233472,
               "kCtasPerSm CTAs (fp16x2) must fit the SM's 228 KB of shared memory");
 
 // What one launch does: kSampler -> steps step_hi..step_lo, two passes each; else one forward.
@@ -343,6 +346,12 @@ __device__ __forceinline__ void tmem_moments(uint32_t ta, int ng, int dt, const 
     fold_moments(s1, s2, s1o, s2o);
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Swish(cond) operand chunks: straight copies of the tile's pre-split image (global scratch, L2) into the A ring;
+// every 16-byte piece of a chunk is in flight at once, no registers are staged.
 __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P) {
     const uint4* img = reinterpret_cast<const uint4*>(E.scr + P.cond_off) + E.row;
     const int nkc = P.Cp / 8;                      // 16-byte K pieces per row
@@ -352,21 +361,11 @@ __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev&
         if (E.fresh >= kASlots) mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
         ++E.fresh;
         const uint32_t base = E.a_hi0 + sl * kSlotBytes + (uint32_t)(E.row >> 3) * (uint32_t)(nk * 128) + E.a_row;
-        for (int k0 = 0; k0 < nk; k0 += 4) {       // 8 independent 16-byte loads in flight
-            uint4 h[4], l[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k0 + k < nk) {
-                    h[k] = img[(size_t)(c0 + k0 + k) * kRows];
-                    l[k] = img[(size_t)(nkc + c0 + k0 + k) * kRows];
-                }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k0 + k < nk) {
-                    sts128(base + (k0 + k) * 128, h[k].x, h[k].y, h[k].z, h[k].w);
-                    sts128(base + kLoOff + (k0 + k) * 128, l[k].x, l[k].y, l[k].z, l[k].w);
-                }
+        for (int k = 0; k < nk; ++k) {
+            cp_async16(base + k * 128, img + (size_t)(c0 + k) * kRows);
+            cp_async16(base + kLoOff + k * 128, img + (size_t)(nkc + c0 + k) * kRows);
         }
+        cp_async_wait_all();
         emit_publish(S, E, sq);
         ++E.aseq;
     }
@@ -379,6 +378,11 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
     const int row = E.row;
     for (int si = 0; si < P.n_stages; ++si) {
         const Stage sg = c_stages[si];
+        const bool has_pkg = sg.pkg_f4 != 0;
+        const uint32_t psl = pseq % kPSlots;
+        // the package was requested long ago: check it first, in the shadow of the accumulator wait
+        if (has_pkg) { TCT_BEGIN(_tk); mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1); TCT_END(_tk, 1); }
+        const float* pk_ = S.pkg[psl];
         if (sg.bits & 4) {
             TCT_BEGIN(_ta);
             mbar_wait(&S.acc_full, acc_phase);
@@ -387,10 +391,6 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             E.fresh = 0;
             TCT_END(_ta, 0);
         }
-        const bool has_pkg = sg.pkg_f4 != 0;
-        const uint32_t psl = pseq % kPSlots;
-        if (has_pkg) { TCT_BEGIN(_tk); mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1); TCT_END(_tk, 1); }
-        const float* pk_ = S.pkg[psl];
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
             const Epi op = c_epis[ei];
             const int np = op.np, ng = np >> 1, dt = op.dt, dp = np * 8;
@@ -653,14 +653,21 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
     }
 }
 
-// Which chunks of a stage are issued in this pass: cond chunks only in a conditional pass; time-bias chunks
-// (images of the step table) only by the sampler -- forward mode adds the row's own time slice in the epilogue.
-template <bool kSampler>
+// Which chunks of a stage are issued in this pass: cond chunks only in a conditional pass.
 __device__ __forceinline__ bool chunk_active(const Chunk& ch, bool use_cond) {
-    if ((ch.flags & kChunkCond) && !use_cond) return false;
-    if ((ch.flags & kChunkTime) && !kSampler) return false;
-    return true;
+    return !(ch.flags & kChunkCond) || use_cond;
 }
+// index of the last chunk of the stage issued in this pass (its W-ring stage also carries the bias image)
+__device__ __forceinline__ int last_active_chunk(const Stage& sg, bool use_cond) {
+    int last = sg.chunk_begin;
+    for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci)
+        if (chunk_active(c_chunks[ci], use_cond)) last = ci;
+    return last;
+}
+// The bias MMA is skipped only for time biases in forward mode (rows carry their own time index: the epilogue
+// adds the row's fp32 table slice instead).
+template <bool kSampler>
+__device__ __forceinline__ bool stage_has_bias_mma(const Stage& sg) { return kSampler || !(sg.bits & 8); }
 
 template <bool kSampler>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, RunArgs R) {
@@ -668,7 +675,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
     uint8_t* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(sm);
     const int w_terms = P.nterms == 3 ? 2 : 1;
-    uint8_t* w_ring = sm + ((sizeof(SmemLayout) + 127) & ~size_t(127));   // [kWStages][w_terms][kWStageBytes]
+    const int w_stage_bytes = w_terms * kWStageBytes + kBiasBytes;
+    uint8_t* w_ring = sm + ((sizeof(SmemLayout) + 127) & ~size_t(127));   // [kWStages] x [w_terms weight images | bias image]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup
@@ -712,23 +720,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                                 const uint32_t bytes = (uint32_t)sg.pkg_f4 * 16u;
                                 mbar_wait_parked(&S.p_empty[sl], ((pseq / kPSlots) & 1) ^ 1);
                                 mbar_arrive_expect_tx(&S.p_full[sl], bytes);
-                                tma_load_1d(S.pkg[sl], P.params + (size_t)sg.pkg_off4 * 4, bytes, &S.p_full[sl]);
+                                tma_load_1d(S.pkg[sl], P.params + (size_t)sg.pkg_off16 * 16, bytes, &S.p_full[sl]);
                                 ++pseq;
                             }
                             if (!(sg.bits & 4)) continue;
-                            for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
+                            const int last = last_active_chunk(sg, use_cond);
+                            for (int ci = sg.chunk_begin; ci <= last; ++ci) {
                                 const Chunk ch = c_chunks[ci];
-                                if (!chunk_active<kSampler>(ch, use_cond)) continue;
+                                if (!chunk_active(ch, use_cond)) continue;
                                 const uint32_t st = wseq % kWStages, ph = (wseq / kWStages) & 1;
                                 const uint32_t bytes = (uint32_t)sg.n16 * 16u * ch.kw * 2u;
-                                const bool bias = (ch.flags & kChunkBias) != 0;
-                                const uint8_t* src = (ch.flags & kChunkTime) ? P.tt_img + (size_t)step * P.tt_img_stride : P.w_hi;
+                                const bool bias = ci == last && stage_has_bias_mma<kSampler>(sg);
+                                const uint32_t bias_bytes = bias ? (uint32_t)sg.n16 * 16u * kBiasK * 2u : 0u;
                                 mbar_wait_parked(&S.w_empty[st], ph ^ 1);
-                                mbar_arrive_expect_tx(&S.w_full[st], bytes * (bias ? 1 : w_terms));
-                                uint8_t* dst = w_ring + (size_t)st * w_terms * kWStageBytes;
-                                tma_load_1d(dst, src + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
-                                if (w_terms == 2 && !bias)
+                                mbar_arrive_expect_tx(&S.w_full[st], bytes * w_terms + bias_bytes);
+                                uint8_t* dst = w_ring + (size_t)st * w_stage_bytes;
+                                tma_load_1d(dst, P.w_hi + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
+                                if (w_terms == 2)
                                     tma_load_1d(dst + kWStageBytes, P.w_lo + (size_t)ch.w_off16 * 16, bytes, &S.w_full[st]);
+                                if (bias) {
+                                    const uint8_t* src = (sg.bits & 8) ? P.tt_img + (size_t)step * P.tt_img_stride : P.w_hi;
+                                    tma_load_1d(dst + w_terms * kWStageBytes, src + (size_t)sg.bias_off16 * 16, bias_bytes, &S.w_full[st]);
+                                }
                                 ++wseq;
                             }
                         }
@@ -749,30 +762,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                             const uint32_t idesc = make_idesc_f16(128, (uint32_t)sg.n16 * 16u);
                             const uint32_t d_tmem = S.tmem_base + (sg.bits & 1) * kRegionCols;
                             uint32_t acc = (sg.bits >> 1) & 1;
-                            for (int ci = sg.chunk_begin; ci < sg.chunk_begin + sg.n_chunks; ++ci) {
+                            const int last = last_active_chunk(sg, use_cond);
+                            for (int ci = sg.chunk_begin; ci <= last; ++ci) {
                                 const Chunk ch = c_chunks[ci];
-                                if (!chunk_active<kSampler>(ch, use_cond)) continue;
+                                if (!chunk_active(ch, use_cond)) continue;
                                 const uint32_t st = wseq % kWStages, wph = (wseq / kWStages) & 1;
-                                const uint32_t sbo = (uint32_t)ch.kw * 16u;
-                                const uint8_t* wst = w_ring + (size_t)st * w_terms * kWStageBytes;
-                                const uint64_t dw_hi = make_smem_desc(smem_u32(wst), 128, sbo, 0);
-                                if (ch.flags & kChunkBias) {
-                                    // accumulator += 1 . [b_hi, b_mid, b_lo]: the constant ones tile is the A operand
-                                    mbar_wait_parked(&S.w_full[st], wph);
-                                    tcgen05_fence_after();
-                                    umma_f16(d_tmem, d_ones, dw_hi, idesc, acc);
-                                    acc = 1;
-                                    umma_commit(&S.w_empty[st]);
-                                    ++wseq;
-                                    continue;
-                                }
                                 const uint32_t sl = aseq % kASlots, aph = (aseq / kASlots) & 1;
-                                mbar_wait_parked(&S.a_full[sl], aph);
-                                mbar_wait_parked(&S.w_full[st], wph);
-                                tcgen05_fence_after();
+                                const uint32_t sbo = (uint32_t)ch.kw * 16u;
+                                const uint8_t* wst = w_ring + (size_t)st * w_stage_bytes;
+                                const uint64_t dw_hi = make_smem_desc(smem_u32(wst), 128, sbo, 0);
+                                const uint64_t dw_lo = make_smem_desc(smem_u32(wst + kWStageBytes), 128, sbo, 0);
                                 const uint64_t da_hi = make_smem_desc(smem_u32(S.a_hi[sl]), 128, sbo, 0);
                                 const uint64_t da_lo = make_smem_desc(smem_u32(S.a_lo[sl]), 128, sbo, 0);
-                                const uint64_t dw_lo = make_smem_desc(smem_u32(wst + kWStageBytes), 128, sbo, 0);
+                                mbar_wait_parked(&S.w_full[st], wph);       // weights were requested long ago: off the critical path
+                                mbar_wait_spin(&S.a_full[sl], aph);         // the operand chunk is what the tile is waiting for
+                                tcgen05_fence_after();
                                 for (uint32_t ks = 0; ks < ch.kw / 16u; ++ks) {
                                     const uint64_t adv = (uint64_t)(ks * 16u);      // 256 bytes >> 4
                                     umma_f16(d_tmem, da_hi + adv, dw_hi + adv, idesc, acc);
@@ -781,6 +785,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                                     if (P.nterms >= 3) umma_f16(d_tmem, da_hi + adv, dw_lo + adv, idesc, 1);
                                 }
                                 umma_commit(&S.a_empty[sl]);
+                                if (ci == last && stage_has_bias_mma<kSampler>(sg))
+                                    // accumulator += 1 . [b_hi, b_mid, b_lo]: the constant ones tile is the A operand
+                                    umma_f16(d_tmem, d_ones, make_smem_desc(smem_u32(wst + w_terms * kWStageBytes), 128, 256, 0), idesc, 1);
                                 umma_commit(&S.w_empty[st]);
                                 ++wseq; ++aseq;
                             }

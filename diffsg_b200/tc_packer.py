@@ -16,11 +16,12 @@ Layout decisions made here:
   * a single-token AttentionBlock is ONE accumulate stage with the fused matrix output.weight @ V.weight;
   * weights are fp16 core-matrix images ([n/8][k/8][n%8][8], one image per <=64-wide K-chunk)
     streamed by 1-D bulk TMA; with nterms == 3 a second image holds the fp16 residual of W;
-  * biases ride on the tensor cores: every GEMM group ends with a K = 16 "bias chunk" whose A operand is the
+  * biases ride on the tensor cores: every GEMM group ends with one K = 16 "bias MMA" whose A operand is the
     kernel's constant tile of ones (K columns 0..2) and whose W image holds the bias as three fp16 terms
-    (hi, mid, lo; exact to 2^-33).  Static biases live in the weight blob; the hoisted time bias
-    (lin1.bias + time_emb(Swish(TimeEmbedding(t)))) is one image row per reverse step (`time_images`).
-    `UNet1D.forward` (rows with arbitrary t) skips the time chunks and adds the row's fp32 table slice instead;
+    (hi, mid, lo; exact to 2^-33); the image travels with the group's last weight chunk (same W-ring stage).
+    Static biases live in the weight blob; the hoisted time bias (lin1.bias + time_emb(Swish(TimeEmbedding(t))))
+    is one image row per reverse step (`time_images`).  `UNet1D.forward` (rows with arbitrary t) skips the
+    time-bias MMAs and adds the row's fp32 table slice in the epilogue instead;
   * the LayerNorm gamma / beta a stage's epilogue needs are packed into ONE contiguous per-stage package that
     the TMA warp streams into shared memory ahead of the epilogue;
   * widths are padded to multiples of 16 (UMMA K / N granularity); pad rows/cols are zero.
@@ -51,8 +52,9 @@ EPI_DT = np.dtype([("kind", "u1"), ("np", "u1"), ("dt", "u1"), ("misc", "u1"), (
                    ("tt_src4", "u2")])
 CHUNK_DT = np.dtype([("kw", "u2"), ("flags", "u2"), ("w_off16", "u4")])          # w_off16: offset / 16 bytes
 STAGE_DT = np.dtype([("chunk_begin", "u2"), ("epi_begin", "u2"), ("n_chunks", "u1"), ("n_epi", "u1"),
-                     ("n16", "u1"), ("bits", "u1"), ("pkg_off4", "u4"), ("pkg_f4", "u2"), ("pad_", "u2")])
-CHUNK_COND, CHUNK_BIAS, CHUNK_TIME = 1, 2, 4
+                     ("n16", "u1"), ("bits", "u1"), ("pkg_off16", "u2"), ("pkg_f4", "u1"), ("pad_", "u1"),
+                     ("bias_off16", "u4")])      # bits: region | accumulate << 1 | has_gemm << 2 | time_bias << 3
+CHUNK_COND = 1
 assert EPI_DT.itemsize == 8 and CHUNK_DT.itemsize == 8 and STAGE_DT.itemsize == 16
 
 
@@ -111,11 +113,10 @@ class TcProgram:
         assert self._open is None
         self._open = dict(chunk_begin=len(self.chunks), n16=pad16(n_out) // 16, region=region, n_out=n_out,
                           accumulate=int(accumulate), has_gemm=int(has_gemm), epi_begin=len(self.epis),
-                          pkg_off=self.n_params, pkg_floats=0, has_bias=False)
+                          pkg_off=self.n_params, pkg_floats=0, has_bias=False, time_bias=0, bias_off16=0)
 
     def add_k_segment(self, weight_fn, n_out: int, k: int, cond: bool = False):
         """Append the K-chunks of one operand segment of width k (weight_fn() -> [n_out, k])."""
-        assert not self._open["has_bias"], "the bias chunk must be the last chunk of a GEMM group"
         npad, kp = pad16(n_out), pad16(k)
         for k0 in range(0, kp, CHUNK_K):
             kw = min(CHUNK_K, kp - k0)
@@ -126,26 +127,26 @@ class TcProgram:
             self.chunks.append(dict(kw=kw, flags=CHUNK_COND if cond else 0, w_off16=off // 16, macs=n_out * kreal))
 
     def add_bias(self, bias_fn):
-        """Close the GEMM group with a static bias chunk (image in the weight blob)."""
+        """The GEMM group's static bias (image in the weight blob)."""
         st = self._open
+        assert not st["has_bias"]
         npad = st["n16"] * 16
         off = self.w_bytes
         self.bpieces.append((off, st["n_out"], npad, bias_fn))
         self.w_bytes += npad * BIAS_K * 2
-        self.chunks.append(dict(kw=BIAS_K, flags=CHUNK_BIAS, w_off16=off // 16, macs=0))
-        st["has_bias"] = True
+        st.update(has_bias=True, time_bias=0, bias_off16=off // 16)
 
     def add_time_bias(self, time_emb, lin1) -> int:
-        """Close the GEMM group with the per-step bias chunk lin1.bias + time_emb(.): one image per reverse step in
-        the step image table; returns the column offset of the same values in the fp32 time table."""
+        """The GEMM group's per-step bias lin1.bias + time_emb(.): one image per reverse step in the step image
+        table; returns the column offset of the same values in the fp32 time table."""
         st = self._open
+        assert not st["has_bias"]
         npad = st["n16"] * 16
         t_off, img_off = self.tt_stride, self.img_stride
         self.time_blocks.append((t_off, img_off, npad, time_emb, lin1))
         self.tt_stride += npad
         self.img_stride += npad * BIAS_K * 2
-        self.chunks.append(dict(kw=BIAS_K, flags=CHUNK_BIAS | CHUNK_TIME, w_off16=img_off // 16, macs=0))
-        st["has_bias"] = True
+        st.update(has_bias=True, time_bias=1, bias_off16=img_off // 16)
         return t_off
 
     def epi(self, kind, width, region=0, flags=0, slot=0, off1=0, tt_src=0):
@@ -155,7 +156,8 @@ class TcProgram:
 
     def end_stage(self):
         st = self._open
-        assert not st["has_gemm"] or st["has_bias"], "every GEMM group ends with its bias chunk"
+        assert not st["has_gemm"] or st["has_bias"], "every GEMM group carries a bias image"
+        assert st["pkg_off"] % 16 == 0 and st["pkg_floats"] // 4 < 256
         st["n_chunks"] = len(self.chunks) - st["chunk_begin"]
         st["n_epi"] = len(self.epis) - st["epi_begin"]
         self.n_params += st["pkg_floats"]
@@ -178,8 +180,8 @@ class TcProgram:
         s = np.zeros(len(self.stages), STAGE_DT)
         for i, d in enumerate(self.stages):
             s[i] = (d["chunk_begin"], d["epi_begin"], d["n_chunks"], d["n_epi"], d["n16"],
-                    d["region"] | (d["accumulate"] << 1) | (d["has_gemm"] << 2),
-                    d["pkg_off"] // 4, d["pkg_floats"] // 4, 0)
+                    d["region"] | (d["accumulate"] << 1) | (d["has_gemm"] << 2) | (d["time_bias"] << 3),
+                    d["pkg_off"] // 16, d["pkg_floats"] // 4, 0, d["bias_off16"])
         c = np.zeros(len(self.chunks), CHUNK_DT)
         for i, d in enumerate(self.chunks):
             c[i] = (d["kw"], d["flags"], d["w_off16"])

@@ -49,18 +49,14 @@ def run_tc_program(p, w_hi, w_lo, params, table, x, t_idx, cond, mask, emulate_f
             N = st["n16"] * 16
             acc = regions[st["region"]][:, :N].clone() if st["accumulate"] else torch.zeros(B, N)
             chs = p.chunks[st["chunk_begin"]:st["chunk_begin"] + st["n_chunks"]]
-            assert chs[-1]["flags"] & T.CHUNK_BIAS and not any(ch["flags"] & T.CHUNK_BIAS for ch in chs[:-1])
+            boff = st["bias_off16"] * 8
+            if not st["time_bias"]:
+                acc = acc + bias_from_image(w_hi[boff:boff + N * T.BIAS_K], N)[None, :]
+            elif images is not None:        # forward mode (images None): the epilogue adds the row's table slice
+                acc = acc + bias_from_image(images[t_idx][:, boff:boff + N * T.BIAS_K], N)
             for ch in chs:
                 kw = ch["kw"]
                 off = ch["w_off16"] * 8
-                if ch["flags"] & T.CHUNK_TIME:
-                    if images is None:
-                        continue            # forward mode: the epilogue adds the row's table slice
-                    acc = acc + bias_from_image(images[t_idx][:, off:off + N * kw], N)
-                    continue
-                if ch["flags"] & T.CHUNK_BIAS:
-                    acc = acc + bias_from_image(w_hi[off:off + N * kw], N)[None, :]
-                    continue
                 a = queue.pop(0)
                 assert a.shape[1] == kw, (a.shape, kw)
                 img = w_hi[off:off + N * kw].float()
