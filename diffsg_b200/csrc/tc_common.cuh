@@ -27,6 +27,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// add `bytes` to the pending transaction count of the current phase without arriving
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -52,7 +56,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
 // shares its scheduler.
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 2000) {
     uint32_t ok;
-    do {
+    while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -60,13 +64,19 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
             : "memory");
-    } while (!ok);
+        if (ok) break;
+        __nanosleep(32);       // the hardware hint returns early on any barrier traffic of the CTA: back off explicitly
+    }
 }
 
 // ------------------------------------------------------------------------------ fences
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// generic-proxy writes (shared or global) -> visible to later async-proxy reads of this thread's CTA
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

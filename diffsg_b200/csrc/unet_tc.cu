@@ -245,6 +245,7 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     D.scratch_floats = (off + 31) & ~size_t(31);
     const int w_terms = g->nterms == 3 ? 2 : 1;
     h->smem_bytes = 128 + ((sizeof(SmemLayout) + 127) & ~size_t(127)) + (size_t)kWStages * (w_terms * kWStageBytes + kBiasBytes);
+    if (getenv("DIFFSG_TC_ONE_CTA")) h->smem_bytes = 180 * 1024;   // experiment: one tile per SM (no co-resident CTA)
     // fp16x2 fits two CTAs (tiles) per SM: 2 x (<= 113 KB smem, 256 TMEM columns, 30 K registers)
     h->grid_max = p->sm_count;
     if ((int)h->smem_bytes > p->max_smem) { set_error("attach_tc: needs %zu B shared memory", h->smem_bytes); return DIFFSG_E_UNSUPPORTED; }
@@ -263,16 +264,17 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
     DIFFSG_CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
     DIFFSG_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
     D.status = h->d_status;
-    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    DIFFSG_CUDA_OK(cudaFuncSetAttribute(tc_unet_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (const void* fn : {(const void*)tc_unet_kernel<true, true>, (const void*)tc_unet_kernel<true, false>,
+                           (const void*)tc_unet_kernel<false, true>, (const void*)tc_unet_kernel<false, false>}) {
+        DIFFSG_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        DIFFSG_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     int occ = 0;
-    DIFFSG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_unet_kernel<true>, kThreads, h->smem_bytes));
+    DIFFSG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_unet_kernel<true, true>, kThreads, h->smem_bytes));
     h->occupancy = occ;
     if (getenv("DIFFSG_DEBUG")) {
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, tc_unet_kernel<true>);
+        cudaFuncGetAttributes(&fa, tc_unet_kernel<true, true>);
         cudaDeviceProp prop;
         cudaGetDeviceProperties(&prop, p->cfg.device);
         fprintf(stderr, "[diffsg] tc kernel: regs %d, static smem %zu, dyn smem %zu (max %d), maxThreads %d, occ %d | SM: regs %d, smem %zu, "
@@ -281,12 +283,12 @@ int tc_attach(diffsg_plan* p, const diffsg_tc_program* g) {
                 prop.reservedSharedMemPerBlock, prop.maxBlocksPerMultiProcessor, prop.maxThreadsPerMultiProcessor);
         for (int thr = 128; thr <= 512; thr += 64) {
             int o = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tc_unet_kernel<true>, thr, h->smem_bytes);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tc_unet_kernel<true, true>, thr, h->smem_bytes);
             fprintf(stderr, "[diffsg]   occupancy at %d threads: %d\n", thr, o);
         }
         for (size_t sm = 32768; sm <= 131072; sm += 16384) {
             int o = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tc_unet_kernel<true>, kThreads, sm);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tc_unet_kernel<true, true>, kThreads, sm);
             fprintf(stderr, "[diffsg]   occupancy at %zu B smem: %d\n", sm, o);
         }
     }
@@ -379,7 +381,9 @@ int tc_forward(diffsg_plan* p, const float* x, const int32_t* t_idx, const float
     RunArgs R;
     memset(&R, 0, sizeof(R));
     R.x = x; R.t_idx = t_idx; R.cond = cond; R.mask = mask; R.eps = eps; R.B = B;
-    tc_unet_kernel<false><<<tc_grid(p, B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+    // fp16x2 (nterms <= 2) runs the one-MUFU Swish; fp16x3 (the ~fp32 mode) the exact two-MUFU form
+    if (p->tc->dev.nterms <= 2) tc_unet_kernel<false, true><<<tc_grid(p, B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+    else tc_unet_kernel<false, false><<<tc_grid(p, B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
     count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
     return tc_mark_launch(p, st);
@@ -402,7 +406,8 @@ int tc_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps
     R.seed = a->philox_seed; R.offset = a->philox_offset;
     for (int i = 0; i < T; ++i) { R.c_eps[i] = a->coef_host[i]; R.c_rs[i] = a->coef_host[T + i]; R.c_noise[i] = a->coef_host[2 * T + i]; }
     R.step_hi = step_hi; R.step_lo = step_lo;
-    tc_unet_kernel<true><<<tc_grid(p, a->B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+    if (p->tc->dev.nterms <= 2) tc_unet_kernel<true, true><<<tc_grid(p, a->B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
+    else tc_unet_kernel<true, false><<<tc_grid(p, a->B), kThreads, p->tc->smem_bytes, st>>>(p->tc->dev, R);
     count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
     if (int rc = tc_mark_launch(p, st)) return rc;

@@ -136,8 +136,21 @@ __device__ __forceinline__ void split2(f2 v, uint32_t& hi, uint32_t& lo) {
     upk(sub2(v, h2_to_f2(hi)), a, b);
     lo = cvt_h2(a, b);
 }
-// x * sigmoid(x), two lanes: one MUFU.EX2 and one MUFU.RCP per lane (relative error ~3e-7)
+// x * sigmoid(x), two lanes.
+//   kFast = false: one MUFU.EX2 and one MUFU.RCP per lane (absolute error <= 1.4e-6, measured on B200)
+//   kFast = true:  h + h * tanh(h), h = x / 2: ONE MUFU per lane.  MUFU.TANH on B200 is good to 8e-6 absolute
+//                  (tools/ubench/tanh_err.cu), the Swish built on it to 1.03e-5 absolute over the whole real line --
+//                  far below the fp16 weight rounding of the fp16x2 mode that uses it; fp16x3 keeps the exact form.
+template <bool kFast>
 __device__ __forceinline__ f2 swish2(f2 u) {
+    if (kFast) {
+        const f2 h = mul2(u, pk(0.5f, 0.5f));
+        float h0, h1, t0, t1;
+        upk(h, h0, h1);
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        return fma2(h, pk(t0, t1), h);
+    }
     float e0, e1;
     upk(mul2(u, pk(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
     upk(add2(pk(ex2_approx(e0), ex2_approx(e1)), pk(1.0f, 1.0f)), e0, e1);
@@ -161,6 +174,24 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
+__device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
 }
 
 #ifdef DIFFSG_TC_TIMING
@@ -244,13 +275,14 @@ __device__ __forceinline__ void normalise16(const uint32_t (&r)[16], f2 sc, f2 s
     for (int j = 0; j < 8; ++j) t[j] = fma2(pku(r[2 * j], r[2 * j + 1]), sc, sh);
 }
 // one group: swish(t * gamma + beta) -> operand pieces.  Pad columns have gamma = beta = 0 -> exact zeros.
+template <bool kFast>
 __device__ __forceinline__ void store_ln_swish(uint32_t addr, const f2 (&t)[8], const float4* gamma, const float4* beta) {
     f2 v[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 g = gamma[q], b = beta[q];
-        v[2 * q] = swish2(fma2(t[2 * q], pk(g.x, g.y), pk(b.x, b.y)));
-        v[2 * q + 1] = swish2(fma2(t[2 * q + 1], pk(g.z, g.w), pk(b.z, b.w)));
+        v[2 * q] = swish2<kFast>(fma2(t[2 * q], pk(g.x, g.y), pk(b.x, b.y)));
+        v[2 * q + 1] = swish2<kFast>(fma2(t[2 * q + 1], pk(g.z, g.w), pk(b.z, b.w)));
     }
     store_split(addr, v);
 }
@@ -320,28 +352,39 @@ __device__ __forceinline__ void skip_walk2(const uint4* sk, int ng, F body) {
     }
 }
 
-// Shifted moments of a TMEM vector (pass 1 of a LayerNorm); optionally spills the vector to a skip slot.
-// Returns shift, s1 = sum(x - shift), s2 = sum((x - shift)^2) over the first dt columns.
+// Shifted moments of a TMEM vector (pass 1 of a LayerNorm), 32 columns per TMEM round trip; optionally spills the
+// vector to a skip slot.  Returns shift, s1 = sum(x - shift), s2 = sum((x - shift)^2) over the first dt columns.
+// (An odd group count reads 16 columns past the vector: still inside the 128-column region, and ignored.)
 template <bool kSampler>
 __device__ __forceinline__ void tmem_moments(uint32_t ta, int ng, int dt, const float* tt_row, uint4* sk_push,
                                              float& shift, float& s1o, float& s2o) {
-    uint32_t r[16];
-    f2 x[8], s1[2] = {0ull, 0ull}, s2[2] = {0ull, 0ull}, sh2 = 0ull;
+    uint32_t r[32];
+    f2 s1[2] = {0ull, 0ull}, s2[2] = {0ull, 0ull}, sh2 = 0ull;
     shift = 0.f;
-    tmem_ld16u(ta, r);
-    for (int g = 0; g < ng; ++g) {
-        tmem_wait16(r);
-        if (!kSampler && tt_row) add_time16(r, tt_row + g * 16);
+    tmem_ld32u(ta, r);
+    for (int g = 0; g < ng; g += 2) {
+        tmem_wait32(r);
+        uint32_t (&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[0]);
+        uint32_t (&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[16]);
+        const bool two = g + 1 < ng;
+        if (!kSampler && tt_row) { add_time16(ra, tt_row + g * 16); if (two) add_time16(rb, tt_row + g * 16 + 16); }
         if (g == 0) { shift = __uint_as_float(r[0]); sh2 = pk(shift, shift); }
-        if (sk_push) store_group_skip(r, sk_push + (size_t)g * 4 * kRows);
-        if (g == ng - 1 && dt < ng * 16) {           // pad columns (exact zeros) must not enter the moments
-            const int nval = dt - g * 16;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (j >= nval) r[j] = __float_as_uint(shift);
+        if (sk_push) {
+            store_group_skip(ra, sk_push + (size_t)g * 4 * kRows);
+            if (two) store_group_skip(rb, sk_push + (size_t)(g + 1) * 4 * kRows);
         }
-        centre16(r, sh2, x);
-        if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
-        moments16(x, s1, s2);
+        // pad columns (exact zeros; or, for an odd group count, the 16 columns past the vector) must not enter the moments
+        const int nval = dt - g * 16;
+        if (nval < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j >= nval) r[j] = __float_as_uint(shift);
+        }
+        f2 da[8], db[8];
+        centre16(ra, sh2, da);
+        centre16(rb, sh2, db);
+        if (g + 2 < ng) tmem_ld32u(ta + (g + 2) * 16, r);
+        moments16(da, s1, s2);
+        moments16(db, s1, s2);
     }
     fold_moments(s1, s2, s1o, s2o);
 }
@@ -350,28 +393,33 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// Swish(cond) operand chunks: straight copies of the tile's pre-split image (global scratch, L2) into the A ring;
-// every 16-byte piece of a chunk is in flight at once, no registers are staged.
+// Swish(cond) operand chunks: the tile's pre-split image lives in global scratch already in operand-chunk layout,
+// so a chunk is two bulk-TMA copies (hi, lo) straight into the A-ring slot, issued by one thread; the slot's barrier
+// counts the bytes on top of the usual one arrival per epilogue warp.
 __device__ __forceinline__ void emit_cond(SmemLayout& S, EpiCtx& E, const TcDev& P) {
-    const uint4* img = reinterpret_cast<const uint4*>(E.scr + P.cond_off) + E.row;
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(E.scr + P.cond_off);
     const int nkc = P.Cp / 8;                      // 16-byte K pieces per row
+    uint32_t done = 0;                             // bytes of the chunks before this one (per term)
     for (int c0 = 0; c0 < nkc; c0 += 8) {
         const int nk = min(8, nkc - c0);
         const uint32_t sq = E.aseq, sl = sq % kASlots;
+        const uint32_t bytes = (uint32_t)nk * 128u * (kRows / 8);
+        // every thread waits for the slot: an arrival must not land in the barrier phase of the slot's previous chunk
         if (E.fresh >= kASlots) mbar_wait(&S.a_empty[sl], ((sq / kASlots) & 1) ^ 1);
-        ++E.fresh;
-        const uint32_t base = E.a_hi0 + sl * kSlotBytes + (uint32_t)(E.row >> 3) * (uint32_t)(nk * 128) + E.a_row;
-        for (int k = 0; k < nk; ++k) {
-            cp_async16(base + k * 128, img + (size_t)(c0 + k) * kRows);
-            cp_async16(base + kLoOff + k * 128, img + (size_t)(nkc + c0 + k) * kRows);
+        if (E.row == 0) {
+            mbar_expect_tx(&S.a_full[sl], 2 * bytes);
+            tma_load_1d(S.a_hi[sl], img + done, bytes, &S.a_full[sl]);
+            tma_load_1d(S.a_lo[sl], img + (size_t)P.Cp * kRows * 2 + done, bytes, &S.a_full[sl]);
         }
-        cp_async_wait_all();
-        emit_publish(S, E, sq);
+        ++E.fresh;
+        __syncwarp();
+        if (E.lane == 0) mbar_arrive(&S.a_full[sl]);
+        done += bytes;
         ++E.aseq;
     }
 }
 
-template <bool kSampler>
+template <bool kSampler, bool kFast>
 __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, const RunArgs& R, EpiCtx& E, int trow,
                                              bool use_cond, int pass, int step, uint32_t& acc_phase,
                                              uint32_t& pseq, double& st_s, double& st_q) {
@@ -426,7 +474,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         if (!kSampler && tt_row) add_time16(r, tt_row + g * 16);
                         normalise16(r, sc, sh, x);
                         if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
-                        store_ln_swish(addr, x, pg + g * 4, pb + g * 4);
+                        store_ln_swish<kFast>(addr, x, pg + g * 4, pb + g * 4);
                         emit_done(S, E, em, g);
                     }
                     emit_end(S, E, em);
@@ -456,7 +504,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         const uint32_t addr = emit_addr(S, E, em, g);
                         f2 xs[8];
                         normalise16(rs, sc, sh, xs);
-                        store_ln_swish(addr, xs, pgx + 2 * d4 + g * 4, pgx + 3 * d4 + g * 4);
+                        store_ln_swish<kFast>(addr, xs, pgx + 2 * d4 + g * 4, pgx + 3 * d4 + g * 4);
                         emit_done(S, E, em, g);
                     });
                     emit_end(S, E, em);
@@ -467,7 +515,7 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                         tmem_wait16(r);
                         normalise16(r, sc, sh, x);
                         if (g + 1 < ng) tmem_ld16u(ta + (g + 1) * 16, r);
-                        store_ln_swish(addr, x, pgx + g * 4, pgx + d4 + g * 4);
+                        store_ln_swish<kFast>(addr, x, pgx + g * 4, pgx + d4 + g * 4);
                         emit_done(S, E, em, g);
                     }
                     emit_end(S, E, em);
@@ -669,7 +717,7 @@ __device__ __forceinline__ int last_active_chunk(const Stage& sg, bool use_cond)
 template <bool kSampler>
 __device__ __forceinline__ bool stage_has_bias_mma(const Stage& sg) { return kSampler || !(sg.bits & 8); }
 
-template <bool kSampler>
+template <bool kSampler, bool kFast>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, RunArgs R) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -815,9 +863,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             E.grow = tile * kRows + E.row;
             E.valid = E.grow < R.B;
-            // cond image: swish(cond * mask) as fp16 (hi, lo) 16-byte K pieces (thread-private scratch)
+            // cond image: swish(cond * mask) as fp16 (hi, lo), written in operand-chunk layout (per <= 64-column chunk:
+            // [row / 8][piece][row % 8][8 halves]; all hi chunks, then all lo chunks) so that emit_cond can bulk-copy it
             {
-                uint4* img = reinterpret_cast<uint4*>(E.scr + P.cond_off) + E.row;
+                uint8_t* img = reinterpret_cast<uint8_t*>(E.scr + P.cond_off);
                 const int nkc = P.Cp / 8;
                 const float mk = (!kSampler && R.mask && E.valid) ? R.mask[E.grow] : 1.0f;
                 for (int kc = 0; kc < nkc; ++kc) {
@@ -832,16 +881,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                     split2(pk(xc[2], xc[3]), hi.y, lo.y);
                     split2(pk(xc[4], xc[5]), hi.z, lo.z);
                     split2(pk(xc[6], xc[7]), hi.w, lo.w);
-                    img[(size_t)kc * kRows] = hi;
-                    img[(size_t)(nkc + kc) * kRows] = lo;
+                    const int c0 = kc & ~7, nk = min(8, nkc - c0);     // chunk of this piece and its piece count
+                    const size_t off = (size_t)c0 * 128 * (kRows / 8) + (size_t)(E.row >> 3) * (nk * 128) + (kc - c0) * 128 + E.a_row;
+                    *reinterpret_cast<uint4*>(img + off) = hi;
+                    *reinterpret_cast<uint4*>(img + (size_t)P.Cp * kRows * 2 + off) = lo;
                 }
+                fence_proxy_async_all();           // generic-proxy global writes -> visible to the bulk-TMA reads of emit_cond
             }
             const int trow_fwd = (!kSampler && E.valid) ? R.t_idx[E.grow] : 0;
             for (int step = step_hi; step >= step_lo; --step)
                 for (int pass = 0; pass < n_pass; ++pass) {
                     const bool use_cond = kSampler ? (pass == 1) : true;
                     TCT_BEGIN(_tt);
-                    run_epilogue<kSampler>(S, P, R, E, kSampler ? step : trow_fwd, use_cond, pass, step, acc_phase,
+                    run_epilogue<kSampler, kFast>(S, P, R, E, kSampler ? step : trow_fwd, use_cond, pass, step, acc_phase,
                                            pseq, st_s, st_q);
                     TCT_END(_tt, 8);
                 }
