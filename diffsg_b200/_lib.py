@@ -74,6 +74,7 @@ SYMBOLS = {
     "diffsg_philox_normal": (C.c_int, [_P, _I64, _I32, _I32, _U64, _U64, _P]),
     "diffsg_ema_update": (C.c_int, [_P, _P, _I64, _D, _I32, _P]),
     "diffsg_ema_update_multi": (C.c_int, [_P, _P, _P, _I32, _I64, _D, _I32, _P]),
+    "diffsg_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "diffsg_minmax": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
     "diffsg_objective_msr": (C.c_int, [_P, _P, _P, _F, _P, _P, _I64, _I32, _P]),
     "diffsg_rate_msr": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
@@ -103,27 +104,56 @@ def nvcc_path() -> str:
     raise DiffsgError("nvcc not found; cannot build libdiffsg_b200.so")
 
 
+HASH_PATH = PKG_DIR / "libdiffsg_b200.srchash"      # digest of the sources the in-tree .so was built from
+
+
+def _source_digest() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))) + [INCLUDE_DIR / "diffsg_b200.h"]
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    """True if the .so is missing or was built from other sources / flags (content digest, not mtimes: the snapshot
+    that ships the tree to a GPU box does not have to preserve them)."""
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [INCLUDE_DIR / "diffsg_b200.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    return HASH_PATH.read_text().strip() != _source_digest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into diffsg_b200/libdiffsg_b200.so (in-tree)."""
+    """Compile every CUDA source for sm_100a into diffsg_b200/libdiffsg_b200.so (in-tree).
+
+    Safe under torchrun: ranks serialise on a lock file, the first one builds into a temporary file and renames it
+    into place (atomic), the others find a fresh library when they get the lock."""
     if not force and not _stale():
         return LIB_PATH
-    srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [nvcc_path(), *NVCC_FLAGS, *EXTRA_FLAGS, "-I", str(INCLUDE_DIR), *srcs, "-o", str(LIB_PATH)]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise DiffsgError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(str(LIB_PATH) + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
+            tmp = LIB_PATH.with_name(f".{LIB_PATH.name}.{os.getpid()}.tmp")
+            cmd = [nvcc_path(), *NVCC_FLAGS, *EXTRA_FLAGS, "-I", str(INCLUDE_DIR), *srcs, "-o", str(tmp)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise DiffsgError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, LIB_PATH)
+            HASH_PATH.write_text(_source_digest() + "\n")
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -132,11 +162,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    if _stale():        # missing, or older than a source / the header: rebuild (needs nvcc; a stale binary is never loaded silently)
         try:
             build_library()
         except DiffsgError as e:
-            raise DiffsgError(f"{LIB_PATH} is missing and could not be built: {e}") from e
+            if not LIB_PATH.exists():
+                raise DiffsgError(f"{LIB_PATH} is missing and could not be built: {e}") from e
+            raise DiffsgError(f"{LIB_PATH} is older than its sources and could not be rebuilt: {e}") from e
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it

@@ -89,3 +89,37 @@ def evaluate(diffusion_model, X_test, Y_test, custom_config, omega=500.0, batch_
     return dict(exceeded_ratio=float(pred_cost.sum() / true_cost.sum()),
                 avg_cost_diff=float((pred_cost - true_cost).mean()), accuracy=int(same.sum()),
                 terrible=int(terrible.sum()), pred_cost=pred_cost, true_cost=true_cost, Y_pred=Y_pred)
+
+
+# ---- script-level entry points (reference classifier_free_CO.py:203-252, 293-356): same names, same constants
+CO_NET = dict(proj_dim=64, dims=(64, 32, 16, 8), is_attn=(False, False, False, False), middle_attn=False, n_blocks=3)
+
+
+def _co_net(n, sfn=3):
+    return dict(input_dim=n, cond_dim=sfn * n, **CO_NET)
+
+
+def train_ddpm_co(dataset_path="../datasets/3nodes_50000samples_new.csv", epochs=200, lr=0.005, milestones=(15, 80, 150),
+                  use_ema=False, device=None, **fit_kw):
+    """`train_ddpm_co()` of the reference (T = 20, Adam lr 0.005, MultiStepLR [15, 80, 150], bs 512, 200 epochs)."""
+    from . import scripts
+    X_train, Y_train, _, _, cfg = co_data_load(dataset_path)
+    n = Y_train.shape[1]
+    return scripts.train(DDPM, (n,), _co_net(n, cfg["sfn"]), cfg, X_train, Y_train, epochs=epochs, lr=lr,
+                         milestones=milestones, use_ema=use_ema, device=device, **fit_kw)
+
+
+@torch.no_grad()
+def load_test_co(ckpt_path, dataset_path="../datasets/3nodes_50000samples_new.csv", omega=500.0, device=None, verbose=True):
+    """`load_test_co(ckpt_path)` of the reference; also returns the numbers it prints."""
+    from . import scripts
+    X_train, Y_train, X_test, Y_test, cfg = co_data_load(dataset_path)
+    n = Y_train.shape[1]
+    ddpm = scripts.load(DDPM, (n,), _co_net(n, cfg["sfn"]), cfg, ckpt_path, device=device)
+    out = evaluate(ddpm, X_test, Y_test, cfg, omega=omega, batch_size=512)
+    if verbose:
+        scripts.report([("Y_pred", customized_real_decoder(out["Y_pred"])), ("Y_test", Y_test),
+                        ("pred_cost", out["pred_cost"]), ("true_cost", out["true_cost"])],
+                       [f"exceeded ratio: {out['exceeded_ratio']}", f"avg cost diff:\n {out['avg_cost_diff']}",
+                        f"terrible samples num: {out['terrible']}/{len(X_test)}.", f"accuracy: {out['accuracy']}/{len(X_test)}"])
+    return out

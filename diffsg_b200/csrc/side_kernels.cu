@@ -44,6 +44,39 @@ __global__ void ema_multi_kernel(float* const* __restrict__ avgs, const float* c
         avg[j] = copy_first ? p[j] : d * avg[j] + omd * p[j];
 }
 
+// ------------------------------------------------------------------------------ Adam (+ EMA)
+// One launch over the flat parameter / gradient buffers: torch.optim.Adam's update (no weight decay, no amsgrad;
+// reference loop classifier_free_MSR.py:213,225) and, when hyper[5] != 0, the EMA of ddpm_opt/ema.py:10-14 on the
+// freshly updated parameters in the same pass (12 + 8 B/param instead of two kernels re-reading p).
+// Every hyper-parameter and the step counter live in DEVICE memory so the launch can sit in a CUDA graph:
+//   hyper = [lr, beta1, beta2, eps, ema_decay, ema_mode (0 off, 1 copy, 2 blend)]
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ ema, int64_t n,
+                                 const float* __restrict__ hyper, const int64_t* __restrict__ step_dev) {
+    __shared__ float sh[2];
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], d = hyper[4];
+    const int ema_mode = ema ? (int)hyper[5] : 0;
+    if (threadIdx.x == 0) {
+        const double s = (double)(step_dev[0] + 1);
+        sh[0] = (float)(1.0 - pow((double)b1, s));            // bias_correction1
+        sh[1] = (float)sqrt(1.0 - pow((double)b2, s));        // sqrt(bias_correction2)
+    }
+    __syncthreads();
+    const float step_size = lr / sh[0], rs2 = 1.0f / sh[1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.0f - b1);    // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float pi = p[i] - step_size * (mi / (sqrtf(vi) * rs2 + eps));
+        p[i] = pi;
+        if (ema_mode == 1) ema[i] = pi;
+        else if (ema_mode == 2) ema[i] = d * ema[i] + (1.0f - d) * pi;
+    }
+}
+__global__ void adam_bump_kernel(int64_t* step_dev) { step_dev[0] += 1; }
+
 // ------------------------------------------------------------------------------ min/max
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
     if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
@@ -228,6 +261,18 @@ int diffsg_ema_update_multi(float* const* avgs, const float* const* ps, const in
     ema_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(avgs, ps, sizes, (float)decay,
                                                              (float)(1.0 - decay), copy_first);
     count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, const float* hyper,
+                     int64_t* step_dev, void* stream) {
+    if (!p || !g || !m || !v || !hyper || !step_dev || n < 0) { set_error("adam_step: bad argument"); return DIFFSG_E_INVALID; }
+    if (n == 0) return DIFFSG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_flat_kernel<<<blocks_for(n, 1024), 256, 0, st>>>(p, g, m, v, ema, n, hyper, step_dev);
+    adam_bump_kernel<<<1, 1, 0, st>>>(step_dev);
+    count_launch(2);
     DIFFSG_CUDA_OK(cudaGetLastError());
     return DIFFSG_OK;
 }

@@ -419,7 +419,7 @@ int tc_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps
         cudaStreamSynchronize(st);
         long long h[12];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[12] = {"acc_wait", "pkg_wait", "ln_pass1", "ln_pass2", "catln", "raw", "cond", "out", "total", "-", "-", "-"};
+        const char* names[12] = {"acc_wait", "pkg_wait", "ln_pass1", "ln_pass2", "catln", "raw", "cond", "out", "total", "mma_wait_w", "mma_wait_a", "-"};
         fprintf(stderr, "[tc timing, cycles of thread 0 / CTA 0, previous launch]");
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
         fprintf(stderr, "\n");

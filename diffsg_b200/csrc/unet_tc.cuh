@@ -799,6 +799,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         // =========================== MMA issuer
         if (lane == 0) {
             uint32_t wseq = 0, aseq = 0;
+#ifdef DIFFSG_TC_TIMING
+            long long mma_t_w = 0, mma_t_a = 0;
+#endif
             const uint64_t d_ones = make_smem_desc(smem_u32(S.ones), 128, 256, 0);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int step = step_hi; step >= step_lo; --step)
@@ -822,8 +825,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                                 const uint64_t dw_lo = make_smem_desc(smem_u32(wst + kWStageBytes), 128, sbo, 0);
                                 const uint64_t da_hi = make_smem_desc(smem_u32(S.a_hi[sl]), 128, sbo, 0);
                                 const uint64_t da_lo = make_smem_desc(smem_u32(S.a_lo[sl]), 128, sbo, 0);
+#ifdef DIFFSG_TC_TIMING
+                                const long long _m0 = clock64();
+#endif
                                 mbar_wait_parked(&S.w_full[st], wph);       // weights were requested long ago: off the critical path
+#ifdef DIFFSG_TC_TIMING
+                                const long long _m1 = clock64();
+#endif
                                 mbar_wait_spin(&S.a_full[sl], aph);         // the operand chunk is what the tile is waiting for
+#ifdef DIFFSG_TC_TIMING
+                                // how long the weights were still missing AFTER the operand chunk was ready = exposed W latency
+                                mma_t_w += _m1 - _m0; mma_t_a += clock64() - _m1;
+#endif
                                 tcgen05_fence_after();
                                 for (uint32_t ks = 0; ks < ch.kw / 16u; ++ks) {
                                     const uint64_t adv = (uint64_t)(ks * 16u);      // 256 bytes >> 4
@@ -842,6 +855,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                             umma_commit(&S.acc_full);
                         }
                     }
+#ifdef DIFFSG_TC_TIMING
+            if (blockIdx.x == 0 && P.debug) { P.debug[9] = mma_t_w; P.debug[10] = mma_t_a; }
+#endif
         }
     } else {
         // =========================== epilogue / operand producers (thread == row == TMEM lane)
@@ -900,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         }
 #ifdef DIFFSG_TC_TIMING
         if (blockIdx.x == 0 && threadIdx.x == 0 && P.debug)
-            for (int i = 0; i < 12; ++i) P.debug[i] = E.tacc[i];
+            for (int i = 0; i < 9; ++i) P.debug[i] = E.tacc[i];
 #endif
         if (E.amax > 65504.0f && P.status) atomicOr(P.status, kStatusOverflow);
         if (kSampler && R.step_hi > R.T - 1 - R.norm_steps) {

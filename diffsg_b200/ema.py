@@ -25,6 +25,7 @@ class ExponentialMovingAverage(AveragedModel):
         super().__init__(model, device, ema_avg, use_buffers=True)
         self.decay = float(decay)
         self._tables = None
+        self._n_host = None     # host mirror of n_averaged: the fused path never reads the device counter back
 
     def _pairs(self, model):
         own = itertools.chain(self.module.parameters(), self.module.buffers())
@@ -51,9 +52,18 @@ class ExponentialMovingAverage(AveragedModel):
             return super().update_parameters(model)
         avg, src, sizes, max_size = self._device_tables(pairs)
         lib = _lib.load()
-        first = int(self.n_averaged.item()) == 0
+        # one device -> host read at most (first fused call, or after load_state_dict replaced the counter); afterwards
+        # the host mirror decides "first update copies" (ddpm_opt/ema.py:10-14 via AveragedModel) without a stream sync
+        if self._n_host is None or self._n_host[0] != (self.n_averaged.data_ptr(), self.n_averaged._version):
+            self._n_host = [None, int(self.n_averaged.item())]
+        first = self._n_host[1] == 0
         with torch.cuda.device(pairs[0][0].device):
             _lib.check(lib.diffsg_ema_update_multi(avg.data_ptr(), src.data_ptr(), sizes.data_ptr(), len(pairs),
                                                    max_size, self.decay, 1 if first else 0, _lib.stream_ptr()),
                        "diffsg_ema_update_multi")
         self.n_averaged += 1
+        self._n_host = [(self.n_averaged.data_ptr(), self.n_averaged._version), self._n_host[1] + 1]
+        # the kernel wrote the averaged parameters through raw pointers: tensor versions did not move, so tell the
+        # averaged module's kernel plan (if it has one) that its packed weights are stale
+        if hasattr(self.module, "mark_params_changed"):
+            self.module.mark_params_changed()

@@ -163,8 +163,9 @@ class UNetEngine:
         if self.tc is None:
             return
         flags = C.c_int32(0)
-        _lib.check(self.lib.diffsg_plan_status(self.handle, C.byref(flags), 1 if reset else 0, _lib.stream_ptr()),
-                   "diffsg_plan_status")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.diffsg_plan_status(self.handle, C.byref(flags), 1 if reset else 0, _lib.stream_ptr()),
+                       "diffsg_plan_status")
         if flags.value & 1:
             raise _lib.DiffsgError(
                 f"precision {self.precision!r}: an un-normalised operand (y_t or the residual stream) exceeded the fp16 range "
@@ -192,6 +193,10 @@ class UNetEngine:
         """`t` [1, B] arbitrary time values (the distinct ones are found with torch.unique: one host sync), or
         `t_index` [B] integer steps of an `n_steps` schedule (cached step table, no sync)."""
         _require_cuda(x, t, cond, cond_mask, t_index)
+        with torch.cuda.device(self.device):        # streams, allocations and the C side all follow the model's device
+            return self._forward(x, t, cond, cond_mask, t_index, n_steps)
+
+    def _forward(self, x, t, cond, cond_mask, t_index, n_steps):
         self.refresh()
         x2 = _f32c(x).reshape(-1, self.program.input_dim)
         B = x2.shape[0]
@@ -234,6 +239,10 @@ class UNetEngine:
         _require_cuda(cond, y_init, noise, rec_y, rec_eps)
         if y_init.shape[0] == 0 and stats_reduce is None:
             return y_init
+        with torch.cuda.device(self.device):
+            return self._sample(cond, y_init, coef, T, omega, noise, seed, offset, norm_steps, rec_y, rec_eps, stats_reduce)
+
+    def _sample(self, cond, y_init, coef, T, omega, noise, seed, offset, norm_steps, rec_y, rec_eps, stats_reduce):
         self.refresh()
         table, images = self.step_table(T)
         self._bind(table, images)
@@ -271,6 +280,41 @@ class UNetEngine:
         if B > 0 and T - 1 - n_norm >= 0:
             _lib.check(self.lib.diffsg_sample_steps(self.handle, C.byref(args), T - 1 - n_norm, 0, 1, _lib.stream_ptr()), "diffsg_sample_steps")
         return y_init
+
+
+def _sample_args(engine, cond, y, coef_arr, T, omega, noise=None, seed=0, offset=0, norm_steps=4, rec_y=None, rec_eps=None):
+    return _lib.SampleArgs(cond_dev=cond.data_ptr(), y_dev=y.data_ptr(),
+                           noise_dev=noise.data_ptr() if noise is not None else None,
+                           rec_y_dev=rec_y.data_ptr() if rec_y is not None else None,
+                           rec_eps_dev=rec_eps.data_ptr() if rec_eps is not None else None,
+                           stat_ws_dev=engine._stat_ws.data_ptr(), coef_host=C.cast(coef_arr, C.c_void_p),
+                           B=y.shape[0], T=T, norm_steps=norm_steps, omega=float(omega), pad_=0,
+                           philox_seed=int(seed) & (2**64 - 1), philox_offset=int(offset) & (2**64 - 1))
+
+
+def sampler_pass_eps(engine: UNetEngine, cond, y_t, step: int, coef, T: int):
+    """(eps_0, eps_1): the unconditional and the conditional prediction of the SAMPLER kernels (the fused path, not
+    `forward`) on the state `y_t` [B, M] of reverse step `step`: two single-step launches whose guidance weight turns
+    the recorded mixed eps = (1 + omega) eps_1 - omega eps_0 into one pass each (omega = -1 -> eps_0, omega = 0 ->
+    eps_1).  Teacher-forced parity checks and bench.py's `parity` record read per-pass errors through this."""
+    _require_cuda(cond, y_t)
+    B, M = y_t.shape
+    with torch.cuda.device(engine.device):
+        engine.refresh()
+        table, images = engine.step_table(T)
+        engine._bind(table, images)
+        if engine._stat_ws is None or engine._stat_ws.numel() < 2 * T:
+            engine._stat_ws = torch.zeros(2 * max(T, 64), dtype=torch.float64, device=engine.device)
+        coef_arr = (C.c_float * (3 * T))(*[float(v) for v in coef])
+        rec = torch.empty(T, B, M, dtype=torch.float32, device=engine.device)     # only plane T-1-step is written
+        out = []
+        for omega in (-1.0, 0.0):
+            y = y_t.detach().to(torch.float32).clone().contiguous()
+            args = _sample_args(engine, cond, y, coef_arr, T, omega, rec_eps=rec)
+            _lib.check(engine.lib.diffsg_sample_steps(engine.handle, C.byref(args), step, step, 0, _lib.stream_ptr()),
+                       "diffsg_sample_steps")
+            out.append(rec[T - 1 - step].clone())
+    return out[0], out[1]
 
 
 def unet_forward(model, x, t, cond, cond_mask):

@@ -78,3 +78,39 @@ def evaluate(diffusion_model, X_test, Y_test, custom_config, omega=500, batch_si
     return dict(less_ratio=float(pred_rate.sum() / true_rate.sum()),
                 avg_rate_diff=float((pred_rate - true_rate).mean()), pred_rate=pred_rate,
                 true_rate=true_rate, Y_pred=Y_pred)
+
+
+# ---- script-level entry points (reference classifier_free_MSR.py:187-236, 248-298): same names, same constants
+MSR_NET = dict(proj_dim=128, dims=(64, 32, 16, 8), is_attn=(False, False, False, False), middle_attn=False, n_blocks=2)
+
+
+def _msr_net(M, sfn=1):
+    return dict(input_dim=M, cond_dim=sfn * M, **MSR_NET)
+
+
+def train_ddpm_msr(dataset_path="../datasets/3c_10w_10000samples.csv", epochs=200, lr=0.005, milestones=(100, 150),
+                   use_ema=False, device=None, **fit_kw):
+    """`train_ddpm_msr()` of the reference (T = 20, Adam lr 0.005, MultiStepLR [100, 150], bs 512, 200 epochs)."""
+    from . import scripts
+    X_train, Y_train, _, _, cfg = msr_data_load(dataset_path)
+    M, W = cfg["M"], cfg["W"]
+    return scripts.train(DDPM, (M, W), _msr_net(M, cfg["sfn"]), cfg, X_train, Y_train, epochs=epochs, lr=lr,
+                         milestones=milestones, use_ema=use_ema, device=device, **fit_kw)
+
+
+@torch.no_grad()
+def load_test_msr(ckpt_path, dataset_path="../datasets/3c_10w_10000samples.csv", omega=500, device=None, verbose=True):
+    """`load_test_msr(ckpt_path)` of the reference: sample the test split in 512-row batches at omega = 500, decode,
+    print the same report; additionally returns the numbers (the reference returns None)."""
+    from . import scripts
+    _, _, X_test, Y_test, cfg = msr_data_load(dataset_path)
+    M, W = cfg["M"], cfg["W"]
+    ddpm = scripts.load(DDPM, (M, W), _msr_net(M, cfg["sfn"]), cfg, ckpt_path, device=device)
+    out = evaluate(ddpm, X_test, Y_test, cfg, omega=omega, batch_size=512)
+    if verbose:
+        lo, hi = cfg["scaler_min"], cfg["scaler_max"]
+        Xs = torch.as_tensor(X_test, dtype=torch.float32, device=out["Y_pred"].device) * (hi - lo) + lo
+        scripts.report([("Y_pred", W * custom_decoder(out["Y_pred"])), ("Y_test", Y_test), ("X_test", Xs),
+                        ("pred_rate", out["pred_rate"]), ("true_rate", out["true_rate"])],
+                       [f"less ratio: {out['less_ratio']}", f"avg rate diff:\n {out['avg_rate_diff']}"])
+    return out

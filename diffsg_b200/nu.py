@@ -76,3 +76,37 @@ def evaluate(diffusion_model, X_test, Y_test, custom_config, omega=500, batch_si
     return dict(less_ratio=float(pred_rate.sum() / true_rate.sum()),
                 avg_rate_diff=float((pred_rate - true_rate).mean()), pred_rate=pred_rate,
                 true_rate=true_rate, Y_pred=Y_pred)
+
+
+# ---- script-level entry points (reference classifier_free_NU.py:213-264, 306-361): same names, same constants
+NU_NET = dict(proj_dim=32, dims=(32, 16, 8), is_attn=(False, False, False), middle_attn=False, n_blocks=2)
+
+
+def _nu_net(K):
+    return dict(input_dim=2 + K, cond_dim=2 * K, **NU_NET)
+
+
+def train_ddpm_nu(dataset_path="../datasets/3u_18mW_10000samples.csv", width=400, height=400, epochs=200, lr=0.004,
+                  milestones=(80, 200), use_ema=False, device=None, **fit_kw):
+    """`train_ddpm_nu()` of the reference (T = 20, Adam lr 0.004, MultiStepLR [80, 200], bs 512, 200 epochs)."""
+    from . import scripts
+    X_train, Y_train, _, _, _, cfg = nu_data_load(dataset_path, width, height)
+    K, P_sum = cfg["K"], cfg["P_sum"]
+    return scripts.train(DDPM, (K, P_sum), _nu_net(K), cfg, X_train, Y_train, epochs=epochs, lr=lr,
+                         milestones=milestones, use_ema=use_ema, device=device, **fit_kw)
+
+
+@torch.no_grad()
+def load_test_nu(ckpt_path, dataset_path="../datasets/3u_18mW_10000samples.csv", width=400, height=400, omega=500,
+                 device=None, verbose=True):
+    """`load_test_nu(ckpt_path)` of the reference; also returns the numbers it prints."""
+    from . import scripts
+    _, _, X_test, Y_test, _, cfg = nu_data_load(dataset_path, width, height)
+    K, P_sum = cfg["K"], cfg["P_sum"]
+    ddpm = scripts.load(DDPM, (K, P_sum), _nu_net(K), cfg, ckpt_path, device=device)
+    out = evaluate(ddpm, X_test, Y_test, cfg, omega=omega, batch_size=512)
+    if verbose:
+        scripts.report([("Y_pred", custom_decoder(out["Y_pred"], width, height, P_sum)), ("pred_rate", out["pred_rate"]),
+                        ("true_rate", out["true_rate"])],
+                       [f"less ratio: {out['less_ratio']}", f"avg rate diff:\n {out['avg_rate_diff']}"], precision=8)
+    return out

@@ -236,6 +236,15 @@ int diffsg_ema_update_multi(float* const* avg_ptrs_dev, const float* const* p_pt
                             const int64_t* sizes_dev, int32_t n_tensors, int64_t max_size,
                             double decay, int32_t copy_first, void* stream);
 
+/* Fused Adam (+ optional EMA) over flat fp32 buffers: torch.optim.Adam's update without weight decay / amsgrad
+ * (reference training loop: ddpm_opt/classifier_free_MSR.py:213,225 `optimizer.step()`), and in the same pass the
+ * EMA of ddpm_opt/ema.py:10-14 on the updated parameters when ema_dev != NULL and hyper_dev[5] != 0.
+ *   hyper_dev: 6 floats on the DEVICE = {lr, beta1, beta2, eps, ema_decay, ema_mode (0 off, 1 copy, 2 blend)}
+ *   step_dev : int64 on the device, number of steps taken so far (incremented by this call)
+ * Device-resident hyper-parameters keep the launch valid inside a CUDA graph while lr / the EMA gate change. */
+int diffsg_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, float* ema_dev, int64_t n,
+                     const float* hyper_dev, int64_t* step_dev, void* stream);
+
 /* Global (min, max) of a strided [B, width] slice -> mm_dev[2] (decoder statistics). */
 int diffsg_minmax(const float* y_dev, int64_t B, int32_t ld, int32_t col0, int32_t width,
                   float* mm_dev, void* stream);

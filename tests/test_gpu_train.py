@@ -1,0 +1,242 @@
+"""GPU tests of the training side and the script-level drop-in: the fused Adam (+ EMA) kernel, the EMA / kernel-plan
+coherence fix, loss + gradient parity on the 80-channel and attention nets, `train_ddpm_*` / `load_test_*`,
+`msr.evaluate` / `co.evaluate`, and the config-2 (80c) objective parity on data from the reference's generator."""
+import numpy as np
+import pytest
+import torch
+
+import diffsg_b200 as D
+from diffsg_b200 import _lib
+from oracle import ddpm_oracle as O
+from oracle.standin import CONFIGS
+
+from conftest import load_golden, rel_l2, standin_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+T = 20
+
+
+def cuda(a):
+    return torch.as_tensor(a).to(DEV)
+
+
+def test_fused_adam_matches_torch_adam_and_fuses_ema():
+    from diffsg_b200.parallel import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    n = 100_003
+    p0 = torch.randn(n, generator=g)
+    flat, grad = p0.clone().to(DEV), torch.zeros(n, device=DEV)
+    opt = FusedAdam(flat, grad, lr=3e-3)
+    ref_p = torch.nn.Parameter(p0.clone().to(DEV))
+    ref = torch.optim.Adam([ref_p], lr=3e-3)
+    ema = torch.zeros(n, device=DEV)
+    ema_ref = None
+    for step in range(1, 8):
+        gr = torch.randn(n, generator=g).to(DEV) * (10.0 ** (step % 3 - 1))
+        grad.copy_(gr)
+        ref_p.grad = gr.clone()
+        if step == 4:
+            opt.set_lr(1e-3)
+            ref.param_groups[0]["lr"] = 1e-3
+        mode = 0 if step < 3 else (1 if step == 3 else 2)      # EMA gate: closed, first update copies, then blends
+        opt.set_ema(0.99, mode)
+        opt.step(ema)
+        ref.step()
+        if mode == 1:
+            ema_ref = ref_p.detach().clone()
+        elif mode == 2:
+            ema_ref = 0.99 * ema_ref + 0.01 * ref_p.detach()
+        assert torch.allclose(flat, ref_p.detach(), rtol=2e-6, atol=1e-7), step
+    assert int(opt.step_dev) == 7
+    assert torch.allclose(ema, ema_ref, rtol=1e-5, atol=1e-7)
+
+
+def test_ema_update_invalidates_the_averaged_modules_kernel_plan():
+    """the fused EMA kernel writes `ema.module`'s parameters through raw pointers; a kernel plan already
+    built for the averaged module must notice, or it keeps running stale packed weights."""
+    ddpm, cfg = standin_model("nu_like", DEV)
+    g = load_golden("standin_nu_like.npz")
+    args = (cuda(g["x"]), cuda(g["ts"]) / T, cuda(g["cond"]), cuda(g["mask"]))
+    ddpm.ema.update_parameters(ddpm.model)                   # first update: copy
+    with torch.no_grad():
+        e0 = ddpm.ema.module(*args).clone()                  # builds + packs the averaged module's plan
+        assert rel_l2(e0.cpu(), g["eps"]) < 1e-3
+        for p in ddpm.model.parameters():
+            p.mul_(1.5)
+        ddpm.model.mark_params_changed()
+        for _ in range(50):
+            ddpm.ema.update_parameters(ddpm.model)           # decay 0.9999: moves the average a little each time
+        e1 = ddpm.ema.module(*args)
+        fresh = D.UNet1D(**cfg).to(DEV)
+        fresh.load_state_dict(ddpm.ema.module.state_dict())
+        e2 = fresh(*args)
+    assert rel_l2(e1.cpu(), e0.cpu()) > 1e-6                 # the plan saw the update ...
+    assert rel_l2(e1.cpu(), e2.cpu()) < 1e-5                 # ... and runs exactly the averaged weights
+    assert int(ddpm.ema.n_averaged) == 51
+
+
+@pytest.mark.parametrize("name", ["msr80c", "attn"])
+def test_training_loss_and_grads_match_oracle_autograd(name):
+    """Loss and every parameter gradient of the eps-MSE step on the 80-channel and the attention nets against the
+    oracle's autograd (the oracle is bit-identical to the reference forward; `oracle/make_golden.py`)."""
+    ddpm, cfg = standin_model(name, DEV)
+    M, Cd, B = cfg["input_dim"], cfg["cond_dim"], 192
+    g = torch.Generator().manual_seed(9)
+    y = torch.rand(B, M, generator=g)
+    cond = torch.rand(B, Cd, generator=g)
+    noise = torch.randn(B, M, generator=g)
+    ts = torch.randint(0, T, (1, B), generator=g)
+    mask = (torch.rand(B, 1, generator=g) < 0.9).float()
+    sd = {k: v.detach().cpu().clone().requires_grad_(k.startswith("model.")) for k, v in ddpm.state_dict().items()
+          if not k.startswith("ema.")}
+    loss_ref = O.q_sample_loss(sd, T, y, cond, ts, noise, mask)
+    loss_ref.backward()
+    y_t = torch.squeeze(ddpm.sqrt_alphas_cumprod[ts.to(DEV), None] * y.to(DEV)
+                        + ddpm.sqrt_one_minus_alphas_cumprod[ts.to(DEV), None] * noise.to(DEV))
+    ddpm.zero_grad()
+    loss = ddpm.loss_from(y_t, ts.to(DEV), cond.to(DEV), mask.to(DEV), noise.to(DEV))
+    loss.backward()
+    assert abs(float(loss.detach()) / float(loss_ref.detach()) - 1) < 1e-5
+    worst = 0.0
+    for pname, p in ddpm.model.named_parameters():
+        want = sd["model." + pname].grad
+        if want is None or float(want.abs().max()) == 0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-10, pname      # e.g. the attention block's unused norm
+            continue
+        worst = max(worst, rel_l2(p.grad.cpu(), want))
+    assert worst < 3e-4, worst
+
+
+# ---------------------------------------------------------------------------------------- script-level drop-in
+def _write_csv(path, arr):
+    np.savetxt(path, arr, delimiter=",", fmt="%.9g")
+
+
+def _msr_csv(tmp_path, n=700):
+    d = load_golden("msr_data.npz")
+    lo, hi, W = (float(v) for v in d["scaler"])
+    g = np.concatenate((d["X_train"], d["X_test"]))[:n] * (hi - lo) + lo
+    p = np.concatenate((d["Y_train"], d["Y_test"]))[:n]
+    rate = np.log2(1.0 + p * g).sum(axis=1, keepdims=True)
+    path = tmp_path / "3c_10w_700samples.csv"
+    _write_csv(path, np.concatenate((g, rate, p), axis=1))
+    return str(path)
+
+
+def _nu_csv(tmp_path, n=700):
+    d = load_golden("nu_data.npz")
+    X = d["X_test"][:n].copy()
+    Y = d["Y_test"][:n].copy()
+    X *= 400.0
+    Y[:, :2] *= 400.0
+    Y[:, 2:] *= 18.0
+    path = tmp_path / "3u_18mW_700samples.csv"
+    _write_csv(path, np.concatenate((X, Y, d["R_test"][:n, None]), axis=1))
+    return str(path)
+
+
+def _co_csv(tmp_path, n=600, nodes=3):
+    g = np.random.default_rng(3)
+    f = np.stack([g.uniform(1e5, 5e5, (n, nodes)), g.uniform(1e8, 5e8, (n, nodes)), g.uniform(1e9, 2e9, (n, nodes)),
+                  g.uniform(1e-6, 1e-5, (n, nodes)), g.integers(0, 2, (n, nodes)).astype(float), np.zeros((n, nodes))], axis=2)
+    alloc = g.dirichlet(np.ones(nodes), n) * (g.random((n, nodes)) > 0.3)
+    alloc = alloc / np.maximum(alloc.sum(axis=1, keepdims=True), 1e-9)
+    path = tmp_path / "3nodes_600samples.csv"
+    _write_csv(path, np.concatenate((f.reshape(n, -1), np.zeros((n, 1)), alloc), axis=1))
+    return str(path)
+
+
+@pytest.mark.parametrize("kind", ["msr", "nu", "co"])
+def test_train_and_load_test_entry_points(kind, tmp_path, capsys):
+    """`train_ddpm_*` -> `torch.save(state_dict)` -> `load_test_*`, the scripts' own round trip
+    (classifier_free_MSR.py:347-355), on a small CSV in the reference's file format."""
+    mod = getattr(D, kind)
+    csv = {"msr": _msr_csv, "nu": _nu_csv, "co": _co_csv}[kind](tmp_path)
+    train, test = getattr(mod, f"train_ddpm_{kind}"), getattr(mod, f"load_test_{kind}")
+    torch.manual_seed(0)
+    ddpm = train(dataset_path=csv, epochs=3, lr=1e-3, milestones=(2,), seed=0)
+    out = capsys.readouterr().out
+    assert "Epoch: 0, Loss:" in out and "Epoch: 2, Loss:" in out
+    sd = ddpm.state_dict()
+    assert len(sd) == 8 + 2 * len(list(ddpm.model.state_dict())) + 1        # buffers + model.* + ema.n_averaged + ema.module.*
+    ckpt = tmp_path / f"ddpm_{kind}.pt"
+    torch.save(sd, ckpt)
+    torch.manual_seed(1)
+    res = test(str(ckpt), dataset_path=csv, omega=3)
+    out = capsys.readouterr().out
+    key = "exceeded ratio" if kind == "co" else "less ratio"
+    assert key in out
+    val = res["exceeded_ratio" if kind == "co" else "less_ratio"]
+    assert np.isfinite(val) and val > 0
+    # the topology recorded nowhere but in the tensor shapes is recovered from them
+    assert D.infer_config_from_state_dict(sd)["dims"] == tuple(ddpm.model.dims)
+
+
+def test_msr_and_co_evaluate_use_the_reference_objectives():
+    """`msr.evaluate` / `co.evaluate` (the GPU-side `load_test_*` cores): decode + objective of what they sampled,
+    recomputed by the oracle's restatement of the reference decoders / objectives (MSR.py:239-245,284-288; CO.py:255-290)."""
+    d = load_golden("msr_data.npz")
+    lo, hi, W = (float(v) for v in d["scaler"])
+    ddpm, _ = standin_model("msr3c", DEV)
+    n = 1100
+    torch.manual_seed(3)
+    out = D.msr.evaluate(ddpm, d["X_test"][:n], d["Y_test"][:n], {"scaler_min": lo, "scaler_max": hi, "W": W}, omega=3, batch_size=512)
+    gains = torch.tensor(d["X_test"][:n]) * (hi - lo) + lo
+    want = O.msr_rate(W * O.msr_decode(out["Y_pred"].cpu()), gains)
+    assert rel_l2(out["pred_rate"].cpu(), want) < 1e-5 and rel_l2(out["true_rate"].cpu(), d["true_rate"][:n]) < 1e-6
+    assert abs(out["less_ratio"] - float(want.sum() / torch.tensor(d["true_rate"][:n]).sum())) < 1e-5
+    d = load_golden("co_data.npz")
+    lo, hi = (float(v) for v in d["scaler"])
+    ddpm, _ = standin_model("co", DEV)
+    torch.manual_seed(4)
+    out = D.co.evaluate(ddpm, d["X_test"], d["Y_test"], {"scaler_min": lo, "scaler_max": hi}, omega=3.0, batch_size=512)
+    raw = torch.tensor(d["X_test"]) * (hi - lo) + lo
+    want = O.co_cost(raw, O.co_decode(out["Y_pred"].cpu()))
+    assert rel_l2(out["pred_cost"].cpu(), want) < 1e-4 and rel_l2(out["true_cost"].cpu(), d["true_cost"]) < 1e-5
+    assert 0 <= out["accuracy"] <= len(d["X_test"]) and out["terrible"] >= 0
+
+
+def test_msr80c_objective_parity_on_reference_generated_data():
+    """BASELINE config 2 (the headline network): 80-channel data from the reference's own `SUM_RATE_GEN(M=80, W=20)`
+    (oracle/make_golden_80c.py), a STAND-IN checkpoint trained here with the reference recipe (the real
+    ddpm_msr_80c.pt is missing), omega = 500, identical injected noise: mean sum rate of every engine
+    within 0.5 % of the oracle's."""
+    from diffsg_b200.parallel import DataParallelTrainer
+    d = load_golden("msr80c_data.npz")
+    W = float(d["W"])
+    g_all, p_all = torch.tensor(d["g"]), torch.tensor(d["p"])
+    lo, hi = float(g_all.min()), float(g_all.max())
+    X = (g_all - lo) / (hi - lo)                       # msr_data_load's global min-max scaling (MSR.py:176-177)
+    n_tr = 1536
+    net = CONFIGS["msr80c"][1]
+    torch.manual_seed(0)
+    model = D.UNet1D(**net)
+    ddpm = D.msr.DDPM(T, model, 80, W, 1.0 - D.generate_cosine_schedule(T), DEV, (1, 80), {}, 0.1, 0.9999, 10, 5, False)
+    ddpm.apply(D.init_weights)
+    ddpm.to(DEV)
+    tr = DataParallelTrainer(ddpm, lr=1e-3, cuda_graph=True)
+    Xd, Yd = X[:n_tr].to(DEV), p_all[:n_tr].to(DEV)
+    gen = torch.Generator().manual_seed(1)
+    losses = []
+    for s in range(600):
+        idx = torch.randint(0, n_tr, (512,), generator=gen).to(DEV)
+        losses.append(tr.step(Yd[idx], Xd[idx]))
+    first, last = float(torch.stack(losses[:10]).mean()), float(torch.stack(losses[-50:]).mean())
+    assert last < 0.7 * first, (first, last)
+    Xte, gte = X[n_tr:], g_all[n_tr:]
+    B = Xte.shape[0]
+    sd = {k: v.detach().cpu().clone() for k, v in ddpm.state_dict().items() if not k.startswith("ema.")}
+    y_T, steps = O.draw_noise(B, (1, 80), T, 21)
+    with torch.no_grad():
+        y_ref = O.sample(sd, T, Xte, 500.0, y_T, steps)
+    ref = O.msr_rate(W * O.msr_decode(y_ref), gte).reshape(-1)
+    label = O.msr_rate(p_all[n_tr:], gte).reshape(-1)
+    for precision in ("fp32", "fp16x3", "fp16x2"):
+        ddpm.model.precision = precision
+        y0 = ddpm.sample(Xte.to(DEV), 500.0, y_init=y_T.reshape(B, 80), noise=torch.stack(steps).reshape(T - 2, B, 80))
+        obj = D.objectives.msr_decode_rate(y0.reshape(B, 80), gte.to(DEV), W).cpu().reshape(-1)
+        ratio = float(obj.mean()) / float(ref.mean())
+        print(f"[80c stand-in, omega=500, {precision}] mean sum rate {float(obj.mean()):.4f} vs oracle {float(ref.mean()):.4f} "
+              f"(labels {float(label.mean()):.4f}); ratio {ratio:.5f}")
+        assert abs(ratio - 1) < 5e-3, (precision, ratio)
