@@ -48,8 +48,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // Tight spin with a short back-off: for the one wait that sits on a tile's critical path (the MMA thread waiting
 // for the operand chunk the epilogue is about to publish).
+#ifndef DIFFSG_SPIN_NS
+#define DIFFSG_SPIN_NS 20
+#endif
+#ifndef DIFFSG_PARK_NS
+#define DIFFSG_PARK_NS 32
+#endif
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(DIFFSG_SPIN_NS);
 }
 // Producer-side wait (TMA / MMA threads): let the hardware park the thread for up to `ns` per probe
 // instead of spinning, so the waiting warp does not steal issue slots from the epilogue warp that
@@ -65,7 +71,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
             : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
             : "memory");
         if (ok) break;
-        __nanosleep(32);       // the hardware hint returns early on any barrier traffic of the CTA: back off explicitly
+        __nanosleep(DIFFSG_PARK_NS);       // the hardware hint returns early on any barrier traffic of the CTA: back off explicitly
     }
 }
 

@@ -181,6 +181,13 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 }
 
+// 4 consecutive columns, complete on return
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
 __device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -607,6 +614,9 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                 }
                 case OP_OUT: {
                     TCT_BEGIN(_t9);
+                    // One column quad (4 columns) per iteration of a ROLLED loop: this op runs once per pass over at most
+                    // 32 quads, and unrolled (with the Philox rounds and Box-Muller inlined per quad) it was a third of the
+                    // kernel's instructions -- instruction-cache footprint the hot LayerNorm loops pay for.
                     float4* stash = reinterpret_cast<float4*>(E.scr + P.stash_off) + row;
                     const float w1 = 1.0f + R.omega, w0 = R.omega;
                     const float ce = R.c_eps[step], crs = R.c_rs[step], cn = R.c_noise[step];
@@ -614,74 +624,68 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
                     const bool want_stats = step > R.T - 1 - R.norm_steps;
                     const int64_t plane = R.B * (int64_t)P.M;
                     const int64_t pidx = (int64_t)(R.T - 1 - step) * plane;
-                    for (int g = 0; g < ng; ++g) {
-                        tmem_ld16u(ta + g * 16, r);
-                        tmem_wait16(r);
-                        float xv[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) xv[j] = __uint_as_float(r[j]);
+                    const bool vec4 = (P.M & 3) == 0;           // rows are 16-byte aligned: float4 traffic
+                    const int nq = (dt + 3) >> 2;
+#pragma unroll 1
+                    for (int q = 0; q < nq; ++q) {
+                        const int c0 = q * 4;
+                        float xv[4];
+                        tmem_ld4(ta + c0, xv);
                         if (!kSampler) {
                             if (E.valid) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (g * 16 + j < dt) R.eps[E.grow * P.M + g * 16 + j] = xv[j];
+                                for (int j = 0; j < 4; ++j)
+                                    if (c0 + j < dt) R.eps[E.grow * P.M + c0 + j] = xv[j];
                             }
                             continue;
                         }
                         if (pass == 0) {           // unconditional pass: park eps_0
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                stash[(size_t)(g * 4 + q) * kRows] = make_float4(xv[q * 4], xv[q * 4 + 1], xv[q * 4 + 2], xv[q * 4 + 3]);
+                            stash[(size_t)q * kRows] = make_float4(xv[0], xv[1], xv[2], xv[3]);
                             continue;
                         }
+                        if (!E.valid) continue;
                         // conditional pass: guidance mix + posterior update (classifier_free_MSR.py:132-134)
-                        const bool vec4 = (P.M & 3) == 0;           // rows are 16-byte aligned: float4 traffic
+                        const int64_t idx = E.grow * P.M + c0;
+                        const float4 e0 = stash[(size_t)q * kRows];
+                        const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
+                        float z[4] = {0.f, 0.f, 0.f, 0.f}, yo[4], yn[4], ev[4];
+                        if (add_noise) {
+                            if (R.noise == nullptr) {
+                                philox_normal4((uint64_t)E.grow + R.offset, (uint32_t)step, (uint32_t)q, R.seed, z);
+                            } else if (vec4) {
+                                const float4 t = *reinterpret_cast<const float4*>(R.noise + pidx + idx);
+                                z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+                            } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int c0 = g * 16 + q * 4;
-                            if (c0 >= dt || !E.valid) continue;
-                            const int64_t idx = E.grow * P.M + c0;
-                            const float4 e0 = stash[(size_t)(g * 4 + q) * kRows];
-                            const float e0a[4] = {e0.x, e0.y, e0.z, e0.w};
-                            float z[4] = {0.f, 0.f, 0.f, 0.f}, yo[4], yn[4], ev[4];
-                            if (add_noise) {
-                                if (R.noise == nullptr) {
-                                    philox_normal4((uint64_t)E.grow + R.offset, (uint32_t)step, (uint32_t)(g * 4 + q), R.seed, z);
-                                } else if (vec4) {
-                                    const float4 t = *reinterpret_cast<const float4*>(R.noise + pidx + idx);
-                                    z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-                                } else {
+                                for (int j = 0; j < 4; ++j) if (c0 + j < dt) z[j] = R.noise[pidx + idx + j];
+                            }
+                        }
+                        if (vec4) {
+                            const float4 t = *reinterpret_cast<const float4*>(R.y + idx);
+                            yo[0] = t.x; yo[1] = t.y; yo[2] = t.z; yo[3] = t.w;
+                        } else {
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) if (c0 + j < dt) z[j] = R.noise[pidx + idx + j];
+                            for (int j = 0; j < 4; ++j) yo[j] = (c0 + j < dt) ? R.y[idx + j] : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ev[j] = w1 * xv[j] - w0 * e0a[j];
+                            yn[j] = (yo[j] - ce * ev[j]) * crs;
+                            if (add_noise) yn[j] += cn * z[j];
+                            if (want_stats && c0 + j < dt) { st_s += (double)yn[j]; st_q += (double)yn[j] * (double)yn[j]; }
+                        }
+                        if (vec4) {
+                            *reinterpret_cast<float4*>(R.y + idx) = make_float4(yn[0], yn[1], yn[2], yn[3]);
+                            if (R.rec_eps) *reinterpret_cast<float4*>(R.rec_eps + pidx + idx) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                            if (R.rec_y && !want_stats) *reinterpret_cast<float4*>(R.rec_y + pidx + idx) = make_float4(yn[0], yn[1], yn[2], yn[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (c0 + j < dt) {
+                                    R.y[idx + j] = yn[j];
+                                    if (R.rec_eps) R.rec_eps[pidx + idx + j] = ev[j];
+                                    if (R.rec_y && !want_stats) R.rec_y[pidx + idx + j] = yn[j];
                                 }
-                            }
-                            if (vec4) {
-                                const float4 t = *reinterpret_cast<const float4*>(R.y + idx);
-                                yo[0] = t.x; yo[1] = t.y; yo[2] = t.z; yo[3] = t.w;
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) yo[j] = (c0 + j < dt) ? R.y[idx + j] : 0.f;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                ev[j] = w1 * xv[q * 4 + j] - w0 * e0a[j];
-                                yn[j] = (yo[j] - ce * ev[j]) * crs;
-                                if (add_noise) yn[j] += cn * z[j];
-                                if (want_stats && c0 + j < dt) { st_s += (double)yn[j]; st_q += (double)yn[j] * (double)yn[j]; }
-                            }
-                            if (vec4) {
-                                *reinterpret_cast<float4*>(R.y + idx) = make_float4(yn[0], yn[1], yn[2], yn[3]);
-                                if (R.rec_eps) *reinterpret_cast<float4*>(R.rec_eps + pidx + idx) = make_float4(ev[0], ev[1], ev[2], ev[3]);
-                                if (R.rec_y && !want_stats) *reinterpret_cast<float4*>(R.rec_y + pidx + idx) = make_float4(yn[0], yn[1], yn[2], yn[3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (c0 + j < dt) {
-                                        R.y[idx + j] = yn[j];
-                                        if (R.rec_eps) R.rec_eps[pidx + idx + j] = ev[j];
-                                        if (R.rec_y && !want_stats) R.rec_y[pidx + idx + j] = yn[j];
-                                    }
-                            }
                         }
                     }
                     TCT_END(_t9, 7);
