@@ -75,6 +75,7 @@ SYMBOLS = {
     "diffsg_ema_update": (C.c_int, [_P, _P, _I64, _D, _I32, _P]),
     "diffsg_ema_update_multi": (C.c_int, [_P, _P, _P, _I32, _I64, _D, _I32, _P]),
     "diffsg_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "diffsg_mlp_forward": (C.c_int, [_P, _P, _I64, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32, _I32, _P, _P]),
     "diffsg_minmax": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
     "diffsg_objective_msr": (C.c_int, [_P, _P, _P, _F, _P, _P, _I64, _I32, _P]),
     "diffsg_rate_msr": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),

@@ -5,6 +5,7 @@
 //   NU decode/rate ddpm_opt/classifier_free_NU.py:267-303
 //   CO decode/cost ddpm_opt/classifier_free_CO.py:255-290
 #include <cfloat>
+#include <cstring>
 #include "common.cuh"
 
 namespace diffsg {
@@ -76,6 +77,58 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
     }
 }
 __global__ void adam_bump_kernel(int64_t* step_dev) { step_dev[0] += 1; }
+
+// ------------------------------------------------------------------------------ batched small MLP
+// The comparison baselines of the reference are tiny MLPs evaluated row by row (MTFNN: baselines/MTFNN.py:43-52,
+// 122-131, 187-211; the PPO actor / critic: baselines/PPO.py:44-62): Linear -> {ReLU, Tanh} chains with a Sigmoid /
+// Softmax / split head.  One thread carries one row through all layers; the weights sit in shared memory and are
+// read as warp-wide broadcasts, so the kernel moves in + out floats per row over HBM and nothing else.
+constexpr int kMlpMaxLayers = 8, kMlpMaxWidth = 128;
+struct MlpDesc {
+    int n_layers, in_dim;
+    int out[kMlpMaxLayers];      // output width of layer l
+    int act[kMlpMaxLayers];      // 0 none, 1 ReLU, 2 Tanh, 3 Sigmoid
+    int w_off[kMlpMaxLayers];    // float offsets of W [out][in] and b [out] in the parameter blob
+    int b_off[kMlpMaxLayers];
+    int head, head_split;        // head: 0 none, 1 softmax over all columns, 2 sigmoid on [0, split) + softmax on [split, N)
+    int n_params;
+};
+__global__ void mlp_forward_kernel(const float* __restrict__ x, const float* __restrict__ params, MlpDesc d,
+                                   float* __restrict__ out, int64_t B) {
+    extern __shared__ float sp[];
+    for (int i = threadIdx.x; i < d.n_params; i += blockDim.x) sp[i] = params[i];
+    __syncthreads();
+    float a[kMlpMaxWidth], h[kMlpMaxWidth];
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < B; row += (int64_t)gridDim.x * blockDim.x) {
+        for (int k = 0; k < d.in_dim; ++k) a[k] = x[row * d.in_dim + k];
+        int kin = d.in_dim;
+        for (int l = 0; l < d.n_layers; ++l) {
+            const float* W = sp + d.w_off[l];
+            const float* bias = sp + d.b_off[l];
+            const int n_out = d.out[l];
+            for (int n = 0; n < n_out; ++n) {
+                float acc = bias[n];
+                for (int k = 0; k < kin; ++k) acc = fmaf(W[n * kin + k], a[k], acc);
+                if (d.act[l] == 1) acc = fmaxf(acc, 0.f);
+                else if (d.act[l] == 2) acc = tanhf(acc);
+                else if (d.act[l] == 3) acc = 1.0f / (1.0f + expf(-acc));
+                h[n] = acc;
+            }
+            for (int n = 0; n < n_out; ++n) a[n] = h[n];
+            kin = n_out;
+        }
+        const int s0 = d.head == 2 ? d.head_split : 0;
+        if (d.head == 2)
+            for (int n = 0; n < s0 && n < kin; ++n) a[n] = 1.0f / (1.0f + expf(-a[n]));
+        if (d.head != 0 && kin > s0) {
+            float m = -FLT_MAX, z = 0.f;
+            for (int n = s0; n < kin; ++n) m = fmaxf(m, a[n]);
+            for (int n = s0; n < kin; ++n) { a[n] = expf(a[n] - m); z += a[n]; }
+            for (int n = s0; n < kin; ++n) a[n] /= z;
+        }
+        for (int n = 0; n < kin; ++n) out[row * kin + n] = a[n];
+    }
+}
 
 // ------------------------------------------------------------------------------ min/max
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
@@ -273,6 +326,33 @@ int diffsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, i
     adam_flat_kernel<<<blocks_for(n, 1024), 256, 0, st>>>(p, g, m, v, ema, n, hyper, step_dev);
     adam_bump_kernel<<<1, 1, 0, st>>>(step_dev);
     count_launch(2);
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_mlp_forward(const float* x, const float* params, int64_t B, int32_t in_dim, int32_t n_layers,
+                       const int32_t* out_dims, const int32_t* acts, int32_t head, int32_t head_split, float* out,
+                       void* stream) {
+    if (!x || !params || !out || !out_dims || !acts || B < 0 || in_dim < 1 || in_dim > kMlpMaxWidth || n_layers < 1 ||
+        n_layers > kMlpMaxLayers || head < 0 || head > 2 || head_split < 0) { set_error("mlp_forward: bad argument"); return DIFFSG_E_INVALID; }
+    if (B == 0) return DIFFSG_OK;
+    MlpDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n_layers = n_layers; d.in_dim = in_dim; d.head = head; d.head_split = head_split;
+    int off = 0, kin = in_dim;
+    for (int l = 0; l < n_layers; ++l) {
+        if (out_dims[l] < 1 || out_dims[l] > kMlpMaxWidth || acts[l] < 0 || acts[l] > 3) { set_error("mlp_forward: layer %d out of range", l); return DIFFSG_E_UNSUPPORTED; }
+        d.out[l] = out_dims[l]; d.act[l] = acts[l];
+        d.w_off[l] = off; off += out_dims[l] * kin;      // the blob is W_0 | b_0 | W_1 | b_1 | ... (nn.Linear layouts)
+        d.b_off[l] = off; off += out_dims[l];
+        kin = out_dims[l];
+    }
+    d.n_params = off;
+    const size_t smem = sizeof(float) * (size_t)off;
+    if (smem > 200 * 1024) { set_error("mlp_forward: %zu bytes of weights exceed shared memory", smem); return DIFFSG_E_UNSUPPORTED; }
+    DIFFSG_CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_forward_kernel<<<blocks_for(B, 128, 148 * 8), 128, smem, (cudaStream_t)stream>>>(x, params, d, out, B);
+    count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
     return DIFFSG_OK;
 }

@@ -245,6 +245,15 @@ int diffsg_ema_update_multi(float* const* avg_ptrs_dev, const float* const* p_pt
 int diffsg_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, float* ema_dev, int64_t n,
                      const float* hyper_dev, int64_t* step_dev, void* stream);
 
+/* Batched forward of a small MLP: x[B, in_dim] -> out[B, out_dims[n_layers-1]].  Replaces the row-by-row torch
+ * evaluation of the reference's comparison baselines: MTFNN (baselines/MTFNN.py:43-52, 122-131, 187-211) and the PPO
+ * actor / critic (baselines/PPO.py:44-62).  params_dev = W_0 [out_0][in] | b_0 | W_1 | b_1 | ... (nn.Linear layouts);
+ * acts[l]: 0 none, 1 ReLU, 2 Tanh, 3 Sigmoid; head: 0 none, 1 row softmax, 2 sigmoid on columns [0, head_split)
+ * and softmax on the rest (MTFNN.forward for NU, MTFNN.py:208-210).  Widths <= 128, <= 8 layers. */
+int diffsg_mlp_forward(const float* x_dev, const float* params_dev, int64_t B, int32_t in_dim, int32_t n_layers,
+                       const int32_t* out_dims, const int32_t* acts, int32_t head, int32_t head_split, float* out_dev,
+                       void* stream);
+
 /* Global (min, max) of a strided [B, width] slice -> mm_dev[2] (decoder statistics). */
 int diffsg_minmax(const float* y_dev, int64_t B, int32_t ld, int32_t col0, int32_t width,
                   float* mm_dev, void* stream);

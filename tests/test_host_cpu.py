@@ -388,3 +388,24 @@ def test_script_entry_points_exist_with_reference_names_and_defaults():
         from diffsg_b200 import scripts
         with pytest.raises(_lib.DiffsgError):
             scripts.default_device()
+
+
+# ------------------------------------------------------------------------------ batched baselines
+def test_baseline_mirrors_strict_load_reference_checkpoints():
+    from baseline_cases import CASES, build_case, golden
+    from diffsg_b200 import _lib
+    z = golden()
+    for name in CASES:
+        m = build_case(name, z)                      # load_state_dict(strict=True) inside
+        with pytest.raises(_lib.DiffsgError):        # no CPU path
+            m(torch.from_numpy(z[f"{name}.x"]))
+
+
+def test_baseline_mlp_plan_codes():
+    from diffsg_b200 import baselines as B
+    lin, acts, head = B._mlp_plan(list(B.mtfnn_msr_model(3, 3)))
+    assert [m.out_features for m in lin] == [8, 16, 8, 3] and acts == [1, 1, 1, 0] and head == 1
+    lin, acts, head = B._mlp_plan(list(B.mtfnn_co_model(9, 3)))
+    assert acts == [1, 1, 1, 3] and head == 0
+    lin, acts, head = B._mlp_plan(list(B.PPOAgent(6, 5).actor))
+    assert acts == [2, 2, 2, 0] and head == 0
