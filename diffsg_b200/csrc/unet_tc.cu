@@ -414,14 +414,18 @@ int tc_sample_launch(diffsg_plan* p, const diffsg_sample_args* a, int norm_steps
 #ifdef DIFFSG_TC_TIMING
     {
         static long long* dbg = nullptr;
-        if (!dbg) { cudaMalloc(&dbg, 12 * sizeof(long long)); }
+        if (!dbg) { cudaMalloc(&dbg, 204 * sizeof(long long)); }
         p->tc->dev.debug = dbg;
         cudaStreamSynchronize(st);
-        long long h[12];
+        long long h[204];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         const char* names[12] = {"acc_wait", "pkg_wait", "ln_pass1", "ln_pass2", "catln", "raw", "cond", "out", "total", "mma_wait_w", "mma_wait_a", "-"};
         fprintf(stderr, "[tc timing, cycles of thread 0 / CTA 0, previous launch]");
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
+        fprintf(stderr, "\n[tc stage wait]");       // per stage: cycles thread 0 waited for the accumulator ...
+        for (int i = 0; i < 96; ++i) fprintf(stderr, " %lld", h[12 + i]);
+        fprintf(stderr, "\n[tc stage work]");       // ... and spent on everything else
+        for (int i = 0; i < 96; ++i) fprintf(stderr, " %lld", h[108 + i]);
         fprintf(stderr, "\n");
     }
 #endif

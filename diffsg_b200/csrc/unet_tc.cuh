@@ -96,10 +96,15 @@ struct SmemLayout {
     uint64_t a_full[kASlots], a_empty[kASlots], w_full[kWStages], w_empty[kWStages], p_full[kPSlots],
         p_empty[kPSlots], acc_full;
     uint32_t tmem_base, pad_;
+#ifdef DIFFSG_TC_TIMING
+    uint32_t t_wait[96], t_work[96];        // per-stage cycles of thread 0 (accumulator wait / everything else)
+#endif
     // followed by the W ring: kWStages x [(nterms == 3 ? 2 : 1) weight images | bias image] (dynamic)
 };
+#ifndef DIFFSG_TC_TIMING
 static_assert((((sizeof(SmemLayout) + 127) & ~size_t(127)) + kWStages * (kWStageBytes + kBiasBytes) + 128 + 1024) * kCtasPerSm <= 233472,
               "kCtasPerSm CTAs (fp16x2) must fit the SM's 228 KB of shared memory");
+#endif
 
 // What one launch does: kSampler -> steps step_hi..step_lo, two passes each; else one forward.
 struct RunArgs {
@@ -434,15 +439,25 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
         const Stage sg = c_stages[si];
         const bool has_pkg = sg.pkg_f4 != 0;
         const uint32_t psl = pseq % kPSlots;
+#ifdef DIFFSG_TC_TIMING
+        const long long _s0 = clock64();
+        long long _s1 = _s0, _s2 = _s0;
+#endif
         // the package was requested long ago: check it first, in the shadow of the accumulator wait
         if (has_pkg) { TCT_BEGIN(_tk); mbar_wait(&S.p_full[psl], (pseq / kPSlots) & 1); TCT_END(_tk, 1); }
         const float* pk_ = S.pkg[psl];
         if (sg.bits & 4) {
             TCT_BEGIN(_ta);
+#ifdef DIFFSG_TC_TIMING
+            _s1 = clock64();
+#endif
             mbar_wait(&S.acc_full, acc_phase);
             acc_phase ^= 1;
             tcgen05_fence_after();
             TCT_END(_ta, 0);
+#ifdef DIFFSG_TC_TIMING
+            _s2 = clock64();
+#endif
         }
         for (int ei = sg.epi_begin; ei < sg.epi_begin + sg.n_epi; ++ei) {
             const Epi op = c_epis[ei];
@@ -699,6 +714,12 @@ __device__ __forceinline__ void run_epilogue(SmemLayout& S, const TcDev& P, cons
             mbar_arrive(&S.p_empty[psl]);
             ++pseq;
         }
+#ifdef DIFFSG_TC_TIMING
+        if (E.row == 0 && si < 96) {
+            S.t_wait[si] += (uint32_t)(_s2 - _s1);
+            S.t_work[si] += (uint32_t)(clock64() - _s0 - (_s2 - _s1));
+        }
+#endif
     }
 }
 
@@ -872,6 +893,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
         E.amax = 0.f;
 #ifdef DIFFSG_TC_TIMING
         for (int i = 0; i < 12; ++i) E.tacc[i] = 0;
+        if (threadIdx.x == 0) for (int i = 0; i < 96; ++i) { S.t_wait[i] = 0; S.t_work[i] = 0; }
 #endif
         E.scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats;
         uint32_t acc_phase = 0, pseq = 0;
@@ -915,8 +937,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) tc_unet_kernel(TcDev P, 
                 }
         }
 #ifdef DIFFSG_TC_TIMING
-        if (blockIdx.x == 0 && threadIdx.x == 0 && P.debug)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && P.debug) {
             for (int i = 0; i < 9; ++i) P.debug[i] = E.tacc[i];
+            for (int i = 0; i < 96; ++i) { P.debug[12 + i] = S.t_wait[i]; P.debug[108 + i] = S.t_work[i]; }
+        }
 #endif
         if (E.amax > 65504.0f && P.status) atomicOr(P.status, kStatusOverflow);
         if (kSampler && R.step_hi > R.T - 1 - R.norm_steps) {
