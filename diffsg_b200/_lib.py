@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libdiffsg_b200.so"
 INCLUDE_DIR = PKG_DIR.parent / "include"
-SOURCES = ("diffsg.cu", "side_kernels.cu", "unet_tc.cu")
+SOURCES = ("diffsg.cu", "side_kernels.cu", "unet_tc.cu", "train_tc.cu")
 # Tensor-core engine geometry (diffsg_b200/csrc/unet_tc.cuh): K columns per operand chunk, TMEM columns per
 # accumulator region (= widest vector), co-resident CTAs per SM.
 TC_VARIANT = dict(chunk=64, aslots=2, region=128, ctas=2)
@@ -24,7 +24,7 @@ NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared")
 EXTRA_FLAGS = tuple(filter(None, os.environ.get("DIFFSG_NVCC_FLAGS", "").split()))   # experiments: -DDIFFSG_TC_TIMING ...
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OP_GEMM, OP_LNSW, OP_PUSH, OP_POP = 1, 2, 3, 4
 F_ACC, F_TIME, F_NOBIAS = 1, 2, 4
 BUF_COND, N_BUF = 4, 4
@@ -60,6 +60,30 @@ class SampleArgs(C.Structure):
                 ("philox_offset", C.c_uint64)]
 
 
+class Mat(C.Structure):
+    """diffsg_mat / diffsg_mat_out: cat(p0[rows, k0], p1[rows, k1]) along columns."""
+    _fields_ = [("p0", C.c_void_p), ("p1", C.c_void_p), ("k0", C.c_int32), ("k1", C.c_int32)]
+
+
+class TlinFwdArgs(C.Structure):
+    _fields_ = [("a", Mat), ("w", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("a2", Mat), ("w2", C.c_void_p), ("bias2", C.c_void_p),
+                ("add", C.c_void_p), ("gadd", C.c_void_p), ("gidx", C.c_void_p), ("y", C.c_void_p), ("B", C.c_int64),
+                ("N", C.c_int32), ("reserved", C.c_int32)]
+
+
+class TlinDgradArgs(C.Structure):
+    _fields_ = [("dy", C.c_void_p), ("w", C.c_void_p), ("x", Mat), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("dres", Mat), ("dx", Mat), ("dgamma", C.c_void_p),
+                ("dbeta", C.c_void_p), ("B", C.c_int64), ("N", C.c_int32), ("K", C.c_int32)]
+
+
+class TlinWgradArgs(C.Structure):
+    _fields_ = [("dy", C.c_void_p), ("a", Mat), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
+                ("rstd", C.c_void_p), ("gidx", C.c_void_p), ("dw", C.c_void_p), ("dbias", C.c_void_p),
+                ("dgadd", C.c_void_p), ("B", C.c_int64), ("N", C.c_int32), ("gadd_rows", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/diffsg_b200.h declares
 _P, _I32, _I64, _F, _D, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
 SYMBOLS = {
@@ -89,6 +113,9 @@ SYMBOLS = {
     "diffsg_plan_set_engine": (C.c_int, [_P, _I32]),
     "diffsg_lnsw_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "diffsg_lnsw_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P]),
+    "diffsg_tlin_forward": (C.c_int, [C.POINTER(TlinFwdArgs), _P]),
+    "diffsg_tlin_dgrad": (C.c_int, [C.POINTER(TlinDgradArgs), _P]),
+    "diffsg_tlin_wgrad": (C.c_int, [C.POINTER(TlinWgradArgs), _P]),
     "diffsg_plan_query": (C.c_int, [_P, _I32]),
     "diffsg_sample_steps": (C.c_int, [_P, C.POINTER(SampleArgs), _I32, _I32, _I32, _P]),
     "diffsg_sample_renorm": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),

@@ -1,0 +1,796 @@
+// Training GEMMs on the 5th-generation tensor cores (sm_100a): the Linear layers of the eps-MSE training step
+// (reference ddpm_opt/UNetCF.py:83-95 ResidualBlock, :318-356 UNet1D.forward; loss classifier_free_MSR.py:100-112)
+// as three hand-written tcgen05 kernels with the LayerNorm -> Swish pairs fused in:
+//
+//   tlin_fwd_kernel    y  = [swish(LN(a)) | a] . W^T (+ a2 . W2^T) + bias (+ bias2) (+ add) (+ gadd[gidx])
+//   tlin_dgrad_kernel  dx = dy . W, optionally pushed through the LayerNorm -> Swish backward in the epilogue
+//                      (dgamma / dbeta column sums by a shuffle butterfly), plus an optional addend
+//   tlin_wgrad_kernel  dW += dy^T . act(a), db += column sums of dy, d(gadd) += scatter of dy by gidx — the last
+//                      two on the tensor cores as well (a ones column and T one-hot columns appended to act(a))
+//
+// Arithmetic: operands are fp32 in HBM; every operand element is split into bf16 (hi, lo) while it is staged into
+// shared memory and each product runs as three kind::f16 (bf16) MMAs (hi.hi + lo.hi + hi.lo) with fp32 accumulation
+// in TMEM: 16 significant operand bits, fp32 range (gradients of 1e-8 do not underflow) — "bf16x3".
+// One CTA = 128 threads = one 128-row tile (thread == row == TMEM lane in every prologue / epilogue); operands are
+// UMMA K-major no-swizzle core-matrix chunks of 64 contraction columns (the sampler engine's layout, unet_tc.cuh).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace diffsg {
+namespace ttc {
+
+using namespace diffsg::tc;
+
+constexpr int kRows = 128;              // rows per tile = UMMA M = TMEM lanes
+constexpr int kKC = 64;                 // contraction columns per staged chunk
+constexpr uint32_t kLBO = 128;          // K-adjacent core matrices are contiguous
+constexpr uint32_t kSBO = kKC * 16;     // next 8 rows
+constexpr int kThreads = 128;
+constexpr int kWgradKT = 224;           // feature columns per wgrad CTA (+ <= 32 extra columns = 256 = max UMMA N)
+constexpr int kMaxExtra = 32;
+
+struct Mat {                            // logical row-major [rows, k0 + k1] = cat(p0[rows, k0], p1[rows, k1])
+    const float* p0;
+    const float* p1;
+    int k0, k1, vec;                    // vec: both halves 8-column / 16-byte aligned
+};
+struct MatOut {
+    float* p0;
+    float* p1;
+    int k0, k1, vec;
+};
+
+__device__ __forceinline__ uint32_t op_off(int mn, int k) {
+    return (uint32_t)(mn >> 3) * kSBO + (uint32_t)(k >> 3) * 128u + (uint32_t)(mn & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+    // c = f32 (bit 4), a = b = bf16 (format 1 at bits 7 and 10), both K-major
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void store_split(uint8_t* hi_base, uint32_t lo_delta, uint32_t off, const float (&v)[8]) {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(hi_base + off) = hi;
+    *reinterpret_cast<uint4*>(hi_base + lo_delta + off) = lo;
+}
+
+// 8 consecutive columns [c, c + 8) of one row; columns beyond the matrix read as 0
+__device__ __forceinline__ void load8(const Mat& m, int64_t row, int c, float (&v)[8]) {
+    const int K = m.k0 + m.k1;
+    if (m.vec) {
+        if (c >= K) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            return;
+        }
+        const float* p = c < m.k0 ? m.p0 + row * m.k0 + c : m.p1 + row * m.k1 + (c - m.k0);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int cc = c + j;
+            v[j] = cc < m.k0 ? __ldg(m.p0 + row * m.k0 + cc) : (cc < K ? __ldg(m.p1 + row * m.k1 + (cc - m.k0)) : 0.f);
+        }
+    }
+}
+__device__ __forceinline__ float load1(const Mat& m, int64_t row, int c) {
+    return c < m.k0 ? __ldg(m.p0 + row * m.k0 + c) : __ldg(m.p1 + row * m.k1 + (c - m.k0));
+}
+__device__ __forceinline__ void store8(const MatOut& m, int64_t row, int c, const float (&v)[8]) {
+    const int K = m.k0 + m.k1;
+    if (m.vec) {
+        if (c >= K) return;
+        float* p = c < m.k0 ? m.p0 + row * m.k0 + c : m.p1 + row * m.k1 + (c - m.k0);
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int cc = c + j;
+            if (cc < m.k0) m.p0[row * m.k0 + cc] = v[j];
+            else if (cc < K) m.p1[row * m.k1 + (cc - m.k0)] = v[j];
+        }
+    }
+}
+__device__ __forceinline__ float sigmoidf_(float n) { return 1.0f / (1.0f + __expf(-n)); }
+
+__device__ __forceinline__ void red_add(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// column sums over the 32 lanes of a warp of 16 per-lane values: 16 shuffles (recursive halving).  Every lane returns the
+// sum of column 8 b4 + 4 b3 + 2 b2 + b1 (b_i = bit i of the lane id); lanes l and l ^ 1 hold the same column.
+__device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4, u1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = u4 ? v[i] : v[i + 8], keep = u4 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = u3 ? a[i] : a[i + 4], keep = u3 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = u2 ? b[i] : b[i + 2], keep = u2 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = u1 ? c[0] : c[1], keep = u1 ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+__device__ __forceinline__ int colsum16_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+// ------------------------------------------------------------------------------------------------ CTA scaffolding
+struct Smem {
+    uint64_t bar;
+    uint32_t tmem_base;
+    uint32_t pad_;
+};
+
+// operand ring: [A hi | A lo | B hi | B lo], A = 128 x 64 bf16 = 16 KB per term, B = bn_pad x 64 bf16 per term
+__device__ __forceinline__ uint32_t a_term_bytes() { return kRows * kKC * 2; }
+
+__device__ __forceinline__ void cta_setup(Smem& S, uint32_t tmem_cols) {
+    if (threadIdx.x == 0) {
+        mbar_init(&S.bar, 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 32) {
+        __syncwarp();
+        tmem_alloc(&S.tmem_base, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+}
+__device__ __forceinline__ void cta_teardown(Smem& S, uint32_t tmem_cols) {
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(S.tmem_base, tmem_cols);
+}
+
+// publish the staged chunk, issue its MMAs (one thread) and wait until the tensor core has consumed it
+__device__ __forceinline__ void mma_chunk(Smem& S, uint8_t* a_hi, uint8_t* b_hi, uint32_t b_term, int kw, uint32_t idesc,
+                                          uint32_t d_tmem, bool first, uint32_t& phase) {
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        const uint64_t da_hi = make_smem_desc(smem_u32(a_hi), kLBO, kSBO, 0);
+        const uint64_t da_lo = make_smem_desc(smem_u32(a_hi + a_term_bytes()), kLBO, kSBO, 0);
+        const uint64_t db_hi = make_smem_desc(smem_u32(b_hi), kLBO, kSBO, 0);
+        const uint64_t db_lo = make_smem_desc(smem_u32(b_hi + b_term), kLBO, kSBO, 0);
+        uint32_t acc = first ? 0u : 1u;
+        for (int ks = 0; ks < kw / 16; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 16);        // two core matrices = 256 bytes, >> 4
+            umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
+            umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
+            umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+            acc = 1;
+        }
+        umma_commit(&S.bar);
+    }
+    mbar_wait(&S.bar, phase);
+    phase ^= 1;
+    tcgen05_fence_after();
+}
+
+// operand whose contraction dimension is contiguous in memory: src[mn][k] with row stride ld (weights [N, K] in the
+// forward).  Items (mn, 8-column piece), mn fastest across lanes: 16-byte conflict-free shared stores.
+__device__ __forceinline__ void stage_rowmajor_w(uint8_t* hi_base, uint32_t lo_delta, const float* __restrict__ w, int ld,
+                                                 int n0, int n_valid, int n_pad, int k0, int K, int kw, bool vec) {
+    const int pieces = kw >> 3;
+    for (int it = threadIdx.x; it < n_pad * pieces; it += kThreads) {
+        const int n = it % n_pad, j = it / n_pad;
+        const int c = k0 + j * 8;
+        float v[8];
+        if (n < n_valid && c < K) {
+            const float* p = w + (size_t)(n0 + n) * ld + c;
+            if (vec) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (c + q < K) ? __ldg(p + q) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+        }
+        store_split(hi_base, lo_delta, op_off(n, j * 8), v);
+    }
+}
+
+// ================================================================================================ forward
+struct FwdArgs {
+    Mat a;
+    const float* w;
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    float* mean;
+    float* rstd;
+    Mat a2;
+    const float* w2;
+    const float* bias2;
+    const float* add;
+    const float* gadd;
+    const int64_t* gidx;
+    float* y;
+    int64_t B;
+    int N, n_pad, tmem_cols, wvec, wvec2, yvec;
+};
+
+__global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Smem S;
+    __shared__ float s_gamma[256], s_beta[256];
+    uint8_t* a_hi = smem_raw;
+    uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
+    const uint32_t b_term = (uint32_t)P.n_pad * kKC * 2;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t row = (int64_t)blockIdx.x * kRows + tid;
+    const bool valid = row < P.B;
+    const int n0 = blockIdx.y * 128;
+    const int n_valid = min(128, P.N - n0);
+    const int n_pad = min(P.n_pad, (n_valid + 15) & ~15);
+    const bool ln = P.gamma != nullptr;
+    const int K0 = P.a.k0 + P.a.k1;
+
+    if (ln)
+        for (int i = tid; i < K0; i += kThreads) { s_gamma[i] = P.gamma[i]; s_beta[i] = P.beta[i]; }
+    cta_setup(S, P.tmem_cols);
+    const uint32_t d_tmem = S.tmem_base;
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad);
+
+    // LayerNorm moments of this thread's row (shifted one-pass sums)
+    float mu = 0.f, rs = 0.f;
+    if (ln && valid) {
+        const float x0 = load1(P.a, row, 0);
+        float s = 0.f, q = 0.f;
+        for (int c = 0; c < K0; c += 8) {
+            float v[8];
+            load8(P.a, row, c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = (c + j < K0) ? v[j] - x0 : 0.f;
+                s += d;
+                q = fmaf(d, d, q);
+            }
+        }
+        const float md = s / (float)K0;
+        mu = x0 + md;
+        rs = rsqrtf(fmaxf(q / (float)K0 - md * md, 0.f) + kLnEps);
+        if (blockIdx.y == 0) { P.mean[row] = mu; P.rstd[row] = rs; }
+    }
+
+    uint32_t phase = 0;
+    bool first = true;
+    const int nseg = P.a2.p0 ? 2 : 1;
+    for (int seg = 0; seg < nseg; ++seg) {
+        const Mat& A = seg ? P.a2 : P.a;
+        const float* W = seg ? P.w2 : P.w;
+        const bool wvec = seg ? P.wvec2 : P.wvec;
+        const bool act = ln && seg == 0;
+        const int K = A.k0 + A.k1;
+        for (int k0 = 0; k0 < K; k0 += kKC) {
+            const int kw = min(kKC, (K - k0 + 15) & ~15);
+            // A chunk: thread == row
+            for (int j = 0; j < (kw >> 3); ++j) {
+                const int c = k0 + j * 8;
+                float v[8];
+                if (valid) {
+                    load8(A, row, c, v);
+                    if (act) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (c + q < K) {
+                                const float n = fmaf((v[q] - mu) * rs, s_gamma[c + q], s_beta[c + q]);
+                                v[q] = n * sigmoidf_(n);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                }
+                store_split(a_hi, a_term_bytes(), op_off(tid, j * 8), v);
+            }
+            stage_rowmajor_w(b_hi, b_term, W, K, n0, n_valid, n_pad, k0, K, kw, wvec);
+            mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
+            first = false;
+        }
+    }
+
+    // epilogue: accumulator row -> + bias (+ add, + gathered add) -> y
+    const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+    const int64_t grow = (valid && P.gidx) ? P.gidx[row] : 0;
+    for (int g = 0; g < n_pad / 16; ++g) {
+        float v[16];
+        tmem_ld16(t_row + g * 16, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int c0 = n0 + g * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = c0 + j;
+            if (c < P.N) {
+                float t = v[j];
+                if (P.bias) t += __ldg(P.bias + c);
+                if (P.bias2) t += __ldg(P.bias2 + c);
+                if (P.add) t += __ldg(P.add + row * P.N + c);
+                if (P.gadd) t += __ldg(P.gadd + grow * P.N + c);
+                v[j] = t;
+            }
+        }
+        float* yp = P.y + row * P.N + c0;
+        if (P.yvec && c0 + 16 <= P.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(yp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < P.N) yp[j] = v[j];
+        }
+    }
+    cta_teardown(S, P.tmem_cols);
+}
+
+// ================================================================================================ dgrad
+struct DgradArgs {
+    const float* dy;       // [B, N]
+    const float* w;        // [N, K]
+    Mat x;                 // LN mode: the forward input
+    const float* gamma;
+    const float* beta;
+    const float* mean;
+    const float* rstd;
+    Mat dres;              // optional addend (p0 == nullptr: none)
+    MatOut dx;
+    float* dgamma;
+    float* dbeta;
+    int64_t B;
+    int N, K, kt, kt_pad, tmem_cols, dyvec;
+};
+
+__global__ void __launch_bounds__(kThreads) tlin_dgrad_kernel(const DgradArgs P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Smem S;
+    __shared__ float s_gamma[256], s_beta[256], s_dg[256], s_db[256];
+    uint8_t* a_hi = smem_raw;
+    uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
+    const uint32_t b_term = (uint32_t)P.kt_pad * kKC * 2;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row = (int64_t)blockIdx.x * kRows + tid;
+    const bool valid = row < P.B;
+    const int kb = blockIdx.y * P.kt;                       // first output column of this CTA
+    const int k_valid = min(P.kt, P.K - kb);
+    const int k_pad = (k_valid + 15) & ~15;
+    const bool ln = P.gamma != nullptr;
+
+    if (ln)
+        for (int i = tid; i < 256; i += kThreads) {
+            s_gamma[i] = i < P.K ? P.gamma[i] : 0.f;
+            s_beta[i] = i < P.K ? P.beta[i] : 0.f;
+            s_dg[i] = 0.f;
+            s_db[i] = 0.f;
+        }
+    cta_setup(S, P.tmem_cols);
+    const uint32_t d_tmem = S.tmem_base;
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)k_pad);
+    const Mat DY{P.dy, nullptr, P.N, 0, P.dyvec};
+
+    uint32_t phase = 0;
+    bool first = true;
+    for (int n0 = 0; n0 < P.N; n0 += kKC) {
+        const int kw = min(kKC, (P.N - n0 + 15) & ~15);
+        // A chunk = dy rows (thread == row)
+        for (int j = 0; j < (kw >> 3); ++j) {
+            float v[8];
+            if (valid) load8(DY, row, n0 + j * 8, v);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            }
+            store_split(a_hi, a_term_bytes(), op_off(tid, j * 8), v);
+        }
+        // B chunk = W^T: (mn = k, kk = n); memory is contiguous along k -> lanes along k, 8 n values per item
+        for (int it = tid; it < k_pad * (kw >> 3); it += kThreads) {
+            const int k = it % k_pad, n8 = it / k_pad;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = n0 + n8 * 8 + q;
+                v[q] = (k < k_valid && n < P.N) ? __ldg(P.w + (size_t)n * P.K + kb + k) : 0.f;
+            }
+            store_split(b_hi, b_term, op_off(k, n8 * 8), v);
+        }
+        mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
+        first = false;
+    }
+
+    const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+    if (!ln) {
+        for (int g = 0; g < k_pad / 16; ++g) {
+            float v[16];
+            tmem_ld16(t_row + g * 16, v);
+            tmem_ld_wait();
+            if (!valid) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = kb + g * 16 + h * 8;
+                if (c >= P.K) continue;
+                float o[8];
+                if (P.dres.p0) {
+                    load8(P.dres, row, c, o);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] += v[h * 8 + q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = v[h * 8 + q];
+                }
+                store8(P.dx, row, c, o);
+            }
+        }
+    } else {
+        // LayerNorm -> Swish backward on the accumulator row g = d(swish(n)), n = gamma xh + beta, xh = (x - mu) rstd:
+        //   dn = g swish'(n);  dxh = dn gamma;  dx = rstd (dxh - mean(dxh) - xh mean(dxh xh));  dgamma += dn xh;  dbeta += dn
+        const float mu = valid ? P.mean[row] : 0.f, rs = valid ? P.rstd[row] : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+        for (int g = 0; g < k_pad / 16; ++g) {
+            float v[16], pg[16], pb[16];
+            tmem_ld16(t_row + g * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = g * 16 + h * 8;
+                float x[8];
+                if (valid) load8(P.x, row, c, x);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float gm = s_gamma[c + q];
+                    const float xh = (x[q] - mu) * rs;
+                    const float n = fmaf(xh, gm, s_beta[c + q]);
+                    const float sg = sigmoidf_(n);
+                    const float dn = (valid && c + q < P.K) ? v[h * 8 + q] * (sg * fmaf(n, 1.0f - sg, 1.0f)) : 0.f;
+                    const float dxh = dn * gm;
+                    s1 += dxh;
+                    s2 = fmaf(dxh, xh, s2);
+                    pg[h * 8 + q] = dn * xh;
+                    pb[h * 8 + q] = dn;
+                }
+            }
+            const float cg = colsum16(pg, lane), cb = colsum16(pb, lane);
+            if (!(lane & 1)) {
+                const int c = g * 16 + colsum16_col(lane);
+                atomicAdd(&s_dg[c], cg);
+                atomicAdd(&s_db[c], cb);
+            }
+        }
+        const float m1 = s1 / (float)P.K, m2 = s2 / (float)P.K;
+        for (int g = 0; g < k_pad / 16; ++g) {
+            float v[16];
+            tmem_ld16(t_row + g * 16, v);
+            tmem_ld_wait();
+            if (!valid) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = g * 16 + h * 8;
+                if (c >= P.K) continue;
+                float x[8], o[8];
+                load8(P.x, row, c, x);
+                if (P.dres.p0) load8(P.dres, row, c, o);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float gm = s_gamma[c + q];
+                    const float xh = (x[q] - mu) * rs;
+                    const float n = fmaf(xh, gm, s_beta[c + q]);
+                    const float sg = sigmoidf_(n);
+                    const float dxh = v[h * 8 + q] * (sg * fmaf(n, 1.0f - sg, 1.0f)) * gm;
+                    o[q] += rs * (dxh - m1 - xh * m2);
+                }
+                store8(P.dx, row, c, o);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < P.K; i += kThreads) {
+            red_add(P.dgamma + i, s_dg[i]);
+            red_add(P.dbeta + i, s_db[i]);
+        }
+    }
+    cta_teardown(S, P.tmem_cols);
+}
+
+// ================================================================================================ wgrad
+struct WgradArgs {
+    const float* dy;       // [B, N]
+    Mat a;                 // [B, K]: the forward A operand (before LayerNorm -> Swish when gamma != nullptr)
+    const float* gamma;
+    const float* beta;
+    const float* mean;
+    const float* rstd;
+    const int64_t* gidx;   // [B] row -> gathered-add row (with dgadd)
+    float* dw;             // [N, K]  +=
+    float* dbias;          // [N]     +=   (nullable)
+    float* dgadd;          // [T, N]  +=   (nullable)
+    int64_t B;
+    int N, K, T, n_chunks, tmem_cols, bcols_pad, dwvec;
+};
+
+__global__ void __launch_bounds__(kThreads) tlin_wgrad_kernel(const WgradArgs P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Smem S;
+    uint8_t* a_hi = smem_raw;
+    uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
+    const uint32_t b_term = (uint32_t)P.bcols_pad * kKC * 2;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n0 = blockIdx.y * 128;
+    const int n_valid = min(128, P.N - n0);
+    const int kb = blockIdx.z * kWgradKT;
+    const int kcols = min(kWgradKT, P.K - kb);
+    const bool last_z = blockIdx.z == gridDim.z - 1;
+    const int n_extra = last_z ? ((P.dbias ? 1 : 0) + (P.dgadd ? P.T : 0)) : 0;
+    const int one_col = (last_z && P.dbias) ? kcols : -1;
+    const int hot0 = (last_z && P.dgadd) ? kcols + (P.dbias ? 1 : 0) : -1;
+    const int bcols = kcols + n_extra;
+    const int bcols_pad = (bcols + 15) & ~15;
+    const bool ln = P.gamma != nullptr;
+
+    cta_setup(S, P.tmem_cols);
+    const uint32_t d_tmem = S.tmem_base;
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)bcols_pad);
+
+    uint32_t phase = 0;
+    bool first = true;
+    for (int ch = blockIdx.x; ch < P.n_chunks; ch += gridDim.x) {
+        const int64_t r0 = (int64_t)ch * kKC;
+        const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
+        // A operand = dy^T: (mn = n, kk = row); lanes along n (contiguous in memory), 8 rows per item
+        for (int it = tid; it < n_valid * (kw >> 3); it += kThreads) {
+            const int n = it % n_valid, r8 = it / n_valid;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t r = r0 + r8 * 8 + q;
+                v[q] = r < P.B ? __ldg(P.dy + r * P.N + n0 + n) : 0.f;
+            }
+            store_split(a_hi, a_term_bytes(), op_off(n, r8 * 8), v);
+        }
+        // B operand = [act(a) | 1 | onehot(gidx)]^T: (mn = column, kk = row)
+        for (int it = tid; it < bcols_pad * (kw >> 3); it += kThreads) {
+            const int c = it % bcols_pad, r8 = it / bcols_pad;
+            float v[8];
+            if (c < kcols) {
+                const int k = kb + c;
+                const float gm = ln ? __ldg(P.gamma + k) : 0.f, bt = ln ? __ldg(P.beta + k) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int64_t r = r0 + r8 * 8 + q;
+                    float t = 0.f;
+                    if (r < P.B) {
+                        t = load1(P.a, r, k);
+                        if (ln) {
+                            const float n = fmaf((t - __ldg(P.mean + r)) * __ldg(P.rstd + r), gm, bt);
+                            t = n * sigmoidf_(n);
+                        }
+                    }
+                    v[q] = t;
+                }
+            } else if (c == one_col) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (r0 + r8 * 8 + q < P.B) ? 1.f : 0.f;
+            } else if (hot0 >= 0 && c >= hot0 && c < hot0 + P.T) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int64_t r = r0 + r8 * 8 + q;
+                    v[q] = (r < P.B && P.gidx[r] == (int64_t)(c - hot0)) ? 1.f : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            }
+            store_split(b_hi, b_term, op_off(c, r8 * 8), v);
+        }
+        mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
+        first = false;
+    }
+
+    // epilogue: TMEM lane n = output feature n0 + n; columns = [dW row | db | d(gadd) column]
+    const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+    const bool has_n = tid < n_valid && !first;
+    const int n = n0 + tid;
+    const bool v4 = P.dwvec != 0;
+    for (int g = 0; g < bcols_pad / 16; ++g) {
+        float v[16];
+        tmem_ld16(t_row + g * 16, v);
+        tmem_ld_wait();
+        if (!has_n) continue;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int c = g * 16 + q4 * 4;
+            if (v4 && c + 4 <= kcols) {
+                red_add4(P.dw + (size_t)n * P.K + kb + c, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = c + q;
+                    if (cc < kcols) red_add(P.dw + (size_t)n * P.K + kb + cc, v[q4 * 4 + q]);
+                    else if (cc == one_col) red_add(P.dbias + n, v[q4 * 4 + q]);
+                    else if (hot0 >= 0 && cc >= hot0 && cc < hot0 + P.T) red_add(P.dgadd + (size_t)(cc - hot0) * P.N + n, v[q4 * 4 + q]);
+                }
+            }
+        }
+    }
+    cta_teardown(S, P.tmem_cols);
+}
+
+static inline uint32_t pow2_cols(int n) {
+    uint32_t c = 32;
+    while ((int)c < n) c <<= 1;
+    return c;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline Mat to_mat(const diffsg_mat& m) {
+    Mat r;
+    r.p0 = m.p0;
+    r.p1 = m.k1 > 0 ? m.p1 : nullptr;
+    r.k0 = m.k0;
+    r.k1 = m.k1 > 0 ? m.k1 : 0;
+    r.vec = (r.k0 % 8 == 0) && (r.k1 % 8 == 0) && aligned16(r.p0) && (!r.p1 || aligned16(r.p1));
+    return r;
+}
+static inline bool mat_ok(const diffsg_mat& m) { return m.p0 && m.k0 > 0 && m.k1 >= 0 && (m.k1 == 0 || m.p1); }
+
+}  // namespace ttc
+}  // namespace diffsg
+
+using namespace diffsg;
+using namespace diffsg::ttc;
+
+// opt-in dynamic shared memory, once per (kernel, device)
+static int set_smem(const void* fn, size_t bytes, int which) {
+    static bool done[3][64] = {};
+    int dev = 0;
+    DIFFSG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[which][dev]) return DIFFSG_OK;
+    DIFFSG_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev >= 0 && dev < 64) done[which][dev] = true;
+    return DIFFSG_OK;
+}
+
+extern "C" {
+
+int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
+    if (a && a->B == 0) return DIFFSG_OK;
+    if (!a || !mat_ok(a->a) || !a->w || !a->y || a->B < 0 || a->N <= 0) { set_error("tlin_forward: bad argument"); return DIFFSG_E_INVALID; }
+    const bool ln = a->gamma != nullptr;
+    if (ln && (!a->beta || !a->mean || !a->rstd)) { set_error("tlin_forward: LayerNorm mode needs beta, mean, rstd"); return DIFFSG_E_INVALID; }
+    if (ln && a->a.k0 + a->a.k1 > 256) { set_error("tlin_forward: LayerNorm width %d > 256", a->a.k0 + a->a.k1); return DIFFSG_E_UNSUPPORTED; }
+    if ((a->gadd != nullptr) != (a->gidx != nullptr)) { set_error("tlin_forward: gadd and gidx go together"); return DIFFSG_E_INVALID; }
+    const bool seg2 = a->a2.p0 != nullptr;
+    if (seg2 && (!mat_ok(a->a2) || !a->w2)) { set_error("tlin_forward: bad second segment"); return DIFFSG_E_INVALID; }
+    FwdArgs P{};
+    P.a = to_mat(a->a);
+    P.w = a->w; P.bias = a->bias; P.gamma = a->gamma; P.beta = a->beta; P.mean = a->mean; P.rstd = a->rstd;
+    if (seg2) P.a2 = to_mat(a->a2); else P.a2 = Mat{nullptr, nullptr, 0, 0, 0};
+    P.w2 = a->w2; P.bias2 = seg2 ? a->bias2 : nullptr;
+    P.add = a->add; P.gadd = a->gadd; P.gidx = a->gidx; P.y = a->y; P.B = a->B; P.N = a->N;
+    P.n_pad = a->N >= 128 ? 128 : ((a->N + 15) & ~15);
+    P.tmem_cols = (int)pow2_cols(P.n_pad);
+    const int K = P.a.k0 + P.a.k1;
+    P.wvec = (K % 8 == 0) && aligned16(a->w);
+    P.wvec2 = seg2 && ((P.a2.k0 + P.a2.k1) % 8 == 0) && aligned16(a->w2);
+    P.yvec = (a->N % 4 == 0) && aligned16(a->y);
+    const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.n_pad * kKC * 2;
+    if (int rc = set_smem((const void*)tlin_fwd_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)128 * kKC * 2, 0)) return rc;
+    const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->N + 127) / 128));
+    tlin_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* a, void* stream) {
+    if (a && a->B == 0) return DIFFSG_OK;
+    if (!a || !a->dy || !a->w || a->N <= 0 || a->K <= 0 || a->B < 0 || !a->dx.p0) { set_error("tlin_dgrad: bad argument"); return DIFFSG_E_INVALID; }
+    if (a->dx.k0 + (a->dx.k1 > 0 ? a->dx.k1 : 0) != a->K) { set_error("tlin_dgrad: dx split does not add up to K"); return DIFFSG_E_INVALID; }
+    const bool ln = a->gamma != nullptr;
+    if (ln && (!a->beta || !a->mean || !a->rstd || !a->dgamma || !a->dbeta || !mat_ok(a->x) || a->x.k0 + (a->x.k1 > 0 ? a->x.k1 : 0) != a->K)) {
+        set_error("tlin_dgrad: LayerNorm mode needs x[B, K], beta, mean, rstd, dgamma, dbeta");
+        return DIFFSG_E_INVALID;
+    }
+    if (ln && a->K > 256) { set_error("tlin_dgrad: LayerNorm width %d > 256", a->K); return DIFFSG_E_UNSUPPORTED; }
+    if (a->dres.p0 && a->dres.k0 + (a->dres.k1 > 0 ? a->dres.k1 : 0) != a->K) { set_error("tlin_dgrad: dres split does not add up to K"); return DIFFSG_E_INVALID; }
+    DgradArgs P{};
+    P.dy = a->dy; P.w = a->w; P.gamma = a->gamma; P.beta = a->beta; P.mean = a->mean; P.rstd = a->rstd;
+    if (ln) P.x = to_mat(a->x);
+    if (a->dres.p0) P.dres = to_mat(a->dres); else P.dres = Mat{nullptr, nullptr, 0, 0, 0};
+    diffsg_mat dxm{a->dx.p0, a->dx.p1, a->dx.k0, a->dx.k1};
+    const Mat t = to_mat(dxm);
+    P.dx = MatOut{a->dx.p0, a->dx.k1 > 0 ? a->dx.p1 : nullptr, t.k0, t.k1, t.vec};
+    P.dgamma = a->dgamma; P.dbeta = a->dbeta; P.B = a->B; P.N = a->N; P.K = a->K;
+    P.kt = ln ? 256 : 128;
+    const int kmax = a->K < P.kt ? a->K : P.kt;
+    P.kt_pad = (kmax + 15) & ~15;
+    P.tmem_cols = (int)pow2_cols(P.kt_pad);
+    P.dyvec = (a->N % 8 == 0) && aligned16(a->dy);
+    const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.kt_pad * kKC * 2;
+    if (int rc = set_smem((const void*)tlin_dgrad_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 1)) return rc;
+    const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->K + P.kt - 1) / P.kt));
+    tlin_dgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* a, void* stream) {
+    if (a && a->B == 0) return DIFFSG_OK;
+    if (!a || !a->dy || !mat_ok(a->a) || !a->dw || a->N <= 0 || a->B < 0) { set_error("tlin_wgrad: bad argument"); return DIFFSG_E_INVALID; }
+    const bool ln = a->gamma != nullptr;
+    if (ln && (!a->beta || !a->mean || !a->rstd)) { set_error("tlin_wgrad: LayerNorm mode needs beta, mean, rstd"); return DIFFSG_E_INVALID; }
+    if (a->dgadd && (!a->gidx || a->gadd_rows <= 0)) { set_error("tlin_wgrad: dgadd needs gidx and gadd_rows"); return DIFFSG_E_INVALID; }
+    const int n_extra = (a->dbias ? 1 : 0) + (a->dgadd ? a->gadd_rows : 0);
+    if (n_extra > kMaxExtra) { set_error("tlin_wgrad: %d gathered rows > %d", a->gadd_rows, kMaxExtra - 1); return DIFFSG_E_UNSUPPORTED; }
+    WgradArgs P{};
+    P.dy = a->dy; P.a = to_mat(a->a); P.gamma = a->gamma; P.beta = a->beta; P.mean = a->mean; P.rstd = a->rstd;
+    P.gidx = a->gidx; P.dw = a->dw; P.dbias = a->dbias; P.dgadd = a->dgadd; P.B = a->B; P.N = a->N;
+    P.K = P.a.k0 + P.a.k1; P.T = a->dgadd ? a->gadd_rows : 0;
+    P.n_chunks = (int)((a->B + kKC - 1) / kKC);
+    const int nz = (P.K + kWgradKT - 1) / kWgradKT, ny = (a->N + 127) / 128;
+    const int k_first = P.K < kWgradKT ? P.K : kWgradKT;
+    const int k_last = P.K - (nz - 1) * kWgradKT;
+    int widest = nz > 1 ? kWgradKT : k_first;
+    if (k_last + n_extra > widest) widest = k_last + n_extra;
+    P.bcols_pad = (widest + 15) & ~15;
+    P.dwvec = (P.K % 4 == 0) && aligned16(a->dw);
+    P.tmem_cols = (int)pow2_cols(P.bcols_pad);
+    int gx = 296 / (ny * nz);
+    if (gx < 1) gx = 1;
+    if (gx > P.n_chunks) gx = P.n_chunks;
+    const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.bcols_pad * kKC * 2;
+    if (int rc = set_smem((const void*)tlin_wgrad_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 2)) return rc;
+    const dim3 grid((unsigned)gx, (unsigned)ny, (unsigned)nz);
+    tlin_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+    count_launch();
+    DIFFSG_CUDA_OK(cudaGetLastError());
+    return DIFFSG_OK;
+}
+
+}  // extern "C"

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DIFFSG_ABI_VERSION 2
+#define DIFFSG_ABI_VERSION 3
 
 enum {
     DIFFSG_OK = 0,
@@ -294,6 +294,88 @@ int diffsg_lnsw_backward(const float* x_dev, const float* gamma_dev, const float
                          const float* mean_dev, const float* rstd_dev, const float* dy_dev, float* dx_dev,
                          float* dgamma_dev, float* dbeta_dev, float* workspace_dev,
                          int64_t workspace_floats, int64_t B, int32_t D, void* stream);
+
+/* ---- training GEMMs on the tensor cores (tcgen05, bf16 hi+lo operands, fp32 accumulate) -------------------
+ * The Linear layers of the eps-MSE training step, with the LayerNorm -> Swish in front of them fused in.  Replaces
+ * nn.Linear forward / autograd dgrad / wgrad of ddpm_opt/UNetCF.py:83-95 (ResidualBlock), :123-157 (attention at
+ * sequence length 1), :318-356 (UNet1D.forward) under the loss of classifier_free_MSR.py:100-112.  All pointers are
+ * device pointers to dense row-major fp32 (gidx: int64). */
+typedef struct diffsg_mat {       /* logical [rows, k0 + k1] = cat(p0[rows, k0], p1[rows, k1]) along columns; k1 = 0: p0 only */
+    const float* p0;
+    const float* p1;
+    int32_t k0;
+    int32_t k1;
+} diffsg_mat;
+typedef struct diffsg_mat_out {
+    float* p0;
+    float* p1;
+    int32_t k0;
+    int32_t k1;
+} diffsg_mat_out;
+
+/* y[B, N] = act(a) . w^T + bias (+ a2 . w2^T + bias2) (+ add) (+ gadd[gidx[row]]);
+ * act = swish(LayerNorm(.; gamma, beta, eps 1e-5)) over the K = a.k0 + a.k1 columns when gamma != NULL (K <= 256;
+ * per-row mean / rstd are written for the backward), identity otherwise. */
+typedef struct diffsg_tlin_fwd_args {
+    diffsg_mat a;
+    const float* w;               /* [N, K] */
+    const float* bias;            /* [N] or NULL */
+    const float* gamma;           /* [K] or NULL */
+    const float* beta;
+    float* mean;                  /* [B] out (LayerNorm mode) */
+    float* rstd;
+    diffsg_mat a2;                /* optional second (identity) segment accumulated into the same tile; a2.p0 = NULL: none */
+    const float* w2;              /* [N, a2.k0 + a2.k1] */
+    const float* bias2;
+    const float* add;             /* [B, N] or NULL */
+    const float* gadd;            /* [T, N] or NULL: row gidx[row] is added to output row `row` */
+    const int64_t* gidx;          /* [B] */
+    float* y;                     /* [B, N] */
+    int64_t B;
+    int32_t N;
+    int32_t reserved;
+} diffsg_tlin_fwd_args;
+int diffsg_tlin_forward(const diffsg_tlin_fwd_args* args, void* stream);
+
+/* dx[B, K] = (dy[B, N] . w[N, K]) (+ dres).  With gamma != NULL the product is the gradient w.r.t. swish(LayerNorm(x))
+ * and is pushed through the LayerNorm -> Swish backward in the epilogue (K <= 256): dx is then the gradient w.r.t. x and
+ * dgamma[K] / dbeta[K] are ACCUMULATED (+=). */
+typedef struct diffsg_tlin_dgrad_args {
+    const float* dy;
+    const float* w;
+    diffsg_mat x;                 /* LayerNorm mode: the forward input */
+    const float* gamma;
+    const float* beta;
+    const float* mean;
+    const float* rstd;
+    diffsg_mat dres;              /* optional addend with K columns; dres.p0 = NULL: none */
+    diffsg_mat_out dx;            /* K = dx.k0 + dx.k1 columns */
+    float* dgamma;
+    float* dbeta;
+    int64_t B;
+    int32_t N;
+    int32_t K;
+} diffsg_tlin_dgrad_args;
+int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* args, void* stream);
+
+/* dw[N, K] += dy^T . act(a);  dbias[N] += column sums of dy;  dgadd[T, N] += rows of dy scattered by gidx
+ * (all three from one pass over the rows; dbias / dgadd optional, gadd_rows <= 31). */
+typedef struct diffsg_tlin_wgrad_args {
+    const float* dy;
+    diffsg_mat a;
+    const float* gamma;
+    const float* beta;
+    const float* mean;
+    const float* rstd;
+    const int64_t* gidx;
+    float* dw;
+    float* dbias;
+    float* dgadd;
+    int64_t B;
+    int32_t N;
+    int32_t gadd_rows;
+} diffsg_tlin_wgrad_args;
+int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* args, void* stream);
 
 /* ---- test hooks (not part of the product surface) ------------------------------------
  * One 128-row tcgen05 GEMM tile: C[128,N] = A[128,K] . W[N,K]^T with A split into fp16
