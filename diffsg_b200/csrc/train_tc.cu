@@ -109,7 +109,9 @@ __device__ __forceinline__ void store8(const MatOut& m, int64_t row, int c, cons
         }
     }
 }
-__device__ __forceinline__ float sigmoidf_(float n) { return 1.0f / (1.0f + __expf(-n)); }
+// branch-free (MUFU.EX2 + MUFU.RCP, ~2 ulp): an IEEE division here puts a slow-path branch between the elements of a
+// row and serialises their dependent chains
+__device__ __forceinline__ float sigmoidf_(float n) { return __fdividef(1.0f, 1.0f + __expf(-n)); }
 
 __device__ __forceinline__ void red_add(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
@@ -180,7 +182,10 @@ __device__ __forceinline__ void mma_chunk(Smem& S, uint8_t* a_hi, uint8_t* b_hi,
                                           uint32_t d_tmem, bool first, uint32_t& phase) {
     fence_proxy_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp 0 issues; its other lanes park at the __syncwarp (a lane spinning on the mbarrier next to the issuing lane
+        // would starve it: try_wait suspends the whole warp)
+        if (threadIdx.x == 0) {
         tcgen05_fence_after();
         const uint64_t da_hi = make_smem_desc(smem_u32(a_hi), kLBO, kSBO, 0);
         const uint64_t da_lo = make_smem_desc(smem_u32(a_hi + a_term_bytes()), kLBO, kSBO, 0);
@@ -195,6 +200,8 @@ __device__ __forceinline__ void mma_chunk(Smem& S, uint8_t* a_hi, uint8_t* b_hi,
             acc = 1;
         }
         umma_commit(&S.bar);
+        }
+        __syncwarp();
     }
     mbar_wait(&S.bar, phase);
     phase ^= 1;
@@ -202,28 +209,87 @@ __device__ __forceinline__ void mma_chunk(Smem& S, uint8_t* a_hi, uint8_t* b_hi,
 }
 
 // operand whose contraction dimension is contiguous in memory: src[mn][k] with row stride ld (weights [N, K] in the
-// forward).  Items (mn, 8-column piece), mn fastest across lanes: 16-byte conflict-free shared stores.
+// forward).  Items (mn, 8-column piece), mn fastest across lanes: 16-byte conflict-free shared stores.  Four items per
+// thread are loaded before the first one is converted (memory-level parallelism: the loop is latency-bound otherwise).
 __device__ __forceinline__ void stage_rowmajor_w(uint8_t* hi_base, uint32_t lo_delta, const float* __restrict__ w, int ld,
                                                  int n0, int n_valid, int n_pad, int k0, int K, int kw, bool vec) {
-    const int pieces = kw >> 3;
-    for (int it = threadIdx.x; it < n_pad * pieces; it += kThreads) {
+    const int pieces = kw >> 3, total = n_pad * pieces;
+    if (vec) {
+        for (int it0 = threadIdx.x; it0 < total; it0 += 4 * kThreads) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * kThreads;
+                const int n = it % n_pad, c = k0 + (it / n_pad) * 8;
+                a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it < total && n < n_valid && c < K) {
+                    const float4* p = reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * ld + c);
+                    a[u] = __ldg(p);
+                    b[u] = __ldg(p + 1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * kThreads;
+                if (it < total) {
+                    const float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+                    store_split(hi_base, lo_delta, op_off(it % n_pad, (it / n_pad) * 8), v);
+                }
+            }
+        }
+        return;
+    }
+    for (int it = threadIdx.x; it < total; it += kThreads) {
         const int n = it % n_pad, j = it / n_pad;
         const int c = k0 + j * 8;
         float v[8];
-        if (n < n_valid && c < K) {
-            const float* p = w + (size_t)(n0 + n) * ld + c;
-            if (vec) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            } else {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (c + q < K) ? __ldg(p + q) : 0.f;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = 0.f;
-        }
+        for (int q = 0; q < 8; ++q) v[q] = (n < n_valid && c + q < K) ? __ldg(w + (size_t)(n0 + n) * ld + c + q) : 0.f;
         store_split(hi_base, lo_delta, op_off(n, j * 8), v);
+    }
+}
+
+// one 64-column chunk of this thread's row (thread == row) of a row-major matrix: all loads first, then the optional
+// LayerNorm -> Swish, the bf16 split and the stores
+template <bool kAct>
+__device__ __forceinline__ void stage_row_chunk(uint8_t* a_hi, const Mat& A, int64_t row, bool valid, int k0, int kw, int K,
+                                                float mu, float rs, const float* s_gamma, const float* s_beta) {
+    const int pieces = kw >> 3;
+    float v[8][8];
+    if (A.vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = k0 + j * 8;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (j < pieces && valid && c < K) {
+                const float4* p = reinterpret_cast<const float4*>(c < A.k0 ? A.p0 + row * A.k0 + c : A.p1 + row * A.k1 + (c - A.k0));
+                a = __ldg(p);
+                b = __ldg(p + 1);
+            }
+            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[j][q] = 0.f;
+            if (j < pieces && valid) load8(A, row, k0 + j * 8, v[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < pieces) {
+            if (kAct && valid) {
+                const int c = k0 + j * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    // columns >= K: x = gamma = beta = 0 (zero-padded tables) -> n = 0 -> swish = 0, no per-element branch
+                    const float n = fmaf((v[j][q] - mu) * rs, s_gamma[c + q], s_beta[c + q]);
+                    v[j][q] = n * sigmoidf_(n);
+                }
+            }
+            store_split(a_hi, a_term_bytes(), op_off(threadIdx.x, j * 8), v[j]);
+        }
     }
 }
 
@@ -265,7 +331,7 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
     const int K0 = P.a.k0 + P.a.k1;
 
     if (ln)
-        for (int i = tid; i < K0; i += kThreads) { s_gamma[i] = P.gamma[i]; s_beta[i] = P.beta[i]; }
+        for (int i = tid; i < 256; i += kThreads) { s_gamma[i] = i < K0 ? P.gamma[i] : 0.f; s_beta[i] = i < K0 ? P.beta[i] : 0.f; }
     cta_setup(S, P.tmem_cols);
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad);
@@ -275,15 +341,18 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
     if (ln && valid) {
         const float x0 = load1(P.a, row, 0);
         float s = 0.f, q = 0.f;
-        for (int c = 0; c < K0; c += 8) {
-            float v[8];
-            load8(P.a, row, c, v);
+        for (int c = 0; c < K0; c += 32) {
+            float v[4][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = (c + j < K0) ? v[j] - x0 : 0.f;
-                s += d;
-                q = fmaf(d, d, q);
-            }
+            for (int u = 0; u < 4; ++u) load8(P.a, row, c + u * 8, v[u]);          // columns >= K read as 0
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = (c + u * 8 + j < K0) ? v[u][j] - x0 : 0.f;
+                    s += d;
+                    q = fmaf(d, d, q);
+                }
         }
         const float md = s / (float)K0;
         mu = x0 + md;
@@ -303,61 +372,83 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
         for (int k0 = 0; k0 < K; k0 += kKC) {
             const int kw = min(kKC, (K - k0 + 15) & ~15);
             // A chunk: thread == row
-            for (int j = 0; j < (kw >> 3); ++j) {
-                const int c = k0 + j * 8;
-                float v[8];
-                if (valid) {
-                    load8(A, row, c, v);
-                    if (act) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (c + q < K) {
-                                const float n = fmaf((v[q] - mu) * rs, s_gamma[c + q], s_beta[c + q]);
-                                v[q] = n * sigmoidf_(n);
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = 0.f;
-                }
-                store_split(a_hi, a_term_bytes(), op_off(tid, j * 8), v);
-            }
+            if (act) stage_row_chunk<true>(a_hi, A, row, valid, k0, kw, K, mu, rs, s_gamma, s_beta);
+            else stage_row_chunk<false>(a_hi, A, row, valid, k0, kw, K, 0.f, 0.f, nullptr, nullptr);
             stage_rowmajor_w(b_hi, b_term, W, K, n0, n_valid, n_pad, k0, K, kw, wvec);
             mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
             first = false;
         }
     }
 
-    // epilogue: accumulator row -> + bias (+ add, + gathered add) -> y
+    // epilogue: accumulator row -> + bias (+ add, + gathered add) -> y; 32 columns per round, addend loads first
     const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
     const int64_t grow = (valid && P.gidx) ? P.gidx[row] : 0;
-    for (int g = 0; g < n_pad / 16; ++g) {
-        float v[16];
-        tmem_ld16(t_row + g * 16, v);
-        tmem_ld_wait();
-        if (!valid) continue;
-        const int c0 = n0 + g * 16;
+    const int ngroups = n_pad / 16;
+    for (int g = 0; g < ngroups; g += 2) {
+        const bool two = g + 1 < ngroups;
+        float ex[2][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c < P.N) {
-                float t = v[j];
-                if (P.bias) t += __ldg(P.bias + c);
-                if (P.bias2) t += __ldg(P.bias2 + c);
-                if (P.add) t += __ldg(P.add + row * P.N + c);
-                if (P.gadd) t += __ldg(P.gadd + grow * P.N + c);
-                v[j] = t;
+        for (int u = 0; u < 2; ++u) {
+            const int c0 = n0 + (g + u) * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ex[u][j] = 0.f;
+            if (!valid || (u == 1 && !two)) continue;
+            if (P.yvec && c0 + 16 <= P.N) {
+                if (P.add) {
+                    const float4* ap = reinterpret_cast<const float4*>(P.add + row * P.N + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t = __ldg(ap + j);
+                        ex[u][4 * j] += t.x; ex[u][4 * j + 1] += t.y; ex[u][4 * j + 2] += t.z; ex[u][4 * j + 3] += t.w;
+                    }
+                }
+                if (P.gadd) {
+                    const float4* gp = reinterpret_cast<const float4*>(P.gadd + grow * P.N + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t = __ldg(gp + j);
+                        ex[u][4 * j] += t.x; ex[u][4 * j + 1] += t.y; ex[u][4 * j + 2] += t.z; ex[u][4 * j + 3] += t.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + j;
+                    if (c < P.N) {
+                        if (P.add) ex[u][j] += __ldg(P.add + row * P.N + c);
+                        if (P.gadd) ex[u][j] += __ldg(P.gadd + grow * P.N + c);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = c0 + j;
+                if (c < P.N) {
+                    if (P.bias) ex[u][j] += __ldg(P.bias + c);
+                    if (P.bias2) ex[u][j] += __ldg(P.bias2 + c);
+                }
             }
         }
-        float* yp = P.y + row * P.N + c0;
-        if (P.yvec && c0 + 16 <= P.N) {
+        float v[2][16];
+        tmem_ld16(t_row + g * 16, v[0]);
+        if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
+        tmem_ld_wait();
+        if (!valid) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(yp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) continue;
+            const int c0 = n0 + (g + u) * 16;
+            float* yp = P.y + row * P.N + c0;
+            if (P.yvec && c0 + 16 <= P.N) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (c0 + j < P.N) yp[j] = v[j];
+                for (int j = 0; j < 4; ++j)
+                    reinterpret_cast<float4*>(yp)[j] = make_float4(v[u][4 * j] + ex[u][4 * j], v[u][4 * j + 1] + ex[u][4 * j + 1],
+                                                                   v[u][4 * j + 2] + ex[u][4 * j + 2], v[u][4 * j + 3] + ex[u][4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < P.N) yp[j] = v[u][j] + ex[u][j];
+            }
         }
     }
     cta_teardown(S, P.tmem_cols);
@@ -413,119 +504,134 @@ __global__ void __launch_bounds__(kThreads) tlin_dgrad_kernel(const DgradArgs P)
     for (int n0 = 0; n0 < P.N; n0 += kKC) {
         const int kw = min(kKC, (P.N - n0 + 15) & ~15);
         // A chunk = dy rows (thread == row)
-        for (int j = 0; j < (kw >> 3); ++j) {
-            float v[8];
-            if (valid) load8(DY, row, n0 + j * 8, v);
-            else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = 0.f;
-            }
-            store_split(a_hi, a_term_bytes(), op_off(tid, j * 8), v);
-        }
+        stage_row_chunk<false>(a_hi, DY, row, valid, n0, kw, P.N, 0.f, 0.f, nullptr, nullptr);
         // B chunk = W^T: (mn = k, kk = n); memory is contiguous along k -> lanes along k, 8 n values per item
-        for (int it = tid; it < k_pad * (kw >> 3); it += kThreads) {
-            const int k = it % k_pad, n8 = it / k_pad;
-            float v[8];
+        const int total = k_pad * (kw >> 3);
+        for (int it0 = tid; it0 < total; it0 += 2 * kThreads) {
+            float v[2][8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int n = n0 + n8 * 8 + q;
-                v[q] = (k < k_valid && n < P.N) ? __ldg(P.w + (size_t)n * P.K + kb + k) : 0.f;
+            for (int u = 0; u < 2; ++u) {
+                const int it = it0 + u * kThreads;
+                const int k = it % k_pad, n8 = it / k_pad;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = n0 + n8 * 8 + q;
+                    v[u][q] = (it < total && k < k_valid && n < P.N) ? __ldg(P.w + (size_t)n * P.K + kb + k) : 0.f;
+                }
             }
-            store_split(b_hi, b_term, op_off(k, n8 * 8), v);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int it = it0 + u * kThreads;
+                if (it < total) store_split(b_hi, b_term, op_off(it % k_pad, (it / k_pad) * 8), v[u]);
+            }
         }
         mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
         first = false;
     }
 
     const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+    const int ngroups = k_pad / 16;
     if (!ln) {
-        for (int g = 0; g < k_pad / 16; ++g) {
-            float v[16];
-            tmem_ld16(t_row + g * 16, v);
+        for (int g = 0; g < ngroups; g += 2) {
+            const bool two = g + 1 < ngroups;
+            float o[4][8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[h][q] = 0.f;
+                if (valid && P.dres.p0 && (h < 2 || two)) load8(P.dres, row, kb + g * 16 + h * 8, o[h]);
+            }
+            float v[2][16];
+            tmem_ld16(t_row + g * 16, v[0]);
+            if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
             tmem_ld_wait();
             if (!valid) continue;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 4; ++h) {
                 const int c = kb + g * 16 + h * 8;
-                if (c >= P.K) continue;
-                float o[8];
-                if (P.dres.p0) {
-                    load8(P.dres, row, c, o);
+                if ((h >= 2 && !two) || c >= P.K) continue;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] += v[h * 8 + q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] = v[h * 8 + q];
-                }
-                store8(P.dx, row, c, o);
+                for (int q = 0; q < 8; ++q) o[h][q] += v[h >> 1][(h & 1) * 8 + q];
+                store8(P.dx, row, c, o[h]);
             }
         }
     } else {
         // LayerNorm -> Swish backward on the accumulator row g = d(swish(n)), n = gamma xh + beta, xh = (x - mu) rstd:
         //   dn = g swish'(n);  dxh = dn gamma;  dx = rstd (dxh - mean(dxh) - xh mean(dxh xh));  dgamma += dn xh;  dbeta += dn
+        // Two passes over the accumulator (row sums first), 32 columns per round with the x loads issued first.
         const float mu = valid ? P.mean[row] : 0.f, rs = valid ? P.rstd[row] : 0.f;
         float s1 = 0.f, s2 = 0.f;
-        for (int g = 0; g < k_pad / 16; ++g) {
-            float v[16], pg[16], pb[16];
-            tmem_ld16(t_row + g * 16, v);
+        for (int g = 0; g < ngroups; g += 2) {
+            const bool two = g + 1 < ngroups;
+            float x[4][8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) x[h][q] = 0.f;
+                if (valid && (h < 2 || two)) load8(P.x, row, g * 16 + h * 8, x[h]);
+            }
+            float v[2][16];
+            tmem_ld16(t_row + g * 16, v[0]);
+            if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
             tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = g * 16 + h * 8;
-                float x[8];
-                if (valid) load8(P.x, row, c, x);
-                else {
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) continue;            // uniform
+                float pg[16], pb[16];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) x[q] = 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float gm = s_gamma[c + q];
-                    const float xh = (x[q] - mu) * rs;
-                    const float n = fmaf(xh, gm, s_beta[c + q]);
+                for (int j = 0; j < 16; ++j) {
+                    const int c = (g + u) * 16 + j;
+                    const float gm = s_gamma[c];
+                    const float xh = (x[2 * u + (j >> 3)][j & 7] - mu) * rs;
+                    const float n = fmaf(xh, gm, s_beta[c]);
                     const float sg = sigmoidf_(n);
-                    const float dn = (valid && c + q < P.K) ? v[h * 8 + q] * (sg * fmaf(n, 1.0f - sg, 1.0f)) : 0.f;
+                    const float dn = v[u][j] * (sg * fmaf(n, 1.0f - sg, 1.0f));    // invalid rows / columns >= K: accumulator is 0
                     const float dxh = dn * gm;
                     s1 += dxh;
                     s2 = fmaf(dxh, xh, s2);
-                    pg[h * 8 + q] = dn * xh;
-                    pb[h * 8 + q] = dn;
+                    pg[j] = dn * xh;
+                    pb[j] = dn;
                 }
-            }
-            const float cg = colsum16(pg, lane), cb = colsum16(pb, lane);
-            if (!(lane & 1)) {
-                const int c = g * 16 + colsum16_col(lane);
-                atomicAdd(&s_dg[c], cg);
-                atomicAdd(&s_db[c], cb);
+                const float cg = colsum16(pg, lane), cb = colsum16(pb, lane);
+                if (!(lane & 1)) {
+                    const int c = (g + u) * 16 + colsum16_col(lane);
+                    atomicAdd(&s_dg[c], cg);
+                    atomicAdd(&s_db[c], cb);
+                }
             }
         }
         const float m1 = s1 / (float)P.K, m2 = s2 / (float)P.K;
-        for (int g = 0; g < k_pad / 16; ++g) {
-            float v[16];
-            tmem_ld16(t_row + g * 16, v);
+        for (int g = 0; g < ngroups; g += 2) {
+            const bool two = g + 1 < ngroups;
+            float x[4][8], o[4][8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { x[h][q] = 0.f; o[h][q] = 0.f; }
+                if (valid && (h < 2 || two)) {
+                    load8(P.x, row, g * 16 + h * 8, x[h]);
+                    if (P.dres.p0) load8(P.dres, row, g * 16 + h * 8, o[h]);
+                }
+            }
+            float v[2][16];
+            tmem_ld16(t_row + g * 16, v[0]);
+            if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
             tmem_ld_wait();
             if (!valid) continue;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 4; ++h) {
                 const int c = g * 16 + h * 8;
-                if (c >= P.K) continue;
-                float x[8], o[8];
-                load8(P.x, row, c, x);
-                if (P.dres.p0) load8(P.dres, row, c, o);
-                else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] = 0.f;
-                }
+                if ((h >= 2 && !two) || c >= P.K) continue;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float gm = s_gamma[c + q];
-                    const float xh = (x[q] - mu) * rs;
+                    const float xh = (x[h][q] - mu) * rs;
                     const float n = fmaf(xh, gm, s_beta[c + q]);
                     const float sg = sigmoidf_(n);
-                    const float dxh = v[h * 8 + q] * (sg * fmaf(n, 1.0f - sg, 1.0f)) * gm;
-                    o[q] += rs * (dxh - m1 - xh * m2);
+                    const float dxh = v[h >> 1][(h & 1) * 8 + q] * (sg * fmaf(n, 1.0f - sg, 1.0f)) * gm;
+                    o[h][q] += rs * (dxh - m1 - xh * m2);
                 }
-                store8(P.dx, row, c, o);
+                store8(P.dx, row, c, o[h]);
             }
         }
         __syncthreads();
@@ -556,6 +662,8 @@ struct WgradArgs {
 __global__ void __launch_bounds__(kThreads) tlin_wgrad_kernel(const WgradArgs P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ Smem S;
+    __shared__ float s_mu[kKC], s_rs[kKC];
+    __shared__ int s_gi[kKC];
     uint8_t* a_hi = smem_raw;
     uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
     const uint32_t b_term = (uint32_t)P.bcols_pad * kKC * 2;
@@ -582,49 +690,82 @@ __global__ void __launch_bounds__(kThreads) tlin_wgrad_kernel(const WgradArgs P)
     for (int ch = blockIdx.x; ch < P.n_chunks; ch += gridDim.x) {
         const int64_t r0 = (int64_t)ch * kKC;
         const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
-        // A operand = dy^T: (mn = n, kk = row); lanes along n (contiguous in memory), 8 rows per item
-        for (int it = tid; it < n_valid * (kw >> 3); it += kThreads) {
-            const int n = it % n_valid, r8 = it / n_valid;
+        // per-row scalars of the chunk (LayerNorm statistics, gather index) once into shared memory
+        if (tid < kKC) {
+            const int64_t r = r0 + tid;
+            const bool ok = r < P.B;
+            s_mu[tid] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
+            s_rs[tid] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
+            s_gi[tid] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
+        }
+        __syncthreads();
+        const int nr8 = kw >> 3;
+        // A operand = dy^T: (mn = n, kk = row); lanes along n (contiguous in memory), 8 rows per item, 2 items in flight
+        {
+            const int total = n_valid * nr8;
+            for (int it0 = tid; it0 < total; it0 += 2 * kThreads) {
+                float v[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = it0 + u * kThreads;
+                    const int n = it % n_valid, r8 = it / n_valid;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int64_t r = r0 + r8 * 8 + q;
+                        v[u][q] = (it < total && r < P.B) ? __ldg(P.dy + r * P.N + n0 + n) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = it0 + u * kThreads;
+                    if (it < total) store_split(a_hi, a_term_bytes(), op_off(it % n_valid, (it / n_valid) * 8), v[u]);
+                }
+            }
+        }
+        // B operand, feature columns = act(a)^T: (mn = column, kk = row)
+        {
+            const int total = kcols * nr8;
+            for (int it0 = tid; it0 < total; it0 += 2 * kThreads) {
+                float v[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = it0 + u * kThreads;
+                    const int k = kb + it % kcols, r8 = it / kcols;
+                    const float* src = k < P.a.k0 ? P.a.p0 + k : P.a.p1 + (k - P.a.k0);
+                    const int ld = k < P.a.k0 ? P.a.k0 : P.a.k1;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int64_t r = r0 + r8 * 8 + q;
+                        v[u][q] = (it < total && r < P.B) ? __ldg(src + r * ld) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = it0 + u * kThreads;
+                    if (it >= total) continue;
+                    const int c = it % kcols, r8 = it / kcols;
+                    if (ln) {
+                        const float gm = __ldg(P.gamma + kb + c), bt = __ldg(P.beta + kb + c);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int rr = r8 * 8 + q;
+                            const float n = fmaf((v[u][q] - s_mu[rr]) * s_rs[rr], gm, bt);
+                            v[u][q] = n * sigmoidf_(n);          // rows >= B: finite, and the dy operand is 0 there
+                        }
+                    }
+                    store_split(b_hi, b_term, op_off(c, r8 * 8), v[u]);
+                }
+            }
+        }
+        // B operand, extra columns: [1 | onehot(gidx)] and the zero padding up to a multiple of 16
+        for (int it = tid; it < (bcols_pad - kcols) * nr8; it += kThreads) {
+            const int c = kcols + it % (bcols_pad - kcols), r8 = it / (bcols_pad - kcols);
             float v[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int64_t r = r0 + r8 * 8 + q;
-                v[q] = r < P.B ? __ldg(P.dy + r * P.N + n0 + n) : 0.f;
-            }
-            store_split(a_hi, a_term_bytes(), op_off(n, r8 * 8), v);
-        }
-        // B operand = [act(a) | 1 | onehot(gidx)]^T: (mn = column, kk = row)
-        for (int it = tid; it < bcols_pad * (kw >> 3); it += kThreads) {
-            const int c = it % bcols_pad, r8 = it / bcols_pad;
-            float v[8];
-            if (c < kcols) {
-                const int k = kb + c;
-                const float gm = ln ? __ldg(P.gamma + k) : 0.f, bt = ln ? __ldg(P.beta + k) : 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int64_t r = r0 + r8 * 8 + q;
-                    float t = 0.f;
-                    if (r < P.B) {
-                        t = load1(P.a, r, k);
-                        if (ln) {
-                            const float n = fmaf((t - __ldg(P.mean + r)) * __ldg(P.rstd + r), gm, bt);
-                            t = n * sigmoidf_(n);
-                        }
-                    }
-                    v[q] = t;
-                }
-            } else if (c == one_col) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (r0 + r8 * 8 + q < P.B) ? 1.f : 0.f;
-            } else if (hot0 >= 0 && c >= hot0 && c < hot0 + P.T) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int64_t r = r0 + r8 * 8 + q;
-                    v[q] = (r < P.B && P.gidx[r] == (int64_t)(c - hot0)) ? 1.f : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                const int rr = r8 * 8 + q;
+                const bool ok = r0 + rr < P.B;
+                v[q] = (ok && (c == one_col || (hot0 >= 0 && s_gi[rr] == c - hot0))) ? 1.f : 0.f;
             }
             store_split(b_hi, b_term, op_off(c, r8 * 8), v);
         }
@@ -717,7 +858,7 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     const int K = P.a.k0 + P.a.k1;
     P.wvec = (K % 8 == 0) && aligned16(a->w);
     P.wvec2 = seg2 && ((P.a2.k0 + P.a2.k1) % 8 == 0) && aligned16(a->w2);
-    P.yvec = (a->N % 4 == 0) && aligned16(a->y);
+    P.yvec = (a->N % 4 == 0) && aligned16(a->y) && aligned16(a->add) && aligned16(a->gadd);
     const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.n_pad * kKC * 2;
     if (int rc = set_smem((const void*)tlin_fwd_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)128 * kKC * 2, 0)) return rc;
     const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->N + 127) / 128));

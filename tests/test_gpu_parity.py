@@ -321,16 +321,23 @@ def test_training_loss_and_grads_match_reference_autograd():
     _lib.launch_count(reset=True)
     loss = ddpm.loss_from(y_t, ts, cond, mask, noise)
     loss.backward()
-    assert _lib.launch_count() >= 2 * 67          # every LayerNorm->Swish pair ran the fused kernels both ways
+    assert _lib.launch_count() >= 3 * 67          # every Linear ran the tcgen05 forward / dgrad / wgrad kernels
     assert abs(float(loss.detach()) / float(g["loss"]) - 1) < 1e-5
-    worst = 0.0
+    worst, who, errs = 0.0, None, []
     for name, p in ddpm.model.named_parameters():
         want = g["grad." + name]
         if np.abs(want).max() == 0:
             assert float(p.grad.abs().max()) < 1e-12, name
             continue
-        worst = max(worst, rel_l2(p.grad.cpu(), want))
-    assert worst < 2e-4, worst
+        e = rel_l2(p.grad.cpu(), want)
+        errs.append(e)
+        if e > worst:
+            worst, who = e, name
+    print(f"worst parameter-gradient rel-L2 {worst:.2e} ({who}), median {float(np.median(errs)):.2e}")
+    # operands are bf16 hi+lo (16 significant bits, csrc/train_tc.cu): well inside the 1e-3 contraction gate of
+    # BASELINE.json's north star (it prescribes bf16 / tf32 contractions); fp32 cuBLAS measured ~2e-5 here
+    assert worst < 5e-4, (worst, who)
+    assert float(np.median(errs)) < 1e-4
 
 
 def test_training_forward_equals_inference_engine():
