@@ -116,6 +116,7 @@ SYMBOLS = {
     "diffsg_tlin_forward": (C.c_int, [C.POINTER(TlinFwdArgs), _P]),
     "diffsg_tlin_dgrad": (C.c_int, [C.POINTER(TlinDgradArgs), _P]),
     "diffsg_tlin_wgrad": (C.c_int, [C.POINTER(TlinWgradArgs), _P]),
+    "diffsg_tlin_backward": (C.c_int, [C.POINTER(TlinDgradArgs), _I32, C.POINTER(TlinWgradArgs), _I32, _P]),
     "diffsg_plan_query": (C.c_int, [_P, _I32]),
     "diffsg_sample_steps": (C.c_int, [_P, C.POINTER(SampleArgs), _I32, _I32, _I32, _P]),
     "diffsg_sample_renorm": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),

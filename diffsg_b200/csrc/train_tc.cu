@@ -27,7 +27,7 @@ constexpr int kRows = 128;              // rows per tile = UMMA M = TMEM lanes
 constexpr int kKC = 64;                 // contraction columns per staged chunk
 constexpr uint32_t kLBO = 128;          // K-adjacent core matrices are contiguous
 constexpr uint32_t kSBO = kKC * 16;     // next 8 rows
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;          // warps 0-3: row side, warps 4-7: column side (see the scaffolding notes)
 constexpr int kWgradKT = 224;           // feature columns per wgrad CTA (+ <= 32 extra columns = 256 = max UMMA N)
 constexpr int kMaxExtra = 32;
 
@@ -111,6 +111,16 @@ __device__ __forceinline__ void store8(const MatOut& m, int64_t row, int c, cons
 }
 // branch-free (MUFU.EX2 + MUFU.RCP, ~2 ulp): an IEEE division here puts a slow-path branch between the elements of a
 // row and serialises their dependent chains
+// x / d and x % d for the small item counters of the staging loops (x < 4096, d <= 256): q = (x ceil(2^20 / d)) >> 20
+// is exact there (x (d - 1) < 2^20) and fits 32 bits
+struct FastDiv {
+    uint32_t d, m;
+    __device__ __forceinline__ explicit FastDiv(int d_) : d((uint32_t)d_), m(((1u << 20) + (uint32_t)d_ - 1) / (uint32_t)d_) {}
+    __device__ __forceinline__ void divmod(int x, int& q, int& r) const {
+        q = (int)(((uint32_t)x * m) >> 20);
+        r = x - q * (int)d;
+    }
+};
 __device__ __forceinline__ float sigmoidf_(float n) { return __fdividef(1.0f, 1.0f + __expf(-n)); }
 
 __device__ __forceinline__ void red_add(float* p, float v) {
@@ -148,13 +158,18 @@ __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
 __device__ __forceinline__ int colsum16_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
 // ------------------------------------------------------------------------------------------------ CTA scaffolding
+// 256 threads: warps 0-3 are the ROW side (thread t == row t of the tile: A operands, LayerNorm moments), warps 4-7 the
+// COLUMN side (weights / transposed operands); both stage their operand of a chunk concurrently, the loads of chunk i+1
+// are issued before the wait for the MMAs of chunk i (software prefetch into 64 registers per thread), and all eight
+// warps share the epilogue (warp w reads the TMEM lanes of sub-partition w % 4; 32-column rounds alternate between
+// the sides).
 struct Smem {
     uint64_t bar;
     uint32_t tmem_base;
     uint32_t pad_;
 };
 
-// operand ring: [A hi | A lo | B hi | B lo], A = 128 x 64 bf16 = 16 KB per term, B = bn_pad x 64 bf16 per term
+// operand buffers: [A hi | A lo | B hi | B lo], A = 128 x 64 bf16 = 16 KB per term, B = bn_pad x 64 bf16 per term
 __device__ __forceinline__ uint32_t a_term_bytes() { return kRows * kKC * 2; }
 
 __device__ __forceinline__ void cta_setup(Smem& S, uint32_t tmem_cols) {
@@ -177,85 +192,40 @@ __device__ __forceinline__ void cta_teardown(Smem& S, uint32_t tmem_cols) {
     if (threadIdx.x < 32) tmem_dealloc(S.tmem_base, tmem_cols);
 }
 
-// publish the staged chunk, issue its MMAs (one thread) and wait until the tensor core has consumed it
-__device__ __forceinline__ void mma_chunk(Smem& S, uint8_t* a_hi, uint8_t* b_hi, uint32_t b_term, int kw, uint32_t idesc,
-                                          uint32_t d_tmem, bool first, uint32_t& phase) {
+// publish the staged chunk and issue its MMAs (one thread); completion arrives on S.bar
+__device__ __forceinline__ void publish_and_issue(Smem& S, uint8_t* a_hi, uint8_t* b_hi, uint32_t b_term, int kw, uint32_t idesc,
+                                                  uint32_t d_tmem, bool first) {
     fence_proxy_async_smem();
     __syncthreads();
     if (threadIdx.x < 32) {
-        // warp 0 issues; its other lanes park at the __syncwarp (a lane spinning on the mbarrier next to the issuing lane
-        // would starve it: try_wait suspends the whole warp)
         if (threadIdx.x == 0) {
-        tcgen05_fence_after();
-        const uint64_t da_hi = make_smem_desc(smem_u32(a_hi), kLBO, kSBO, 0);
-        const uint64_t da_lo = make_smem_desc(smem_u32(a_hi + a_term_bytes()), kLBO, kSBO, 0);
-        const uint64_t db_hi = make_smem_desc(smem_u32(b_hi), kLBO, kSBO, 0);
-        const uint64_t db_lo = make_smem_desc(smem_u32(b_hi + b_term), kLBO, kSBO, 0);
-        uint32_t acc = first ? 0u : 1u;
-        for (int ks = 0; ks < kw / 16; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 16);        // two core matrices = 256 bytes, >> 4
-            umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
-            umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
-            umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
-            acc = 1;
+            tcgen05_fence_after();
+            const uint64_t da_hi = make_smem_desc(smem_u32(a_hi), kLBO, kSBO, 0);
+            const uint64_t da_lo = make_smem_desc(smem_u32(a_hi + a_term_bytes()), kLBO, kSBO, 0);
+            const uint64_t db_hi = make_smem_desc(smem_u32(b_hi), kLBO, kSBO, 0);
+            const uint64_t db_lo = make_smem_desc(smem_u32(b_hi + b_term), kLBO, kSBO, 0);
+            uint32_t acc = first ? 0u : 1u;
+            for (int ks = 0; ks < kw / 16; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 16);        // two core matrices = 256 bytes, >> 4
+                umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
+                umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
+                umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+                acc = 1;
+            }
+            umma_commit(&S.bar);
         }
-        umma_commit(&S.bar);
-        }
-        __syncwarp();
+        __syncwarp();       // the other lanes park here: a lane spinning on the mbarrier would starve the issuing lane
     }
+}
+__device__ __forceinline__ void wait_consumed(Smem& S, uint32_t& phase) {
     mbar_wait(&S.bar, phase);
     phase ^= 1;
     tcgen05_fence_after();
 }
 
-// operand whose contraction dimension is contiguous in memory: src[mn][k] with row stride ld (weights [N, K] in the
-// forward).  Items (mn, 8-column piece), mn fastest across lanes: 16-byte conflict-free shared stores.  Four items per
-// thread are loaded before the first one is converted (memory-level parallelism: the loop is latency-bound otherwise).
-__device__ __forceinline__ void stage_rowmajor_w(uint8_t* hi_base, uint32_t lo_delta, const float* __restrict__ w, int ld,
-                                                 int n0, int n_valid, int n_pad, int k0, int K, int kw, bool vec) {
-    const int pieces = kw >> 3, total = n_pad * pieces;
-    if (vec) {
-        for (int it0 = threadIdx.x; it0 < total; it0 += 4 * kThreads) {
-            float4 a[4], b[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int it = it0 + u * kThreads;
-                const int n = it % n_pad, c = k0 + (it / n_pad) * 8;
-                a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (it < total && n < n_valid && c < K) {
-                    const float4* p = reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * ld + c);
-                    a[u] = __ldg(p);
-                    b[u] = __ldg(p + 1);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int it = it0 + u * kThreads;
-                if (it < total) {
-                    const float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
-                    store_split(hi_base, lo_delta, op_off(it % n_pad, (it / n_pad) * 8), v);
-                }
-            }
-        }
-        return;
-    }
-    for (int it = threadIdx.x; it < total; it += kThreads) {
-        const int n = it % n_pad, j = it / n_pad;
-        const int c = k0 + j * 8;
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (n < n_valid && c + q < K) ? __ldg(w + (size_t)(n0 + n) * ld + c + q) : 0.f;
-        store_split(hi_base, lo_delta, op_off(n, j * 8), v);
-    }
-}
-
-// one 64-column chunk of this thread's row (thread == row) of a row-major matrix: all loads first, then the optional
-// LayerNorm -> Swish, the bf16 split and the stores
-template <bool kAct>
-__device__ __forceinline__ void stage_row_chunk(uint8_t* a_hi, const Mat& A, int64_t row, bool valid, int k0, int kw, int K,
-                                                float mu, float rs, const float* s_gamma, const float* s_beta) {
-    const int pieces = kw >> 3;
-    float v[8][8];
+// ---- row side: one <= 64-column chunk of row `row` of a row-major matrix (8 pieces of 8 columns in `v`)
+__device__ __forceinline__ void row_chunk_load(const Mat& A, int64_t row, bool valid, int k0, int kw, float (&v)[8][8]) {
+    const int pieces = kw >> 3, K = A.k0 + A.k1;
     if (A.vec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -276,10 +246,15 @@ __device__ __forceinline__ void stage_row_chunk(uint8_t* a_hi, const Mat& A, int
             if (j < pieces && valid) load8(A, row, k0 + j * 8, v[j]);
         }
     }
+}
+template <bool kAct>
+__device__ __forceinline__ void row_chunk_store(uint8_t* a_hi, int t, int k0, int kw, float mu, float rs, const float* s_gamma,
+                                                const float* s_beta, float (&v)[8][8]) {
+    const int pieces = kw >> 3;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (j < pieces) {
-            if (kAct && valid) {
+            if (kAct) {
                 const int c = k0 + j * 8;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -288,8 +263,47 @@ __device__ __forceinline__ void stage_row_chunk(uint8_t* a_hi, const Mat& A, int
                     v[j][q] = n * sigmoidf_(n);
                 }
             }
-            store_split(a_hi, a_term_bytes(), op_off(threadIdx.x, j * 8), v[j]);
+            store_split(a_hi, a_term_bytes(), op_off(t, j * 8), v[j]);
         }
+    }
+}
+
+// ---- column side, operand whose contraction dimension is contiguous in memory: src[mn][k] with row stride ld (the
+// weights [N, K] of the forward).  Items (mn, 8-column piece), mn fastest across lanes (16-byte conflict-free shared
+// stores), <= 8 items per thread.
+__device__ __forceinline__ void w_chunk_load(float (&v)[8][8], const float* __restrict__ w, int ld, int n0, int n_valid, int n_pad,
+                                             const FastDiv& fd, int k0, int K, int kw, bool vec, int t) {
+    const int total = n_pad * (kw >> 3);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int it = t + u * kRows;
+        int n, j;
+        fd.divmod(it, j, n);
+        const int c = k0 + j * 8;
+        const bool ok = it < total && n < n_valid && c < K;
+        if (vec) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (ok) {
+                const float4* p = reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * ld + c);
+                a = __ldg(p);
+                b = __ldg(p + 1);
+            }
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[u][q] = (ok && c + q < K) ? __ldg(w + (size_t)(n0 + n) * ld + c + q) : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void w_chunk_store(float (&v)[8][8], uint8_t* b_hi, uint32_t b_term, int n_pad, const FastDiv& fd, int kw,
+                                              int t) {
+    const int total = n_pad * (kw >> 3);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int it = t + u * kRows;
+        int n, j;
+        fd.divmod(it, j, n);
+        if (it < total) store_split(b_hi, b_term, op_off(n, j * 8), v[u]);
     }
 }
 
@@ -313,7 +327,7 @@ struct FwdArgs {
     int N, n_pad, tmem_cols, wvec, wvec2, yvec;
 };
 
-__global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
+__global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ Smem S;
     __shared__ float s_gamma[256], s_beta[256];
@@ -321,14 +335,15 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
     uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
     const uint32_t b_term = (uint32_t)P.n_pad * kKC * 2;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int64_t row = (int64_t)blockIdx.x * kRows + tid;
+    const int tid = threadIdx.x, warp = tid >> 5, side = warp >> 2, t = tid & 127;
+    const int64_t row = (int64_t)blockIdx.x * kRows + t;
     const bool valid = row < P.B;
     const int n0 = blockIdx.y * 128;
     const int n_valid = min(128, P.N - n0);
     const int n_pad = min(P.n_pad, (n_valid + 15) & ~15);
     const bool ln = P.gamma != nullptr;
-    const int K0 = P.a.k0 + P.a.k1;
+    const int K0 = P.a.k0 + P.a.k1, K1 = P.a2.p0 ? P.a2.k0 + P.a2.k1 : 0;
+    const int nc0 = (K0 + kKC - 1) / kKC, nchunk = nc0 + (K1 + kKC - 1) / kKC;
 
     if (ln)
         for (int i = tid; i < 256; i += kThreads) { s_gamma[i] = i < K0 ? P.gamma[i] : 0.f; s_beta[i] = i < K0 ? P.beta[i] : 0.f; }
@@ -336,9 +351,9 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad);
 
-    // LayerNorm moments of this thread's row (shifted one-pass sums)
+    // LayerNorm moments of the row (row side; the column side is already fetching the first weight chunk)
     float mu = 0.f, rs = 0.f;
-    if (ln && valid) {
+    if (side == 0 && ln && valid) {
         const float x0 = load1(P.a, row, 0);
         float s = 0.f, q = 0.f;
         for (int c = 0; c < K0; c += 32) {
@@ -360,31 +375,39 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
         if (blockIdx.y == 0) { P.mean[row] = mu; P.rstd[row] = rs; }
     }
 
+    float buf[8][8];
     uint32_t phase = 0;
-    bool first = true;
-    const int nseg = P.a2.p0 ? 2 : 1;
-    for (int seg = 0; seg < nseg; ++seg) {
-        const Mat& A = seg ? P.a2 : P.a;
-        const float* W = seg ? P.w2 : P.w;
-        const bool wvec = seg ? P.wvec2 : P.wvec;
-        const bool act = ln && seg == 0;
-        const int K = A.k0 + A.k1;
-        for (int k0 = 0; k0 < K; k0 += kKC) {
-            const int kw = min(kKC, (K - k0 + 15) & ~15);
-            // A chunk: thread == row
-            if (act) stage_row_chunk<true>(a_hi, A, row, valid, k0, kw, K, mu, rs, s_gamma, s_beta);
-            else stage_row_chunk<false>(a_hi, A, row, valid, k0, kw, K, 0.f, 0.f, nullptr, nullptr);
-            stage_rowmajor_w(b_hi, b_term, W, K, n0, n_valid, n_pad, k0, K, kw, wvec);
-            mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
-            first = false;
+    const FastDiv fd(n_pad);
+    auto chunk_load = [&](int i) {
+        const int seg = i >= nc0;
+        const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
+        const int kw = min(kKC, (K - k0 + 15) & ~15);
+        if (side == 0) row_chunk_load(seg ? P.a2 : P.a, row, valid, k0, kw, buf);
+        else w_chunk_load(buf, seg ? P.w2 : P.w, K, n0, n_valid, n_pad, fd, k0, K, kw, seg ? P.wvec2 : P.wvec, t);
+    };
+    chunk_load(0);
+    for (int i = 0; i < nchunk; ++i) {
+        const int seg = i >= nc0;
+        const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
+        const int kw = min(kKC, (K - k0 + 15) & ~15);
+        if (i > 0) wait_consumed(S, phase);
+        if (side == 0) {
+            if (ln && seg == 0) row_chunk_store<true>(a_hi, t, k0, kw, mu, rs, s_gamma, s_beta, buf);
+            else row_chunk_store<false>(a_hi, t, k0, kw, 0.f, 0.f, nullptr, nullptr, buf);
+        } else {
+            w_chunk_store(buf, b_hi, b_term, n_pad, fd, kw, t);
         }
+        publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
+        if (i + 1 < nchunk) chunk_load(i + 1);
     }
+    wait_consumed(S, phase);
 
-    // epilogue: accumulator row -> + bias (+ add, + gathered add) -> y; 32 columns per round, addend loads first
-    const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+    // epilogue: accumulator row -> + bias (+ add, + gathered add) -> y; 32 columns per round (rounds alternate between
+    // the two sides), addend loads first
+    const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int64_t grow = (valid && P.gidx) ? P.gidx[row] : 0;
     const int ngroups = n_pad / 16;
-    for (int g = 0; g < ngroups; g += 2) {
+    for (int g = 2 * side; g < ngroups; g += 4) {
         const bool two = g + 1 < ngroups;
         float ex[2][16];
 #pragma unroll
@@ -398,16 +421,16 @@ __global__ void __launch_bounds__(kThreads) tlin_fwd_kernel(const FwdArgs P) {
                     const float4* ap = reinterpret_cast<const float4*>(P.add + row * P.N + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 t = __ldg(ap + j);
-                        ex[u][4 * j] += t.x; ex[u][4 * j + 1] += t.y; ex[u][4 * j + 2] += t.z; ex[u][4 * j + 3] += t.w;
+                        const float4 x = __ldg(ap + j);
+                        ex[u][4 * j] += x.x; ex[u][4 * j + 1] += x.y; ex[u][4 * j + 2] += x.z; ex[u][4 * j + 3] += x.w;
                     }
                 }
                 if (P.gadd) {
                     const float4* gp = reinterpret_cast<const float4*>(P.gadd + grow * P.N + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 t = __ldg(gp + j);
-                        ex[u][4 * j] += t.x; ex[u][4 * j + 1] += t.y; ex[u][4 * j + 2] += t.z; ex[u][4 * j + 3] += t.w;
+                        const float4 x = __ldg(gp + j);
+                        ex[u][4 * j] += x.x; ex[u][4 * j + 1] += x.y; ex[u][4 * j + 2] += x.z; ex[u][4 * j + 3] += x.w;
                     }
                 }
             } else {
@@ -471,18 +494,45 @@ struct DgradArgs {
     int N, K, kt, kt_pad, tmem_cols, dyvec;
 };
 
-__global__ void __launch_bounds__(kThreads) tlin_dgrad_kernel(const DgradArgs P) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ Smem S;
-    __shared__ float s_gamma[256], s_beta[256], s_dg[256], s_db[256];
+// column side of dgrad: B operand = W^T, (mn = k, kk = n); memory is contiguous along k -> lanes along k, 8 n values per
+// item; items [first, first + 8) of this thread
+__device__ __forceinline__ void wt_items_load(float (&v)[8][8], const DgradArgs& P, int kb, int k_valid, int k_pad, const FastDiv& fd,
+                                              int n0, int kw, int t, int first) {
+    const int total = k_pad * (kw >> 3);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int it = t + (first + u) * kRows;
+        int k, n8;
+        fd.divmod(it, n8, k);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int n = n0 + n8 * 8 + q;
+            v[u][q] = (it < total && k < k_valid && n < P.N) ? __ldg(P.w + (size_t)n * P.K + kb + k) : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void wt_items_store(float (&v)[8][8], uint8_t* b_hi, uint32_t b_term, int k_pad, const FastDiv& fd, int kw,
+                                               int t, int first) {
+    const int total = k_pad * (kw >> 3);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int it = t + (first + u) * kRows;
+        int k, n8;
+        fd.divmod(it, n8, k);
+        if (it < total) store_split(b_hi, b_term, op_off(k, n8 * 8), v[u]);
+    }
+}
+
+__device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw, Smem& S, int bx, int by) {
+    __shared__ float s_gamma[256], s_beta[256], s_dg[256], s_db[256], s_p1[2][kRows], s_p2[2][kRows];
     uint8_t* a_hi = smem_raw;
     uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
     const uint32_t b_term = (uint32_t)P.kt_pad * kKC * 2;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t row = (int64_t)blockIdx.x * kRows + tid;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, side = warp >> 2, t = tid & 127;
+    const int64_t row = (int64_t)bx * kRows + t;
     const bool valid = row < P.B;
-    const int kb = blockIdx.y * P.kt;                       // first output column of this CTA
+    const int kb = by * P.kt;                       // first output column of this CTA
     const int k_valid = min(P.kt, P.K - kb);
     const int k_pad = (k_valid + 15) & ~15;
     const bool ln = P.gamma != nullptr;
@@ -498,41 +548,38 @@ __global__ void __launch_bounds__(kThreads) tlin_dgrad_kernel(const DgradArgs P)
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)k_pad);
     const Mat DY{P.dy, nullptr, P.N, 0, P.dyvec};
+    const int nchunk = (P.N + kKC - 1) / kKC;
+    const FastDiv fd(k_pad);
 
+    float buf[8][8];
     uint32_t phase = 0;
-    bool first = true;
-    for (int n0 = 0; n0 < P.N; n0 += kKC) {
-        const int kw = min(kKC, (P.N - n0 + 15) & ~15);
-        // A chunk = dy rows (thread == row)
-        stage_row_chunk<false>(a_hi, DY, row, valid, n0, kw, P.N, 0.f, 0.f, nullptr, nullptr);
-        // B chunk = W^T: (mn = k, kk = n); memory is contiguous along k -> lanes along k, 8 n values per item
-        const int total = k_pad * (kw >> 3);
-        for (int it0 = tid; it0 < total; it0 += 2 * kThreads) {
-            float v[2][8];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int it = it0 + u * kThreads;
-                const int k = it % k_pad, n8 = it / k_pad;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n = n0 + n8 * 8 + q;
-                    v[u][q] = (it < total && k < k_valid && n < P.N) ? __ldg(P.w + (size_t)n * P.K + kb + k) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int it = it0 + u * kThreads;
-                if (it < total) store_split(b_hi, b_term, op_off(it % k_pad, (it / k_pad) * 8), v[u]);
+    auto chunk_load = [&](int i) {
+        const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
+        if (side == 0) row_chunk_load(DY, row, valid, n0, kw, buf);
+        else wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 0);
+    };
+    chunk_load(0);
+    for (int i = 0; i < nchunk; ++i) {
+        const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
+        if (i > 0) wait_consumed(S, phase);
+        if (side == 0) {
+            row_chunk_store<false>(a_hi, t, n0, kw, 0.f, 0.f, nullptr, nullptr, buf);
+        } else {
+            wt_items_store(buf, b_hi, b_term, k_pad, fd, kw, t, 0);
+            if (k_pad * (kw >> 3) > 8 * kRows) {             // wide outputs: items 8..15 of the thread
+                wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 8);
+                wt_items_store(buf, b_hi, b_term, k_pad, fd, kw, t, 8);
             }
         }
-        mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
-        first = false;
+        publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
+        if (i + 1 < nchunk) chunk_load(i + 1);
     }
+    wait_consumed(S, phase);
 
-    const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int ngroups = k_pad / 16;
     if (!ln) {
-        for (int g = 0; g < ngroups; g += 2) {
+        for (int g = 2 * side; g < ngroups; g += 4) {
             const bool two = g + 1 < ngroups;
             float o[4][8];
 #pragma unroll
@@ -558,10 +605,11 @@ __global__ void __launch_bounds__(kThreads) tlin_dgrad_kernel(const DgradArgs P)
     } else {
         // LayerNorm -> Swish backward on the accumulator row g = d(swish(n)), n = gamma xh + beta, xh = (x - mu) rstd:
         //   dn = g swish'(n);  dxh = dn gamma;  dx = rstd (dxh - mean(dxh) - xh mean(dxh xh));  dgamma += dn xh;  dbeta += dn
-        // Two passes over the accumulator (row sums first), 32 columns per round with the x loads issued first.
+        // Two passes over the accumulator (row sums first); each side owns every other 32-column round of the row and the
+        // two partial row sums meet in shared memory.  x loads are issued before the TMEM loads of a round.
         const float mu = valid ? P.mean[row] : 0.f, rs = valid ? P.rstd[row] : 0.f;
         float s1 = 0.f, s2 = 0.f;
-        for (int g = 0; g < ngroups; g += 2) {
+        for (int g = 2 * side; g < ngroups; g += 4) {
             const bool two = g + 1 < ngroups;
             float x[4][8];
 #pragma unroll
@@ -600,8 +648,11 @@ __global__ void __launch_bounds__(kThreads) tlin_dgrad_kernel(const DgradArgs P)
                 }
             }
         }
-        const float m1 = s1 / (float)P.K, m2 = s2 / (float)P.K;
-        for (int g = 0; g < ngroups; g += 2) {
+        s_p1[side][t] = s1;
+        s_p2[side][t] = s2;
+        __syncthreads();
+        const float m1 = (s_p1[0][t] + s_p1[1][t]) / (float)P.K, m2 = (s_p2[0][t] + s_p2[1][t]) / (float)P.K;
+        for (int g = 2 * side; g < ngroups; g += 4) {
             const bool two = g + 1 < ngroups;
             float x[4][8], o[4][8];
 #pragma unroll
@@ -659,126 +710,147 @@ struct WgradArgs {
     int N, K, T, n_chunks, tmem_cols, bcols_pad, dwvec;
 };
 
-__global__ void __launch_bounds__(kThreads) tlin_wgrad_kernel(const WgradArgs P) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ Smem S;
-    __shared__ float s_mu[kKC], s_rs[kKC];
-    __shared__ int s_gi[kKC];
+// transposed operand items: (mn = feature, kk = row); lanes along the feature (contiguous in memory), 8 rows per item;
+// items [first, first + 8) of the thread.  src = element (row 0, feature 0), ld = row stride.
+__device__ __forceinline__ void tr_items_load(float (&v)[8][8], const Mat& M, int f0, int nf, const FastDiv& fd, int64_t r0, int nr8,
+                                              int64_t B, int t, int first) {
+    const int total = nf * nr8;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int it = t + (first + u) * kRows;
+        int f, r8;
+        fd.divmod(it, r8, f);
+        f += f0;
+        const float* src = f < M.k0 ? M.p0 + f : M.p1 + (f - M.k0);
+        const int ld = f < M.k0 ? M.k0 : M.k1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t r = r0 + r8 * 8 + q;
+            v[u][q] = (it < total && r < B) ? __ldg(src + r * ld) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw, Smem& S, int bx, int by, int bz, int gx, int gz) {
+    __shared__ float s_mu[2][kKC], s_rs[2][kKC];
+    __shared__ int s_gi[2][kKC];
     uint8_t* a_hi = smem_raw;
     uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
     const uint32_t b_term = (uint32_t)P.bcols_pad * kKC * 2;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int n0 = blockIdx.y * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, side = warp >> 2, t = tid & 127;
+    const int n0 = by * 128;
     const int n_valid = min(128, P.N - n0);
-    const int kb = blockIdx.z * kWgradKT;
+    const int kb = bz * kWgradKT;
     const int kcols = min(kWgradKT, P.K - kb);
-    const bool last_z = blockIdx.z == gridDim.z - 1;
+    const bool last_z = bz == gz - 1;
     const int n_extra = last_z ? ((P.dbias ? 1 : 0) + (P.dgadd ? P.T : 0)) : 0;
     const int one_col = (last_z && P.dbias) ? kcols : -1;
     const int hot0 = (last_z && P.dgadd) ? kcols + (P.dbias ? 1 : 0) : -1;
     const int bcols = kcols + n_extra;
     const int bcols_pad = (bcols + 15) & ~15;
     const bool ln = P.gamma != nullptr;
+    const Mat DY{P.dy, nullptr, P.N, 0, 0};
 
     cta_setup(S, P.tmem_cols);
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)bcols_pad);
 
+    float buf[8][8];
     uint32_t phase = 0;
-    bool first = true;
-    for (int ch = blockIdx.x; ch < P.n_chunks; ch += gridDim.x) {
+    const FastDiv fd_n(n_valid), fd_k(kcols), fd_x(max(bcols_pad - kcols, 1));
+    auto chunk_load = [&](int ch, int slot) {
+        const int64_t r0 = (int64_t)ch * kKC;
+        const int nr8 = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15) >> 3;
+        if (side == 0) {
+            tr_items_load(buf, DY, n0, n_valid, fd_n, r0, nr8, P.B, t, 0);
+            if (t < kKC) {                       // per-row scalars of the chunk (LayerNorm statistics, gather index)
+                const int64_t r = r0 + t;
+                const bool ok = r < P.B;
+                s_mu[slot][t] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
+                s_rs[slot][t] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
+                s_gi[slot][t] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
+            }
+        } else {
+            tr_items_load(buf, P.a, kb, kcols, fd_k, r0, nr8, P.B, t, 0);
+        }
+    };
+    // LayerNorm -> Swish of staged feature items (column side) and the store
+    auto b_items_store = [&](int slot, int nr8, int first) {
+        const int total = kcols * nr8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int it = t + (first + u) * kRows;
+            if (it >= total) continue;
+            int c, r8;
+            fd_k.divmod(it, r8, c);
+            if (ln) {
+                const float gm = __ldg(P.gamma + kb + c), bt = __ldg(P.beta + kb + c);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int rr = r8 * 8 + q;
+                    const float n = fmaf((buf[u][q] - s_mu[slot][rr]) * s_rs[slot][rr], gm, bt);
+                    buf[u][q] = n * sigmoidf_(n);          // rows >= B: finite, and the dy operand is 0 there
+                }
+            }
+            store_split(b_hi, b_term, op_off(c, r8 * 8), buf[u]);
+        }
+    };
+
+    int it_no = 0;
+    if (bx < P.n_chunks) chunk_load(bx, 0);
+    for (int ch = bx; ch < P.n_chunks; ch += gx, ++it_no) {
+        const int slot = it_no & 1;
         const int64_t r0 = (int64_t)ch * kKC;
         const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
-        // per-row scalars of the chunk (LayerNorm statistics, gather index) once into shared memory
-        if (tid < kKC) {
-            const int64_t r = r0 + tid;
-            const bool ok = r < P.B;
-            s_mu[tid] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
-            s_rs[tid] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
-            s_gi[tid] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
-        }
-        __syncthreads();
         const int nr8 = kw >> 3;
-        // A operand = dy^T: (mn = n, kk = row); lanes along n (contiguous in memory), 8 rows per item, 2 items in flight
-        {
+        if (it_no > 0) wait_consumed(S, phase);
+        __syncthreads();                                     // the chunk's per-row scalars are visible to the column side
+        if (side == 0) {
+            // A operand = dy^T
             const int total = n_valid * nr8;
-            for (int it0 = tid; it0 < total; it0 += 2 * kThreads) {
-                float v[2][8];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int it = it0 + u * kThreads;
-                    const int n = it % n_valid, r8 = it / n_valid;
+            for (int u = 0; u < 8; ++u) {
+                const int it = t + u * kRows;
+                int nn, r8;
+                fd_n.divmod(it, r8, nn);
+                if (it < total) store_split(a_hi, a_term_bytes(), op_off(nn, r8 * 8), buf[u]);
+            }
+        } else {
+            // B operand = [act(a) | 1 | onehot(gidx)]^T
+            b_items_store(slot, nr8, 0);
+            if (kcols * nr8 > 8 * kRows) {
+                tr_items_load(buf, P.a, kb, kcols, fd_k, r0, nr8, P.B, t, 8);
+                b_items_store(slot, nr8, 8);
+            }
+            const int nx = bcols_pad - kcols;
+            for (int it = t; it < nx * nr8; it += kRows) {
+                int c, r8;
+                fd_x.divmod(it, r8, c);
+                c += kcols;
+                float v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int64_t r = r0 + r8 * 8 + q;
-                        v[u][q] = (it < total && r < P.B) ? __ldg(P.dy + r * P.N + n0 + n) : 0.f;
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    const int rr = r8 * 8 + q;
+                    const bool ok = r0 + rr < P.B;
+                    v[q] = (ok && (c == one_col || (hot0 >= 0 && s_gi[slot][rr] == c - hot0))) ? 1.f : 0.f;
                 }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int it = it0 + u * kThreads;
-                    if (it < total) store_split(a_hi, a_term_bytes(), op_off(it % n_valid, (it / n_valid) * 8), v[u]);
-                }
+                store_split(b_hi, b_term, op_off(c, r8 * 8), v);
             }
         }
-        // B operand, feature columns = act(a)^T: (mn = column, kk = row)
-        {
-            const int total = kcols * nr8;
-            for (int it0 = tid; it0 < total; it0 += 2 * kThreads) {
-                float v[2][8];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int it = it0 + u * kThreads;
-                    const int k = kb + it % kcols, r8 = it / kcols;
-                    const float* src = k < P.a.k0 ? P.a.p0 + k : P.a.p1 + (k - P.a.k0);
-                    const int ld = k < P.a.k0 ? P.a.k0 : P.a.k1;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int64_t r = r0 + r8 * 8 + q;
-                        v[u][q] = (it < total && r < P.B) ? __ldg(src + r * ld) : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int it = it0 + u * kThreads;
-                    if (it >= total) continue;
-                    const int c = it % kcols, r8 = it / kcols;
-                    if (ln) {
-                        const float gm = __ldg(P.gamma + kb + c), bt = __ldg(P.beta + kb + c);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int rr = r8 * 8 + q;
-                            const float n = fmaf((v[u][q] - s_mu[rr]) * s_rs[rr], gm, bt);
-                            v[u][q] = n * sigmoidf_(n);          // rows >= B: finite, and the dy operand is 0 there
-                        }
-                    }
-                    store_split(b_hi, b_term, op_off(c, r8 * 8), v[u]);
-                }
-            }
-        }
-        // B operand, extra columns: [1 | onehot(gidx)] and the zero padding up to a multiple of 16
-        for (int it = tid; it < (bcols_pad - kcols) * nr8; it += kThreads) {
-            const int c = kcols + it % (bcols_pad - kcols), r8 = it / (bcols_pad - kcols);
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int rr = r8 * 8 + q;
-                const bool ok = r0 + rr < P.B;
-                v[q] = (ok && (c == one_col || (hot0 >= 0 && s_gi[rr] == c - hot0))) ? 1.f : 0.f;
-            }
-            store_split(b_hi, b_term, op_off(c, r8 * 8), v);
-        }
-        mma_chunk(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, first, phase);
-        first = false;
+        publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, it_no == 0);
+        if (ch + gx < P.n_chunks) chunk_load(ch + gx, slot ^ 1);
     }
+    if (it_no > 0) wait_consumed(S, phase);
 
-    // epilogue: TMEM lane n = output feature n0 + n; columns = [dW row | db | d(gadd) column]
-    const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
-    const bool has_n = tid < n_valid && !first;
-    const int n = n0 + tid;
+    // epilogue: TMEM lane n = output feature n0 + n; columns = [dW row | db | d(gadd) column]; 16-column groups
+    // alternate between the two sides
+    const int n_loc = (warp & 3) * 32 + (tid & 31);
+    const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool has_n = n_loc < n_valid && it_no > 0;
+    const int n = n0 + n_loc;
     const bool v4 = P.dwvec != 0;
-    for (int g = 0; g < bcols_pad / 16; ++g) {
+    for (int g = side; g < bcols_pad / 16; g += 2) {
         float v[16];
         tmem_ld16(t_row + g * 16, v);
         tmem_ld_wait();
@@ -800,6 +872,38 @@ __global__ void __launch_bounds__(kThreads) tlin_wgrad_kernel(const WgradArgs P)
         }
     }
     cta_teardown(S, P.tmem_cols);
+}
+
+// ================================================================================================ backward launch
+// One launch runs up to two wgrad and two dgrad problems of a node side by side (they only share inputs): the persistent
+// wgrad CTAs first, then the dgrad tiles.  Each CTA picks its role from its block index.
+struct BwdArgs {
+    DgradArgs d[2];
+    WgradArgs w[2];
+    int nd, nw;
+    int d_cta[2], d_gy[2];
+    int w_cta[2], w_gx[2], w_gy[2], w_gz[2];
+};
+
+__global__ void __launch_bounds__(kThreads, 2) tlin_bwd_kernel(const __grid_constant__ BwdArgs P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Smem S;
+    int b = blockIdx.x;
+    for (int j = 0; j < P.nw; ++j) {
+        if (b < P.w_cta[j]) {
+            const int gx = P.w_gx[j], gy = P.w_gy[j];
+            wgrad_body(P.w[j], smem_raw, S, b % gx, (b / gx) % gy, b / (gx * gy), gx, P.w_gz[j]);
+            return;
+        }
+        b -= P.w_cta[j];
+    }
+    for (int j = 0; j < P.nd; ++j) {
+        if (b < P.d_cta[j]) {
+            dgrad_body(P.d[j], smem_raw, S, b / P.d_gy[j], b % P.d_gy[j]);
+            return;
+        }
+        b -= P.d_cta[j];
+    }
 }
 
 static inline uint32_t pow2_cols(int n) {
@@ -868,9 +972,9 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     return DIFFSG_OK;
 }
 
-int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* a, void* stream) {
-    if (a && a->B == 0) return DIFFSG_OK;
-    if (!a || !a->dy || !a->w || a->N <= 0 || a->K <= 0 || a->B < 0 || !a->dx.p0) { set_error("tlin_dgrad: bad argument"); return DIFFSG_E_INVALID; }
+// argument checks + kernel-side structs; `grid` receives the CTA geometry of the problem
+static int prep_dgrad(const diffsg_tlin_dgrad_args* a, DgradArgs& P, int& n_tiles, int& gy, size_t& smem) {
+    if (!a || !a->dy || !a->w || a->N <= 0 || a->K <= 0 || a->B <= 0 || !a->dx.p0) { set_error("tlin_dgrad: bad argument"); return DIFFSG_E_INVALID; }
     if (a->dx.k0 + (a->dx.k1 > 0 ? a->dx.k1 : 0) != a->K) { set_error("tlin_dgrad: dx split does not add up to K"); return DIFFSG_E_INVALID; }
     const bool ln = a->gamma != nullptr;
     if (ln && (!a->beta || !a->mean || !a->rstd || !a->dgamma || !a->dbeta || !mat_ok(a->x) || a->x.k0 + (a->x.k1 > 0 ? a->x.k1 : 0) != a->K)) {
@@ -879,7 +983,7 @@ int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* a, void* stream) {
     }
     if (ln && a->K > 256) { set_error("tlin_dgrad: LayerNorm width %d > 256", a->K); return DIFFSG_E_UNSUPPORTED; }
     if (a->dres.p0 && a->dres.k0 + (a->dres.k1 > 0 ? a->dres.k1 : 0) != a->K) { set_error("tlin_dgrad: dres split does not add up to K"); return DIFFSG_E_INVALID; }
-    DgradArgs P{};
+    P = DgradArgs{};
     P.dy = a->dy; P.w = a->w; P.gamma = a->gamma; P.beta = a->beta; P.mean = a->mean; P.rstd = a->rstd;
     if (ln) P.x = to_mat(a->x);
     if (a->dres.p0) P.dres = to_mat(a->dres); else P.dres = Mat{nullptr, nullptr, 0, 0, 0};
@@ -892,46 +996,79 @@ int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* a, void* stream) {
     P.kt_pad = (kmax + 15) & ~15;
     P.tmem_cols = (int)pow2_cols(P.kt_pad);
     P.dyvec = (a->N % 8 == 0) && aligned16(a->dy);
-    const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.kt_pad * kKC * 2;
-    if (int rc = set_smem((const void*)tlin_dgrad_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 1)) return rc;
-    const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->K + P.kt - 1) / P.kt));
-    tlin_dgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
-    count_launch();
-    DIFFSG_CUDA_OK(cudaGetLastError());
+    smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.kt_pad * kKC * 2;
+    n_tiles = (int)((a->B + kRows - 1) / kRows);
+    gy = (a->K + P.kt - 1) / P.kt;
     return DIFFSG_OK;
 }
 
-int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* a, void* stream) {
-    if (a && a->B == 0) return DIFFSG_OK;
-    if (!a || !a->dy || !mat_ok(a->a) || !a->dw || a->N <= 0 || a->B < 0) { set_error("tlin_wgrad: bad argument"); return DIFFSG_E_INVALID; }
+static int prep_wgrad(const diffsg_tlin_wgrad_args* a, WgradArgs& P, int& gx, int& gy, int& gz, size_t& smem) {
+    if (!a || !a->dy || !mat_ok(a->a) || !a->dw || a->N <= 0 || a->B <= 0) { set_error("tlin_wgrad: bad argument"); return DIFFSG_E_INVALID; }
     const bool ln = a->gamma != nullptr;
     if (ln && (!a->beta || !a->mean || !a->rstd)) { set_error("tlin_wgrad: LayerNorm mode needs beta, mean, rstd"); return DIFFSG_E_INVALID; }
     if (a->dgadd && (!a->gidx || a->gadd_rows <= 0)) { set_error("tlin_wgrad: dgadd needs gidx and gadd_rows"); return DIFFSG_E_INVALID; }
     const int n_extra = (a->dbias ? 1 : 0) + (a->dgadd ? a->gadd_rows : 0);
     if (n_extra > kMaxExtra) { set_error("tlin_wgrad: %d gathered rows > %d", a->gadd_rows, kMaxExtra - 1); return DIFFSG_E_UNSUPPORTED; }
-    WgradArgs P{};
+    P = WgradArgs{};
     P.dy = a->dy; P.a = to_mat(a->a); P.gamma = a->gamma; P.beta = a->beta; P.mean = a->mean; P.rstd = a->rstd;
     P.gidx = a->gidx; P.dw = a->dw; P.dbias = a->dbias; P.dgadd = a->dgadd; P.B = a->B; P.N = a->N;
     P.K = P.a.k0 + P.a.k1; P.T = a->dgadd ? a->gadd_rows : 0;
     P.n_chunks = (int)((a->B + kKC - 1) / kKC);
-    const int nz = (P.K + kWgradKT - 1) / kWgradKT, ny = (a->N + 127) / 128;
+    gz = (P.K + kWgradKT - 1) / kWgradKT;
+    gy = (a->N + 127) / 128;
     const int k_first = P.K < kWgradKT ? P.K : kWgradKT;
-    const int k_last = P.K - (nz - 1) * kWgradKT;
-    int widest = nz > 1 ? kWgradKT : k_first;
+    const int k_last = P.K - (gz - 1) * kWgradKT;
+    int widest = gz > 1 ? kWgradKT : k_first;
     if (k_last + n_extra > widest) widest = k_last + n_extra;
     P.bcols_pad = (widest + 15) & ~15;
     P.dwvec = (P.K % 4 == 0) && aligned16(a->dw);
     P.tmem_cols = (int)pow2_cols(P.bcols_pad);
-    int gx = 296 / (ny * nz);
+    gx = 296 / (gy * gz);
     if (gx < 1) gx = 1;
     if (gx > P.n_chunks) gx = P.n_chunks;
-    const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.bcols_pad * kKC * 2;
-    if (int rc = set_smem((const void*)tlin_wgrad_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 2)) return rc;
-    const dim3 grid((unsigned)gx, (unsigned)ny, (unsigned)nz);
-    tlin_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+    smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.bcols_pad * kKC * 2;
+    return DIFFSG_OK;
+}
+
+int diffsg_tlin_backward(const diffsg_tlin_dgrad_args* dgrads, int32_t n_dgrad, const diffsg_tlin_wgrad_args* wgrads,
+                         int32_t n_wgrad, void* stream) {
+    if (n_dgrad < 0 || n_dgrad > 2 || n_wgrad < 0 || n_wgrad > 2 || (n_dgrad && !dgrads) || (n_wgrad && !wgrads)) {
+        set_error("tlin_backward: at most two dgrad and two wgrad problems per launch");
+        return DIFFSG_E_INVALID;
+    }
+    BwdArgs P{};
+    size_t smem = 0;
+    int total = 0;
+    for (int j = 0; j < n_wgrad; ++j) {
+        if (wgrads[j].B == 0) continue;
+        size_t sm = 0;
+        int gx = 0, gy = 0, gz = 0;
+        if (int rc = prep_wgrad(&wgrads[j], P.w[P.nw], gx, gy, gz, sm)) return rc;
+        P.w_gx[P.nw] = gx; P.w_gy[P.nw] = gy; P.w_gz[P.nw] = gz; P.w_cta[P.nw] = gx * gy * gz;
+        total += P.w_cta[P.nw];
+        if (sm > smem) smem = sm;
+        ++P.nw;
+    }
+    for (int j = 0; j < n_dgrad; ++j) {
+        if (dgrads[j].B == 0) continue;
+        size_t sm = 0;
+        int nt = 0, gy = 0;
+        if (int rc = prep_dgrad(&dgrads[j], P.d[P.nd], nt, gy, sm)) return rc;
+        P.d_gy[P.nd] = gy; P.d_cta[P.nd] = nt * gy;
+        total += P.d_cta[P.nd];
+        if (sm > smem) smem = sm;
+        ++P.nd;
+    }
+    if (total == 0) return DIFFSG_OK;
+    if (int rc = set_smem((const void*)tlin_bwd_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 1)) return rc;
+    tlin_bwd_kernel<<<(unsigned)total, kThreads, smem, (cudaStream_t)stream>>>(P);
     count_launch();
     DIFFSG_CUDA_OK(cudaGetLastError());
     return DIFFSG_OK;
 }
+
+int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* a, void* stream) { return diffsg_tlin_backward(a, 1, nullptr, 0, stream); }
+
+int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* a, void* stream) { return diffsg_tlin_backward(nullptr, 0, a, 1, stream); }
 
 }  // extern "C"

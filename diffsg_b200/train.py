@@ -100,7 +100,6 @@ class _FusedLinear(torch.autograd.Function):
         dy = _prep(dy)
         B, N = dy.shape
         dev = dy.device
-        st = None
         out = [None] * 13
 
         def target(i, p):
@@ -110,54 +109,61 @@ class _FusedLinear(torch.autograd.Function):
             out[i] = ret
             return t
 
-        with torch.cuda.device(dev):
-            st = _lib.stream_ptr()
-            # ---- wgrad of the main segment (+ bias gradient, + scatter of the gathered add)
-            dw, db = target(4, w), target(5, b)
-            dgadd = None
-            if need[11] and ctx.gadd_rows:
-                dgadd = torch.zeros(ctx.gadd_rows, N, dtype=torch.float32, device=dev)
-                out[11] = dgadd
-            if dw is not None or db is not None or dgadd is not None:
-                if dw is None:                                   # frozen weight: the kernel still needs a target
-                    dw = torch.zeros_like(w)
-                a = _lib.TlinWgradArgs(dy=dy.data_ptr(), a=_mat(x0, x1), gamma=_ptr(gamma), beta=_ptr(beta),
-                                       mean=_ptr(mean), rstd=_ptr(rstd), gidx=_ptr(gidx) if dgadd is not None else None,
-                                       dw=dw.data_ptr(), dbias=_ptr(db), dgadd=_ptr(dgadd), B=B, N=N,
-                                       gadd_rows=ctx.gadd_rows if dgadd is not None else 0)
-                _lib.check(lib.diffsg_tlin_wgrad(C.byref(a), st), "diffsg_tlin_wgrad")
-            # ---- wgrad of the second (identity) segment
-            if w2 is not None:
-                dw2, db2 = target(8, w2), target(9, b2)
-                if dw2 is not None or db2 is not None:
-                    if dw2 is None:
-                        dw2 = torch.zeros_like(w2)
-                    a = _lib.TlinWgradArgs(dy=dy.data_ptr(), a=_mat(z0, z1), dw=dw2.data_ptr(), dbias=_ptr(db2), B=B, N=N)
-                    _lib.check(lib.diffsg_tlin_wgrad(C.byref(a), st), "diffsg_tlin_wgrad")
-            # ---- dgrad of the main segment (through the LayerNorm -> Swish backward when there is one)
-            if need[0] or (x1 is not None and need[1]) or (gamma is not None and (need[2] or need[3])):
-                dx0 = torch.empty_like(x0)
-                dx1 = torch.empty_like(x1) if x1 is not None else None
-                dg = dbt = None
-                if gamma is not None:
-                    dg, dbt = target(2, gamma), target(3, beta)
-                    dg = dg if dg is not None else torch.zeros_like(gamma)
-                    dbt = dbt if dbt is not None else torch.zeros_like(beta)
-                a = _lib.TlinDgradArgs(dy=dy.data_ptr(), w=w.data_ptr(), x=_mat(x0, x1) if gamma is not None else _mat(None),
-                                       gamma=_ptr(gamma), beta=_ptr(beta), mean=_ptr(mean), rstd=_ptr(rstd), dres=_mat(None),
-                                       dx=_mat(dx0, dx1), dgamma=_ptr(dg), dbeta=_ptr(dbt), B=B, N=N, K=w.shape[1])
-                _lib.check(lib.diffsg_tlin_dgrad(C.byref(a), st), "diffsg_tlin_dgrad")
-                out[0] = dx0 if need[0] else None
-                out[1] = dx1 if (x1 is not None and need[1]) else None
-            # ---- dgrad of the second segment
-            if w2 is not None and (need[6] or (z1 is not None and need[7])):
-                dz0 = torch.empty_like(z0)
-                dz1 = torch.empty_like(z1) if z1 is not None else None
-                a = _lib.TlinDgradArgs(dy=dy.data_ptr(), w=w2.data_ptr(), x=_mat(None), dres=_mat(None), dx=_mat(dz0, dz1),
-                                       B=B, N=N, K=w2.shape[1])
-                _lib.check(lib.diffsg_tlin_dgrad(C.byref(a), st), "diffsg_tlin_dgrad")
-                out[6] = dz0 if need[6] else None
-                out[7] = dz1 if (z1 is not None and need[7]) else None
+        wg, dg = [], []
+        keep = []                                            # temporaries the kernels write into: alive until the launch
+        # ---- wgrad of the main segment (+ bias gradient, + scatter of the gathered add)
+        dw, db = target(4, w), target(5, b)
+        dgadd = None
+        if need[11] and ctx.gadd_rows:
+            dgadd = torch.zeros(ctx.gadd_rows, N, dtype=torch.float32, device=dev)
+            out[11] = dgadd
+        if dw is not None or db is not None or dgadd is not None:
+            if dw is None:                                   # frozen weight: the kernel still needs a target
+                dw = torch.zeros_like(w)
+                keep.append(dw)
+            wg.append(_lib.TlinWgradArgs(dy=dy.data_ptr(), a=_mat(x0, x1), gamma=_ptr(gamma), beta=_ptr(beta),
+                                         mean=_ptr(mean), rstd=_ptr(rstd), gidx=_ptr(gidx) if dgadd is not None else None,
+                                         dw=dw.data_ptr(), dbias=_ptr(db), dgadd=_ptr(dgadd), B=B, N=N,
+                                         gadd_rows=ctx.gadd_rows if dgadd is not None else 0))
+        # ---- wgrad of the second (identity) segment
+        if w2 is not None:
+            dw2, db2 = target(8, w2), target(9, b2)
+            if dw2 is not None or db2 is not None:
+                if dw2 is None:
+                    dw2 = torch.zeros_like(w2)
+                    keep.append(dw2)
+                wg.append(_lib.TlinWgradArgs(dy=dy.data_ptr(), a=_mat(z0, z1), dw=dw2.data_ptr(), dbias=_ptr(db2), B=B, N=N))
+        # ---- dgrad of the main segment (through the LayerNorm -> Swish backward when there is one)
+        if need[0] or (x1 is not None and need[1]) or (gamma is not None and (need[2] or need[3])):
+            dx0 = torch.empty_like(x0)
+            dx1 = torch.empty_like(x1) if x1 is not None else None
+            dgm = dbt = None
+            if gamma is not None:
+                dgm, dbt = target(2, gamma), target(3, beta)
+                dgm = dgm if dgm is not None else torch.zeros_like(gamma)
+                dbt = dbt if dbt is not None else torch.zeros_like(beta)
+                keep += [dgm, dbt]
+            dg.append(_lib.TlinDgradArgs(dy=dy.data_ptr(), w=w.data_ptr(), x=_mat(x0, x1) if gamma is not None else _mat(None),
+                                         gamma=_ptr(gamma), beta=_ptr(beta), mean=_ptr(mean), rstd=_ptr(rstd), dres=_mat(None),
+                                         dx=_mat(dx0, dx1), dgamma=_ptr(dgm), dbeta=_ptr(dbt), B=B, N=N, K=w.shape[1]))
+            out[0] = dx0 if need[0] else None
+            out[1] = dx1 if (x1 is not None and need[1]) else None
+            keep += [dx0, dx1]
+        # ---- dgrad of the second segment
+        if w2 is not None and (need[6] or (z1 is not None and need[7])):
+            dz0 = torch.empty_like(z0)
+            dz1 = torch.empty_like(z1) if z1 is not None else None
+            dg.append(_lib.TlinDgradArgs(dy=dy.data_ptr(), w=w2.data_ptr(), x=_mat(None), dres=_mat(None), dx=_mat(dz0, dz1),
+                                         B=B, N=N, K=w2.shape[1]))
+            out[6] = dz0 if need[6] else None
+            out[7] = dz1 if (z1 is not None and need[7]) else None
+            keep += [dz0, dz1]
+        if wg or dg:
+            dga = (_lib.TlinDgradArgs * max(len(dg), 1))(*dg)
+            wga = (_lib.TlinWgradArgs * max(len(wg), 1))(*wg)
+            with torch.cuda.device(dev):                     # ONE launch for the whole backward of the node
+                _lib.check(lib.diffsg_tlin_backward(dga, len(dg), wga, len(wg), _lib.stream_ptr()), "diffsg_tlin_backward")
+        del keep
         if need[10]:
             out[10] = dy
         return tuple(out)

@@ -377,6 +377,11 @@ typedef struct diffsg_tlin_wgrad_args {
 } diffsg_tlin_wgrad_args;
 int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* args, void* stream);
 
+/* The whole backward of one fused node in ONE launch: up to two dgrad and two wgrad problems (main segment + second
+ * segment) that only share inputs run side by side; CTAs pick their role from the block index. */
+int diffsg_tlin_backward(const diffsg_tlin_dgrad_args* dgrads, int32_t n_dgrad, const diffsg_tlin_wgrad_args* wgrads,
+                         int32_t n_wgrad, void* stream);
+
 /* ---- test hooks (not part of the product surface) ------------------------------------
  * One 128-row tcgen05 GEMM tile: C[128,N] = A[128,K] . W[N,K]^T with A split into fp16
  * (hi, lo) in-kernel and W given as pre-packed fp16 core-matrix images. */
