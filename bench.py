@@ -301,7 +301,7 @@ def run_train(args, rank, local_rank, world):
 
     warm = max(args.warmup, 10)
     steps = 50 if args.steps == 3 else args.steps                    # SURVEY cfg5: 50 timed steps after 10 warm-up
-    # this library's kernels per step (fused LayerNorm->Swish forward / backward, Adam+EMA), counted on one eager step with
+    # this library's kernels per step (tcgen05 forward / backward nodes, Adam+EMA), counted on one eager step with
     # lr = 0: inside the timed region they are replayed from CUDA graphs, which the launch counter cannot see
     lr0 = tr.opt.lr
     tr.opt.set_lr(0.0)
@@ -335,20 +335,22 @@ def run_train(args, rank, local_rank, world):
         pk, pk_kind = peaks()
         peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         line = {"metric": TRAIN_METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
-                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3",
                 "data": "synthetic",
                 "config": {"workload": "BASELINE configs[4]: 80c MSR eps-MSE training step + EMA every 5th step, synthetic "
                                        "x = rand(B,80), y = rand(B,80) * W/40, data-parallel: one flat-gradient NCCL all-reduce per step",
                            "batch_per_gpu": B, "T": T, "optimizer": "fused Adam + EMA kernel (diffsg_adam_step), lr 1e-3",
                            "graph": "eager" if args.no_graph else "forward+backward and optimiser replayed as CUDA graphs",
-                           "gemm": "cuBLAS through autograd (F.linear); LayerNorm->Swish fwd/bwd and Adam+EMA are this library's kernels"},
+                           "gemm": "this library's tcgen05 kernels (tlin_fwd_kernel / tlin_bwd_kernel: bf16 hi+lo operands, fp32 TMEM "
+                                   "accumulators, LayerNorm->Swish fused into the operand prologue / dgrad epilogue); no cuBLAS in the step"},
                 "clocks": clk.summary(), "gpu_launches": own_kernels_per_step * steps, "own_kernels_per_step": own_kernels_per_step,
                 "final_loss": float(loss),
                 "replicas_identical": same, "allreduce_bytes_per_step": tr.flat.numel * 4 if world > 1 else 0,
                 "roofline": {"bound": "tensor", "achieved": value / world * f_train / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                              "frac": value / world * f_train / 1e12 / peak_tf, "traffic": None, "flop_per_sample": f_train,
                              "peak_source": f"{pk_kind} bf16 sustained",
-                             "note": "fp32 cuBLAS GEMMs of width <= 256: launch- and HBM-bound, far from the tensor roofline"}}
+                             "note": "GEMMs of width <= 256 on 128-row tiles: bound by operand staging (fp32 -> bf16 hi+lo through the "
+                                     "LSU) and launch latency, far from the tensor roofline; three MMAs per product are not counted"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -223,47 +223,83 @@ __device__ __forceinline__ void wait_consumed(Smem& S, uint32_t& phase) {
     tcgen05_fence_after();
 }
 
-// ---- row side: one <= 64-column chunk of row `row` of a row-major matrix (8 pieces of 8 columns in `v`)
-__device__ __forceinline__ void row_chunk_load(const Mat& A, int64_t row, bool valid, int k0, int kw, float (&v)[8][8]) {
+// ---- row side: one <= 64-column chunk of the 128-row tile of a row-major matrix.  Lane l of warp w covers row
+// 32 w + 8 g + (l & 7) and the 8-column piece (l >> 3) + 4 h for item u = 2 g + h: one warp-wide load touches 8 rows x
+// 128 contiguous bytes (8 cache lines instead of the 32 of a thread-per-row walk), and the 8 lanes of a quarter warp
+// store one whole 128-byte core matrix (conflict-free).
+struct RowMap {
+    int r_in, pq, wbase;
+    __device__ __forceinline__ explicit RowMap(int t) : r_in(t & 7), pq((t & 31) >> 3), wbase(t & ~31) {}
+    __device__ __forceinline__ int row(int u) const { return wbase + 8 * (u >> 1) + r_in; }      // row inside the tile
+    __device__ __forceinline__ int piece(int u) const { return pq + 4 * (u & 1); }
+};
+__device__ __forceinline__ void row_chunk_load(const Mat& A, const RowMap& rm, int64_t row0, int64_t B, int k0, int kw, float (&v)[8][8]) {
     const int pieces = kw >> 3, K = A.k0 + A.k1;
-    if (A.vec) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = k0 + j * 8;
+    for (int u = 0; u < 8; ++u) {
+        const int64_t row = row0 + rm.row(u);
+        const int pc = rm.piece(u), c = k0 + pc * 8;
+        const bool ok = pc < pieces && row < B;
+        if (A.vec) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (j < pieces && valid && c < K) {
+            if (ok && c < K) {
                 const float4* p = reinterpret_cast<const float4*>(c < A.k0 ? A.p0 + row * A.k0 + c : A.p1 + row * A.k1 + (c - A.k0));
                 a = __ldg(p);
                 b = __ldg(p + 1);
             }
-            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
-        }
-    } else {
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[j][q] = 0.f;
-            if (j < pieces && valid) load8(A, row, k0 + j * 8, v[j]);
+            for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
+            if (ok) load8(A, row, c, v[u]);
         }
     }
 }
+// mu / rs: LayerNorm statistics of the thread's four rows (row group g = u >> 1)
 template <bool kAct>
-__device__ __forceinline__ void row_chunk_store(uint8_t* a_hi, int t, int k0, int kw, float mu, float rs, const float* s_gamma,
-                                                const float* s_beta, float (&v)[8][8]) {
+__device__ __forceinline__ void row_chunk_store(uint8_t* a_hi, const RowMap& rm, int k0, int kw, const float (&mu)[4], const float (&rs)[4],
+                                                const float* s_gamma, const float* s_beta, float (&v)[8][8]) {
     const int pieces = kw >> 3;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (j < pieces) {
+    for (int u = 0; u < 8; ++u) {
+        const int pc = rm.piece(u);
+        if (pc < pieces) {
             if (kAct) {
-                const int c = k0 + j * 8;
+                const int c = k0 + pc * 8;
+                const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c), g1 = *reinterpret_cast<const float4*>(s_gamma + c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c), b1 = *reinterpret_cast<const float4*>(s_beta + c + 4);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float m = mu[u >> 1], r = rs[u >> 1];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     // columns >= K: x = gamma = beta = 0 (zero-padded tables) -> n = 0 -> swish = 0, no per-element branch
-                    const float n = fmaf((v[j][q] - mu) * rs, s_gamma[c + q], s_beta[c + q]);
-                    v[j][q] = n * sigmoidf_(n);
+                    const float n = fmaf((v[u][q] - m) * r, gm[q], bt[q]);
+                    v[u][q] = n * sigmoidf_(n);
                 }
             }
-            store_split(a_hi, a_term_bytes(), op_off(t, j * 8), v[j]);
+            store_split(a_hi, a_term_bytes(), op_off(rm.row(u), pc * 8), v[u]);
+        }
+    }
+}
+
+// ---- epilogue through shared memory: the accumulator rows (thread == row == TMEM lane) are parked in a padded row-major
+// tile in the operand buffers (free after the last MMA) and leave it through row-contiguous, fully coalesced accesses
+constexpr int kTilePad = 4;             // floats; row stride 4 (mod 32) words: conflict-free 16-byte accesses from 8 rows
+__device__ __forceinline__ void tmem_rows_to_tile(float* tile, int ld, uint32_t d_tmem, int warp, int side, int t, int col0, int ncols16) {
+    const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+    for (int g = 2 * side; g < ncols16; g += 4) {
+        const bool two = g + 1 < ncols16;
+        float v[2][16];
+        tmem_ld16(t_row + g * 16, v[0]);
+        if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) continue;
+            float4* dst = reinterpret_cast<float4*>(tile + (size_t)t * ld + (g + u) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[u][4 * j], v[u][4 * j + 1], v[u][4 * j + 2], v[u][4 * j + 3]);
         }
     }
 }
@@ -336,8 +372,6 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     const uint32_t b_term = (uint32_t)P.n_pad * kKC * 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, side = warp >> 2, t = tid & 127;
-    const int64_t row = (int64_t)blockIdx.x * kRows + t;
-    const bool valid = row < P.B;
     const int n0 = blockIdx.y * 128;
     const int n_valid = min(128, P.N - n0);
     const int n_pad = min(P.n_pad, (n_valid + 15) & ~15);
@@ -351,28 +385,49 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad);
 
-    // LayerNorm moments of the row (row side; the column side is already fetching the first weight chunk)
-    float mu = 0.f, rs = 0.f;
-    if (side == 0 && ln && valid) {
-        const float x0 = load1(P.a, row, 0);
-        float s = 0.f, q = 0.f;
-        for (int c = 0; c < K0; c += 32) {
+    // LayerNorm moments of the thread's four rows (row side; the column side is already fetching the first weight chunk):
+    // shifted one-pass sums over the lane's pieces, then over the four lanes that share a row
+    const RowMap rm(t);
+    const int64_t row0 = (int64_t)blockIdx.x * kRows;
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (side == 0 && ln) {
+        float x0[4], sm[4], sq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int64_t r = row0 + rm.row(2 * g);
+            x0[g] = r < P.B ? load1(P.a, r, 0) : 0.f;
+            sm[g] = sq[g] = 0.f;
+        }
+        for (int c = rm.pq * 8; c < K0; c += 32) {
             float v[4][8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) load8(P.a, row, c + u * 8, v[u]);          // columns >= K read as 0
+            for (int g = 0; g < 4; ++g) {
+                const int64_t r = row0 + rm.row(2 * g);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int j = 0; j < 8; ++j) v[g][j] = 0.f;
+                if (r < P.B) load8(P.a, r, c, v[g]);                       // columns >= K read as 0
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float d = (c + u * 8 + j < K0) ? v[u][j] - x0 : 0.f;
-                    s += d;
-                    q = fmaf(d, d, q);
+                    const float d = (c + j < K0) ? v[g][j] - x0[g] : 0.f;
+                    sm[g] += d;
+                    sq[g] = fmaf(d, d, sq[g]);
                 }
         }
-        const float md = s / (float)K0;
-        mu = x0 + md;
-        rs = rsqrtf(fmaxf(q / (float)K0 - md * md, 0.f) + kLnEps);
-        if (blockIdx.y == 0) { P.mean[row] = mu; P.rstd[row] = rs; }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            sm[g] += __shfl_xor_sync(0xffffffffu, sm[g], 8);
+            sq[g] += __shfl_xor_sync(0xffffffffu, sq[g], 8);
+            sm[g] += __shfl_xor_sync(0xffffffffu, sm[g], 16);
+            sq[g] += __shfl_xor_sync(0xffffffffu, sq[g], 16);
+            const float md = sm[g] / (float)K0;
+            mu[g] = x0[g] + md;
+            rs[g] = rsqrtf(fmaxf(sq[g] / (float)K0 - md * md, 0.f) + kLnEps);
+            const int64_t r = row0 + rm.row(2 * g);
+            if (blockIdx.y == 0 && rm.pq == 0 && r < P.B) { P.mean[r] = mu[g]; P.rstd[r] = rs[g]; }
+        }
     }
 
     float buf[8][8];
@@ -382,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
         const int seg = i >= nc0;
         const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
         const int kw = min(kKC, (K - k0 + 15) & ~15);
-        if (side == 0) row_chunk_load(seg ? P.a2 : P.a, row, valid, k0, kw, buf);
+        if (side == 0) row_chunk_load(seg ? P.a2 : P.a, rm, row0, P.B, k0, kw, buf);
         else w_chunk_load(buf, seg ? P.w2 : P.w, K, n0, n_valid, n_pad, fd, k0, K, kw, seg ? P.wvec2 : P.wvec, t);
     };
     chunk_load(0);
@@ -392,8 +447,8 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
         const int kw = min(kKC, (K - k0 + 15) & ~15);
         if (i > 0) wait_consumed(S, phase);
         if (side == 0) {
-            if (ln && seg == 0) row_chunk_store<true>(a_hi, t, k0, kw, mu, rs, s_gamma, s_beta, buf);
-            else row_chunk_store<false>(a_hi, t, k0, kw, 0.f, 0.f, nullptr, nullptr, buf);
+            if (ln && seg == 0) row_chunk_store<true>(a_hi, rm, k0, kw, mu, rs, s_gamma, s_beta, buf);
+            else row_chunk_store<false>(a_hi, rm, k0, kw, mu, rs, nullptr, nullptr, buf);
         } else {
             w_chunk_store(buf, b_hi, b_term, n_pad, fd, kw, t);
         }
@@ -402,76 +457,63 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     }
     wait_consumed(S, phase);
 
-    // epilogue: accumulator row -> + bias (+ add, + gathered add) -> y; 32 columns per round (rounds alternate between
-    // the two sides), addend loads first
-    const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int64_t grow = (valid && P.gidx) ? P.gidx[row] : 0;
-    const int ngroups = n_pad / 16;
-    for (int g = 2 * side; g < ngroups; g += 4) {
-        const bool two = g + 1 < ngroups;
-        float ex[2][16];
+    // epilogue: accumulator rows -> shared-memory tile -> (+ bias, + add, + gathered add) -> y, row-contiguous
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    const int ld = n_pad + kTilePad;
+    tmem_rows_to_tile(tile, ld, d_tmem, warp, side, t, 0, n_pad / 16);
+    __syncthreads();
+    if (P.yvec) {
+        const int nc4 = n_valid >> 2;                       // N % 4 == 0
+        const FastDiv f4(nc4);
+        const int total = kRows * nc4;
+        for (int it0 = tid; it0 < total; it0 += 4 * kThreads) {
+            float4 ex[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int c0 = n0 + (g + u) * 16;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ex[u][j] = 0.f;
-            if (!valid || (u == 1 && !two)) continue;
-            if (P.yvec && c0 + 16 <= P.N) {
-                if (P.add) {
-                    const float4* ap = reinterpret_cast<const float4*>(P.add + row * P.N + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 x = __ldg(ap + j);
-                        ex[u][4 * j] += x.x; ex[u][4 * j + 1] += x.y; ex[u][4 * j + 2] += x.z; ex[u][4 * j + 3] += x.w;
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * kThreads;
+                int r, c4;
+                f4.divmod(it, r, c4);
+                const int64_t grow_ = row0 + r;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it < total && grow_ < P.B) {
+                    const int c = n0 + c4 * 4;
+                    if (P.bias) { const float4 x = __ldg(reinterpret_cast<const float4*>(P.bias + c)); e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w; }
+                    if (P.bias2) { const float4 x = __ldg(reinterpret_cast<const float4*>(P.bias2 + c)); e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w; }
+                    if (P.add) { const float4 x = __ldg(reinterpret_cast<const float4*>(P.add + grow_ * P.N + c)); e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w; }
+                    if (P.gadd) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(P.gadd + P.gidx[grow_] * P.N + c));
+                        e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w;
                     }
                 }
-                if (P.gadd) {
-                    const float4* gp = reinterpret_cast<const float4*>(P.gadd + grow * P.N + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 x = __ldg(gp + j);
-                        ex[u][4 * j] += x.x; ex[u][4 * j + 1] += x.y; ex[u][4 * j + 2] += x.z; ex[u][4 * j + 3] += x.w;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = c0 + j;
-                    if (c < P.N) {
-                        if (P.add) ex[u][j] += __ldg(P.add + row * P.N + c);
-                        if (P.gadd) ex[u][j] += __ldg(P.gadd + grow * P.N + c);
-                    }
-                }
+                ex[u] = e;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int c = c0 + j;
-                if (c < P.N) {
-                    if (P.bias) ex[u][j] += __ldg(P.bias + c);
-                    if (P.bias2) ex[u][j] += __ldg(P.bias2 + c);
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * kThreads;
+                int r, c4;
+                f4.divmod(it, r, c4);
+                const int64_t grow_ = row0 + r;
+                if (it < total && grow_ < P.B) {
+                    const float4 a = *reinterpret_cast<const float4*>(tile + (size_t)r * ld + c4 * 4);
+                    *reinterpret_cast<float4*>(P.y + grow_ * P.N + n0 + c4 * 4) = make_float4(a.x + ex[u].x, a.y + ex[u].y, a.z + ex[u].z, a.w + ex[u].w);
                 }
             }
         }
-        float v[2][16];
-        tmem_ld16(t_row + g * 16, v[0]);
-        if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
-        tmem_ld_wait();
-        if (!valid) continue;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) continue;
-            const int c0 = n0 + (g + u) * 16;
-            float* yp = P.y + row * P.N + c0;
-            if (P.yvec && c0 + 16 <= P.N) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    reinterpret_cast<float4*>(yp)[j] = make_float4(v[u][4 * j] + ex[u][4 * j], v[u][4 * j + 1] + ex[u][4 * j + 1],
-                                                                   v[u][4 * j + 2] + ex[u][4 * j + 2], v[u][4 * j + 3] + ex[u][4 * j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < P.N) yp[j] = v[u][j] + ex[u][j];
-            }
+    } else {
+        const FastDiv f1(n_valid);
+        const int total = kRows * n_valid;
+        for (int it = tid; it < total; it += kThreads) {
+            int r, cl;
+            f1.divmod(it, r, cl);
+            const int64_t grow_ = row0 + r;
+            if (grow_ >= P.B) continue;
+            const int c = n0 + cl;
+            float e = tile[(size_t)r * ld + cl];
+            if (P.bias) e += __ldg(P.bias + c);
+            if (P.bias2) e += __ldg(P.bias2 + c);
+            if (P.add) e += __ldg(P.add + grow_ * P.N + c);
+            if (P.gadd) e += __ldg(P.gadd + P.gidx[grow_] * P.N + c);
+            P.y[grow_ * P.N + c] = e;
         }
     }
     cta_teardown(S, P.tmem_cols);
@@ -550,12 +592,15 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
     const Mat DY{P.dy, nullptr, P.N, 0, P.dyvec};
     const int nchunk = (P.N + kKC - 1) / kKC;
     const FastDiv fd(k_pad);
+    const RowMap rm(t);
+    const int64_t row0 = (int64_t)bx * kRows;
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
 
     float buf[8][8];
     uint32_t phase = 0;
     auto chunk_load = [&](int i) {
         const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
-        if (side == 0) row_chunk_load(DY, row, valid, n0, kw, buf);
+        if (side == 0) row_chunk_load(DY, rm, row0, P.B, n0, kw, buf);
         else wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 0);
     };
     chunk_load(0);
@@ -563,7 +608,7 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
         const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
         if (i > 0) wait_consumed(S, phase);
         if (side == 0) {
-            row_chunk_store<false>(a_hi, t, n0, kw, 0.f, 0.f, nullptr, nullptr, buf);
+            row_chunk_store<false>(a_hi, rm, n0, kw, zero4, zero4, nullptr, nullptr, buf);
         } else {
             wt_items_store(buf, b_hi, b_term, k_pad, fd, kw, t, 0);
             if (k_pad * (kw >> 3) > 8 * kRows) {             // wide outputs: items 8..15 of the thread
@@ -579,27 +624,56 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
     const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int ngroups = k_pad / 16;
     if (!ln) {
-        for (int g = 2 * side; g < ngroups; g += 4) {
-            const bool two = g + 1 < ngroups;
-            float o[4][8];
+        // accumulator rows -> shared-memory tile -> (+ dres) -> dx, row-contiguous
+        float* tile = reinterpret_cast<float*>(smem_raw);
+        const int ld = k_pad + kTilePad;
+        tmem_rows_to_tile(tile, ld, d_tmem, warp, side, t, 0, ngroups);
+        __syncthreads();
+        if (P.dx.vec && (!P.dres.p0 || P.dres.vec)) {
+            const int nc4 = k_valid >> 2;
+            const FastDiv f4(nc4);
+            const int total = kRows * nc4;
+            for (int it0 = tid; it0 < total; it0 += 4 * kThreads) {
+                float4 ex[4];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + u * kThreads;
+                    int r, c4;
+                    f4.divmod(it, r, c4);
+                    const int64_t grow_ = row0 + r;
+                    const int c = kb + c4 * 4;
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (it < total && grow_ < P.B && P.dres.p0)
+                        e = __ldg(reinterpret_cast<const float4*>(c < P.dres.k0 ? P.dres.p0 + grow_ * P.dres.k0 + c : P.dres.p1 + grow_ * P.dres.k1 + (c - P.dres.k0)));
+                    ex[u] = e;
+                }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[h][q] = 0.f;
-                if (valid && P.dres.p0 && (h < 2 || two)) load8(P.dres, row, kb + g * 16 + h * 8, o[h]);
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + u * kThreads;
+                    int r, c4;
+                    f4.divmod(it, r, c4);
+                    const int64_t grow_ = row0 + r;
+                    const int c = kb + c4 * 4;
+                    if (it < total && grow_ < P.B) {
+                        const float4 a = *reinterpret_cast<const float4*>(tile + (size_t)r * ld + c4 * 4);
+                        float* dst = c < P.dx.k0 ? P.dx.p0 + grow_ * P.dx.k0 + c : P.dx.p1 + grow_ * P.dx.k1 + (c - P.dx.k0);
+                        *reinterpret_cast<float4*>(dst) = make_float4(a.x + ex[u].x, a.y + ex[u].y, a.z + ex[u].z, a.w + ex[u].w);
+                    }
+                }
             }
-            float v[2][16];
-            tmem_ld16(t_row + g * 16, v[0]);
-            if (two) tmem_ld16(t_row + (g + 1) * 16, v[1]);
-            tmem_ld_wait();
-            if (!valid) continue;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int c = kb + g * 16 + h * 8;
-                if ((h >= 2 && !two) || c >= P.K) continue;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[h][q] += v[h >> 1][(h & 1) * 8 + q];
-                store8(P.dx, row, c, o[h]);
+        } else {
+            const FastDiv f1(k_valid);
+            const int total = kRows * k_valid;
+            for (int it = tid; it < total; it += kThreads) {
+                int r, cl;
+                f1.divmod(it, r, cl);
+                const int64_t grow_ = row0 + r;
+                if (grow_ >= P.B) continue;
+                const int c = kb + cl;
+                float e = tile[(size_t)r * ld + cl];
+                if (P.dres.p0) e += load1(P.dres, grow_, c);
+                if (c < P.dx.k0) P.dx.p0[grow_ * P.dx.k0 + c] = e;
+                else P.dx.p1[grow_ * P.dx.k1 + (c - P.dx.k0)] = e;
             }
         }
     } else {
@@ -962,9 +1036,11 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     const int K = P.a.k0 + P.a.k1;
     P.wvec = (K % 8 == 0) && aligned16(a->w);
     P.wvec2 = seg2 && ((P.a2.k0 + P.a2.k1) % 8 == 0) && aligned16(a->w2);
-    P.yvec = (a->N % 4 == 0) && aligned16(a->y) && aligned16(a->add) && aligned16(a->gadd);
-    const size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.n_pad * kKC * 2;
-    if (int rc = set_smem((const void*)tlin_fwd_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)128 * kKC * 2, 0)) return rc;
+    P.yvec = (a->N % 4 == 0) && aligned16(a->y) && aligned16(a->add) && aligned16(a->gadd) && aligned16(a->bias) && aligned16(P.bias2);
+    size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.n_pad * kKC * 2;
+    const size_t tile = (size_t)kRows * (P.n_pad + kTilePad) * sizeof(float);        // epilogue tile shares the operand buffers
+    if (tile > smem) smem = tile;
+    if (int rc = set_smem((const void*)tlin_fwd_kernel, (size_t)kRows * (128 + kTilePad) * sizeof(float), 0)) return rc;
     const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->N + 127) / 128));
     tlin_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
     count_launch();
@@ -997,6 +1073,8 @@ static int prep_dgrad(const diffsg_tlin_dgrad_args* a, DgradArgs& P, int& n_tile
     P.tmem_cols = (int)pow2_cols(P.kt_pad);
     P.dyvec = (a->N % 8 == 0) && aligned16(a->dy);
     smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.kt_pad * kKC * 2;
+    const size_t tile = ln ? 0 : (size_t)kRows * (P.kt_pad + kTilePad) * sizeof(float);
+    if (tile > smem) smem = tile;
     n_tiles = (int)((a->B + kRows - 1) / kRows);
     gy = (a->K + P.kt - 1) / P.kt;
     return DIFFSG_OK;

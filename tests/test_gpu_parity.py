@@ -321,7 +321,7 @@ def test_training_loss_and_grads_match_reference_autograd():
     _lib.launch_count(reset=True)
     loss = ddpm.loss_from(y_t, ts, cond, mask, noise)
     loss.backward()
-    assert _lib.launch_count() >= 3 * 67          # every Linear ran the tcgen05 forward / dgrad / wgrad kernels
+    assert _lib.launch_count() >= 2 * 67          # every Linear ran the tcgen05 forward node and the one-launch backward node
     assert abs(float(loss.detach()) / float(g["loss"]) - 1) < 1e-5
     worst, who, errs = 0.0, None, []
     for name, p in ddpm.model.named_parameters():
