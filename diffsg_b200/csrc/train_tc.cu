@@ -14,6 +14,7 @@
 // One CTA = 128 threads = one 128-row tile (thread == row == TMEM lane in every prologue / epilogue); operands are
 // UMMA K-major no-swizzle core-matrix chunks of 64 contraction columns (the sampler engine's layout, unet_tc.cuh).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -156,6 +157,17 @@ __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
     return d;
 }
 __device__ __forceinline__ int colsum16_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+// Programmatic dependent launch: the kernels are launched with programmatic stream serialization, so a CTA may start
+// while the previous kernel of the stream is still draining.  Everything before pdl_wait() touches only parameters
+// (weights, LayerNorm gamma / beta: last written by the optimiser, many full stream barriers ago) and on-chip state
+// (barriers, TMEM allocation); activations and gradients are read and written after it.  pdl_wait() returns when the
+// previous kernel has completed and flushed, which (every kernel of this file waits before it finishes) orders the
+// whole chain.  launch_dependents right after the wait lets the NEXT kernel's prologue overlap this kernel's body.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------------------ CTA scaffolding
 // 256 threads: warps 0-3 are the ROW side (thread t == row t of the tile: A operands, LayerNorm moments), warps 4-7 the
@@ -385,6 +397,14 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad);
 
+    float buf[8][8];
+    const FastDiv fd(n_pad);
+    if (side == 1) {                     // first weight chunk: parameters only, may run ahead of the previous kernel
+        const int kw0 = min(kKC, (K0 + 15) & ~15);
+        w_chunk_load(buf, P.w, K0, n0, n_valid, n_pad, fd, 0, K0, kw0, P.wvec, t);
+    }
+    pdl_wait();
+
     // LayerNorm moments of the thread's four rows (row side; the column side is already fetching the first weight chunk):
     // shifted one-pass sums over the lane's pieces, then over the four lanes that share a row
     const RowMap rm(t);
@@ -430,9 +450,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
         }
     }
 
-    float buf[8][8];
     uint32_t phase = 0;
-    const FastDiv fd(n_pad);
     auto chunk_load = [&](int i) {
         const int seg = i >= nc0;
         const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
@@ -440,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
         if (side == 0) row_chunk_load(seg ? P.a2 : P.a, rm, row0, P.B, k0, kw, buf);
         else w_chunk_load(buf, seg ? P.w2 : P.w, K, n0, n_valid, n_pad, fd, k0, K, kw, seg ? P.wvec2 : P.wvec, t);
     };
-    chunk_load(0);
+    if (side == 0) chunk_load(0);
     for (int i = 0; i < nchunk; ++i) {
         const int seg = i >= nc0;
         const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
@@ -603,7 +621,9 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
         if (side == 0) row_chunk_load(DY, rm, row0, P.B, n0, kw, buf);
         else wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 0);
     };
-    chunk_load(0);
+    if (side == 1) chunk_load(0);        // weights only: may run ahead of the previous kernel
+    pdl_wait();
+    if (side == 0) chunk_load(0);
     for (int i = 0; i < nchunk; ++i) {
         const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
         if (i > 0) wait_consumed(S, phase);
@@ -830,6 +850,7 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)bcols_pad);
 
+    pdl_wait();                          // both operands are activations / gradients of earlier kernels
     float buf[8][8];
     uint32_t phase = 0;
     const FastDiv fd_n(n_valid), fd_k(kcols), fd_x(max(bcols_pad - kcols, 1));
@@ -1003,6 +1024,23 @@ static inline bool mat_ok(const diffsg_mat& m) { return m.p0 && m.k0 > 0 && m.k1
 using namespace diffsg;
 using namespace diffsg::ttc;
 
+// launch with programmatic stream serialization (see pdl_wait); DIFFSG_NO_PDL=1 falls back to a plain launch
+template <typename Args>
+static cudaError_t launch_pdl(void (*kernel)(Args), dim3 grid, size_t smem, cudaStream_t st, const Args& P) {
+    static const bool no_pdl = [] { const char* e = getenv("DIFFSG_NO_PDL"); return e && e[0] == '1'; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, P);
+}
+
 // opt-in dynamic shared memory, once per (kernel, device)
 static int set_smem(const void* fn, size_t bytes, int which) {
     static bool done[3][64] = {};
@@ -1042,9 +1080,8 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     if (tile > smem) smem = tile;
     if (int rc = set_smem((const void*)tlin_fwd_kernel, (size_t)kRows * (128 + kTilePad) * sizeof(float), 0)) return rc;
     const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->N + 127) / 128));
-    tlin_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+    DIFFSG_CUDA_OK(launch_pdl(tlin_fwd_kernel, grid, smem, (cudaStream_t)stream, P));
     count_launch();
-    DIFFSG_CUDA_OK(cudaGetLastError());
     return DIFFSG_OK;
 }
 
@@ -1139,9 +1176,8 @@ int diffsg_tlin_backward(const diffsg_tlin_dgrad_args* dgrads, int32_t n_dgrad, 
     }
     if (total == 0) return DIFFSG_OK;
     if (int rc = set_smem((const void*)tlin_bwd_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 1)) return rc;
-    tlin_bwd_kernel<<<(unsigned)total, kThreads, smem, (cudaStream_t)stream>>>(P);
+    DIFFSG_CUDA_OK(launch_pdl(tlin_bwd_kernel, dim3((unsigned)total), smem, (cudaStream_t)stream, P));
     count_launch();
-    DIFFSG_CUDA_OK(cudaGetLastError());
     return DIFFSG_OK;
 }
 
