@@ -71,9 +71,10 @@ __device__ __forceinline__ void store_split(uint8_t* hi_base, uint32_t lo_delta,
 }
 
 // 8 consecutive columns [c, c + 8) of one row; columns beyond the matrix read as 0
+template <bool kV>
 __device__ __forceinline__ void load8(const Mat& m, int64_t row, int c, float (&v)[8]) {
     const int K = m.k0 + m.k1;
-    if (m.vec) {
+    if (kV || m.vec) {
         if (c >= K) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -94,9 +95,10 @@ __device__ __forceinline__ void load8(const Mat& m, int64_t row, int c, float (&
 __device__ __forceinline__ float load1(const Mat& m, int64_t row, int c) {
     return c < m.k0 ? __ldg(m.p0 + row * m.k0 + c) : __ldg(m.p1 + row * m.k1 + (c - m.k0));
 }
+template <bool kV>
 __device__ __forceinline__ void store8(const MatOut& m, int64_t row, int c, const float (&v)[8]) {
     const int K = m.k0 + m.k1;
-    if (m.vec) {
+    if (kV || m.vec) {
         if (c >= K) return;
         float* p = c < m.k0 ? m.p0 + row * m.k0 + c : m.p1 + row * m.k1 + (c - m.k0);
         reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -245,6 +247,7 @@ struct RowMap {
     __device__ __forceinline__ int row(int u) const { return wbase + 8 * (u >> 1) + r_in; }      // row inside the tile
     __device__ __forceinline__ int piece(int u) const { return pq + 4 * (u & 1); }
 };
+template <bool kV>
 __device__ __forceinline__ void row_chunk_load(const Mat& A, const RowMap& rm, int64_t row0, int64_t B, int k0, int kw, float (&v)[8][8]) {
     const int pieces = kw >> 3, K = A.k0 + A.k1;
 #pragma unroll
@@ -252,7 +255,7 @@ __device__ __forceinline__ void row_chunk_load(const Mat& A, const RowMap& rm, i
         const int64_t row = row0 + rm.row(u);
         const int pc = rm.piece(u), c = k0 + pc * 8;
         const bool ok = pc < pieces && row < B;
-        if (A.vec) {
+        if (kV || A.vec) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             if (ok && c < K) {
                 const float4* p = reinterpret_cast<const float4*>(c < A.k0 ? A.p0 + row * A.k0 + c : A.p1 + row * A.k1 + (c - A.k0));
@@ -263,7 +266,7 @@ __device__ __forceinline__ void row_chunk_load(const Mat& A, const RowMap& rm, i
         } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
-            if (ok) load8(A, row, c, v[u]);
+            if (ok) load8<kV>(A, row, c, v[u]);
         }
     }
 }
@@ -319,6 +322,7 @@ __device__ __forceinline__ void tmem_rows_to_tile(float* tile, int ld, uint32_t 
 // ---- column side, operand whose contraction dimension is contiguous in memory: src[mn][k] with row stride ld (the
 // weights [N, K] of the forward).  Items (mn, 8-column piece), mn fastest across lanes (16-byte conflict-free shared
 // stores), <= 8 items per thread.
+template <bool kV>
 __device__ __forceinline__ void w_chunk_load(float (&v)[8][8], const float* __restrict__ w, int ld, int n0, int n_valid, int n_pad,
                                              const FastDiv& fd, int k0, int K, int kw, bool vec, int t) {
     const int total = n_pad * (kw >> 3);
@@ -329,7 +333,7 @@ __device__ __forceinline__ void w_chunk_load(float (&v)[8][8], const float* __re
         fd.divmod(it, j, n);
         const int c = k0 + j * 8;
         const bool ok = it < total && n < n_valid && c < K;
-        if (vec) {
+        if (kV || vec) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             if (ok) {
                 const float4* p = reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * ld + c);
@@ -375,6 +379,7 @@ struct FwdArgs {
     int N, n_pad, tmem_cols, wvec, wvec2, yvec;
 };
 
+template <bool kV>
 __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ Smem S;
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     const FastDiv fd(n_pad);
     if (side == 1) {                     // first weight chunk: parameters only, may run ahead of the previous kernel
         const int kw0 = min(kKC, (K0 + 15) & ~15);
-        w_chunk_load(buf, P.w, K0, n0, n_valid, n_pad, fd, 0, K0, kw0, P.wvec, t);
+        w_chunk_load<kV>(buf, P.w, K0, n0, n_valid, n_pad, fd, 0, K0, kw0, P.wvec, t);
     }
     pdl_wait();
 
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
                 const int64_t r = row0 + rm.row(2 * g);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[g][j] = 0.f;
-                if (r < P.B) load8(P.a, r, c, v[g]);                       // columns >= K read as 0
+                if (r < P.B) load8<kV>(P.a, r, c, v[g]);                       // columns >= K read as 0
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g)
@@ -455,8 +460,8 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
         const int seg = i >= nc0;
         const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
         const int kw = min(kKC, (K - k0 + 15) & ~15);
-        if (side == 0) row_chunk_load(seg ? P.a2 : P.a, rm, row0, P.B, k0, kw, buf);
-        else w_chunk_load(buf, seg ? P.w2 : P.w, K, n0, n_valid, n_pad, fd, k0, K, kw, seg ? P.wvec2 : P.wvec, t);
+        if (side == 0) row_chunk_load<kV>(seg ? P.a2 : P.a, rm, row0, P.B, k0, kw, buf);
+        else w_chunk_load<kV>(buf, seg ? P.w2 : P.w, K, n0, n_valid, n_pad, fd, k0, K, kw, seg ? P.wvec2 : P.wvec, t);
     };
     if (side == 0) chunk_load(0);
     for (int i = 0; i < nchunk; ++i) {
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     const int ld = n_pad + kTilePad;
     tmem_rows_to_tile(tile, ld, d_tmem, warp, side, t, 0, n_pad / 16);
     __syncthreads();
-    if (P.yvec) {
+    if (kV || P.yvec) {
         const int nc4 = n_valid >> 2;                       // N % 4 == 0
         const FastDiv f4(nc4);
         const int total = kRows * nc4;
@@ -583,6 +588,7 @@ __device__ __forceinline__ void wt_items_store(float (&v)[8][8], uint8_t* b_hi, 
     }
 }
 
+template <bool kV>
 __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw, Smem& S, int bx, int by) {
     __shared__ float s_gamma[256], s_beta[256], s_dg[256], s_db[256], s_p1[2][kRows], s_p2[2][kRows];
     uint8_t* a_hi = smem_raw;
@@ -618,7 +624,7 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
     uint32_t phase = 0;
     auto chunk_load = [&](int i) {
         const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
-        if (side == 0) row_chunk_load(DY, rm, row0, P.B, n0, kw, buf);
+        if (side == 0) row_chunk_load<kV>(DY, rm, row0, P.B, n0, kw, buf);
         else wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 0);
     };
     if (side == 1) chunk_load(0);        // weights only: may run ahead of the previous kernel
@@ -649,7 +655,7 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
         const int ld = k_pad + kTilePad;
         tmem_rows_to_tile(tile, ld, d_tmem, warp, side, t, 0, ngroups);
         __syncthreads();
-        if (P.dx.vec && (!P.dres.p0 || P.dres.vec)) {
+        if (kV || (P.dx.vec && (!P.dres.p0 || P.dres.vec))) {
             const int nc4 = k_valid >> 2;
             const FastDiv f4(nc4);
             const int total = kRows * nc4;
@@ -710,7 +716,7 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
             for (int h = 0; h < 4; ++h) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) x[h][q] = 0.f;
-                if (valid && (h < 2 || two)) load8(P.x, row, g * 16 + h * 8, x[h]);
+                if (valid && (h < 2 || two)) load8<kV>(P.x, row, g * 16 + h * 8, x[h]);
             }
             float v[2][16];
             tmem_ld16(t_row + g * 16, v[0]);
@@ -754,8 +760,8 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { x[h][q] = 0.f; o[h][q] = 0.f; }
                 if (valid && (h < 2 || two)) {
-                    load8(P.x, row, g * 16 + h * 8, x[h]);
-                    if (P.dres.p0) load8(P.dres, row, g * 16 + h * 8, o[h]);
+                    load8<kV>(P.x, row, g * 16 + h * 8, x[h]);
+                    if (P.dres.p0) load8<kV>(P.dres, row, g * 16 + h * 8, o[h]);
                 }
             }
             float v[2][16];
@@ -776,7 +782,7 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
                     const float dxh = v[h >> 1][(h & 1) * 8 + q] * (sg * fmaf(n, 1.0f - sg, 1.0f)) * gm;
                     o[h][q] += rs * (dxh - m1 - xh * m2);
                 }
-                store8(P.dx, row, c, o[h]);
+                store8<kV>(P.dx, row, c, o[h]);
             }
         }
         __syncthreads();
@@ -825,6 +831,7 @@ __device__ __forceinline__ void tr_items_load(float (&v)[8][8], const Mat& M, in
     }
 }
 
+template <bool kV>
 __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw, Smem& S, int bx, int by, int bz, int gx, int gz) {
     __shared__ float s_mu[2][kKC], s_rs[2][kKC];
     __shared__ int s_gi[2][kKC];
@@ -944,7 +951,7 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw
     const uint32_t t_row = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const bool has_n = n_loc < n_valid && it_no > 0;
     const int n = n0 + n_loc;
-    const bool v4 = P.dwvec != 0;
+    const bool v4 = kV || P.dwvec != 0;
     for (int g = side; g < bcols_pad / 16; g += 2) {
         float v[16];
         tmem_ld16(t_row + g * 16, v);
@@ -980,6 +987,7 @@ struct BwdArgs {
     int w_cta[2], w_gx[2], w_gy[2], w_gz[2];
 };
 
+template <bool kV>
 __global__ void __launch_bounds__(kThreads, 2) tlin_bwd_kernel(const __grid_constant__ BwdArgs P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ Smem S;
@@ -987,14 +995,14 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_bwd_kernel(const __grid_cons
     for (int j = 0; j < P.nw; ++j) {
         if (b < P.w_cta[j]) {
             const int gx = P.w_gx[j], gy = P.w_gy[j];
-            wgrad_body(P.w[j], smem_raw, S, b % gx, (b / gx) % gy, b / (gx * gy), gx, P.w_gz[j]);
+            wgrad_body<kV>(P.w[j], smem_raw, S, b % gx, (b / gx) % gy, b / (gx * gy), gx, P.w_gz[j]);
             return;
         }
         b -= P.w_cta[j];
     }
     for (int j = 0; j < P.nd; ++j) {
         if (b < P.d_cta[j]) {
-            dgrad_body(P.d[j], smem_raw, S, b / P.d_gy[j], b % P.d_gy[j]);
+            dgrad_body<kV>(P.d[j], smem_raw, S, b / P.d_gy[j], b % P.d_gy[j]);
             return;
         }
         b -= P.d_cta[j];
@@ -1043,7 +1051,7 @@ static cudaError_t launch_pdl(void (*kernel)(Args), dim3 grid, size_t smem, cuda
 
 // opt-in dynamic shared memory, once per (kernel, device)
 static int set_smem(const void* fn, size_t bytes, int which) {
-    static bool done[3][64] = {};
+    static bool done[4][64] = {};
     int dev = 0;
     DIFFSG_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && done[which][dev]) return DIFFSG_OK;
@@ -1078,9 +1086,12 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.n_pad * kKC * 2;
     const size_t tile = (size_t)kRows * (P.n_pad + kTilePad) * sizeof(float);        // epilogue tile shares the operand buffers
     if (tile > smem) smem = tile;
-    if (int rc = set_smem((const void*)tlin_fwd_kernel, (size_t)kRows * (128 + kTilePad) * sizeof(float), 0)) return rc;
+    // fast variant: every operand 8-column / 16-byte aligned (the generic paths compiled out: half the instructions)
+    const bool all_vec = P.a.vec && P.wvec && P.yvec && (!seg2 || (P.a2.vec && P.wvec2));
+    if (int rc = set_smem(all_vec ? (const void*)tlin_fwd_kernel<true> : (const void*)tlin_fwd_kernel<false>,
+                          (size_t)kRows * (128 + kTilePad) * sizeof(float), all_vec ? 0 : 1)) return rc;
     const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->N + 127) / 128));
-    DIFFSG_CUDA_OK(launch_pdl(tlin_fwd_kernel, grid, smem, (cudaStream_t)stream, P));
+    DIFFSG_CUDA_OK(launch_pdl(all_vec ? tlin_fwd_kernel<true> : tlin_fwd_kernel<false>, grid, smem, (cudaStream_t)stream, P));
     count_launch();
     return DIFFSG_OK;
 }
@@ -1175,8 +1186,22 @@ int diffsg_tlin_backward(const diffsg_tlin_dgrad_args* dgrads, int32_t n_dgrad, 
         ++P.nd;
     }
     if (total == 0) return DIFFSG_OK;
-    if (int rc = set_smem((const void*)tlin_bwd_kernel, 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, 1)) return rc;
-    DIFFSG_CUDA_OK(launch_pdl(tlin_bwd_kernel, dim3((unsigned)total), smem, (cudaStream_t)stream, P));
+    // Several waves of CTAs: the roles gain nothing from sharing a launch and each runs better alone (one role's
+    // instruction stream per launch; the kernel is far larger than the instruction cache)
+    if (total > 4 * 296 && P.nw + P.nd > 1) {
+        for (int j = 0; j < n_wgrad; ++j)
+            if (int rc = diffsg_tlin_backward(nullptr, 0, &wgrads[j], 1, stream)) return rc;
+        for (int j = 0; j < n_dgrad; ++j)
+            if (int rc = diffsg_tlin_backward(&dgrads[j], 1, nullptr, 0, stream)) return rc;
+        return DIFFSG_OK;
+    }
+    bool all_vec = true;
+    for (int j = 0; j < P.nw; ++j) all_vec = all_vec && P.w[j].dwvec && P.w[j].a.vec && (P.w[j].N % 8 == 0) && aligned16(P.w[j].dy);
+    for (int j = 0; j < P.nd; ++j)
+        all_vec = all_vec && P.d[j].dyvec && P.d[j].dx.vec && (!P.d[j].dres.p0 || P.d[j].dres.vec) && (!P.d[j].gamma || P.d[j].x.vec);
+    if (int rc = set_smem(all_vec ? (const void*)tlin_bwd_kernel<true> : (const void*)tlin_bwd_kernel<false>,
+                          2 * (size_t)kRows * kKC * 2 + 2 * (size_t)256 * kKC * 2, all_vec ? 2 : 3)) return rc;
+    DIFFSG_CUDA_OK(launch_pdl(all_vec ? tlin_bwd_kernel<true> : tlin_bwd_kernel<false>, dim3((unsigned)total), smem, (cudaStream_t)stream, P));
     count_launch();
     return DIFFSG_OK;
 }
