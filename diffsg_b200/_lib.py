@@ -69,7 +69,7 @@ class TlinFwdArgs(C.Structure):
     _fields_ = [("a", Mat), ("w", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("a2", Mat), ("w2", C.c_void_p), ("bias2", C.c_void_p),
                 ("add", C.c_void_p), ("gadd", C.c_void_p), ("gidx", C.c_void_p), ("y", C.c_void_p), ("B", C.c_int64),
-                ("N", C.c_int32), ("reserved", C.c_int32)]
+                ("N", C.c_int32), ("gadd_ld", C.c_int32)]
 
 
 class TlinDgradArgs(C.Structure):
@@ -81,7 +81,8 @@ class TlinDgradArgs(C.Structure):
 class TlinWgradArgs(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("a", Mat), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
                 ("rstd", C.c_void_p), ("gidx", C.c_void_p), ("dw", C.c_void_p), ("dbias", C.c_void_p),
-                ("dgadd", C.c_void_p), ("B", C.c_int64), ("N", C.c_int32), ("gadd_rows", C.c_int32)]
+                ("dgadd", C.c_void_p), ("B", C.c_int64), ("N", C.c_int32), ("gadd_rows", C.c_int32), ("dgadd_ld", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/diffsg_b200.h declares

@@ -376,7 +376,7 @@ struct FwdArgs {
     const int64_t* gidx;
     float* y;
     int64_t B;
-    int N, n_pad, tmem_cols, wvec, wvec2, yvec;
+    int N, n_pad, tmem_cols, wvec, wvec2, yvec, gadd_ld;
 };
 
 template <bool kV>
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
                     if (P.bias2) { const float4 x = __ldg(reinterpret_cast<const float4*>(P.bias2 + c)); e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w; }
                     if (P.add) { const float4 x = __ldg(reinterpret_cast<const float4*>(P.add + grow_ * P.N + c)); e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w; }
                     if (P.gadd) {
-                        const float4 x = __ldg(reinterpret_cast<const float4*>(P.gadd + P.gidx[grow_] * P.N + c));
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(P.gadd + P.gidx[grow_] * P.gadd_ld + c));
                         e.x += x.x; e.y += x.y; e.z += x.z; e.w += x.w;
                     }
                 }
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
             if (P.bias) e += __ldg(P.bias + c);
             if (P.bias2) e += __ldg(P.bias2 + c);
             if (P.add) e += __ldg(P.add + grow_ * P.N + c);
-            if (P.gadd) e += __ldg(P.gadd + P.gidx[grow_] * P.N + c);
+            if (P.gadd) e += __ldg(P.gadd + P.gidx[grow_] * P.gadd_ld + c);
             P.y[grow_ * P.N + c] = e;
         }
     }
@@ -807,7 +807,7 @@ struct WgradArgs {
     float* dbias;          // [N]     +=   (nullable)
     float* dgadd;          // [T, N]  +=   (nullable)
     int64_t B;
-    int N, K, T, n_chunks, tmem_cols, bcols_pad, dwvec;
+    int N, K, T, n_chunks, tmem_cols, bcols_pad, dwvec, dgadd_ld;
 };
 
 // transposed operand items: (mn = feature, kk = row); lanes along the feature (contiguous in memory), 8 rows per item;
@@ -968,7 +968,7 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw
                     const int cc = c + q;
                     if (cc < kcols) red_add(P.dw + (size_t)n * P.K + kb + cc, v[q4 * 4 + q]);
                     else if (cc == one_col) red_add(P.dbias + n, v[q4 * 4 + q]);
-                    else if (hot0 >= 0 && cc >= hot0 && cc < hot0 + P.T) red_add(P.dgadd + (size_t)(cc - hot0) * P.N + n, v[q4 * 4 + q]);
+                    else if (hot0 >= 0 && cc >= hot0 && cc < hot0 + P.T) red_add(P.dgadd + (size_t)(cc - hot0) * P.dgadd_ld + n, v[q4 * 4 + q]);
                 }
             }
         }
@@ -1077,12 +1077,13 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     if (seg2) P.a2 = to_mat(a->a2); else P.a2 = Mat{nullptr, nullptr, 0, 0, 0};
     P.w2 = a->w2; P.bias2 = seg2 ? a->bias2 : nullptr;
     P.add = a->add; P.gadd = a->gadd; P.gidx = a->gidx; P.y = a->y; P.B = a->B; P.N = a->N;
+    P.gadd_ld = a->gadd_ld > 0 ? a->gadd_ld : a->N;
     P.n_pad = a->N >= 128 ? 128 : ((a->N + 15) & ~15);
     P.tmem_cols = (int)pow2_cols(P.n_pad);
     const int K = P.a.k0 + P.a.k1;
     P.wvec = (K % 8 == 0) && aligned16(a->w);
     P.wvec2 = seg2 && ((P.a2.k0 + P.a2.k1) % 8 == 0) && aligned16(a->w2);
-    P.yvec = (a->N % 4 == 0) && aligned16(a->y) && aligned16(a->add) && aligned16(a->gadd) && aligned16(a->bias) && aligned16(P.bias2);
+    P.yvec = (a->N % 4 == 0) && aligned16(a->y) && aligned16(a->add) && aligned16(a->gadd) && (P.gadd_ld % 4 == 0) && aligned16(a->bias) && aligned16(P.bias2);
     size_t smem = 2 * (size_t)kRows * kKC * 2 + 2 * (size_t)P.n_pad * kKC * 2;
     const size_t tile = (size_t)kRows * (P.n_pad + kTilePad) * sizeof(float);        // epilogue tile shares the operand buffers
     if (tile > smem) smem = tile;
@@ -1139,6 +1140,7 @@ static int prep_wgrad(const diffsg_tlin_wgrad_args* a, WgradArgs& P, int& gx, in
     P.dy = a->dy; P.a = to_mat(a->a); P.gamma = a->gamma; P.beta = a->beta; P.mean = a->mean; P.rstd = a->rstd;
     P.gidx = a->gidx; P.dw = a->dw; P.dbias = a->dbias; P.dgadd = a->dgadd; P.B = a->B; P.N = a->N;
     P.K = P.a.k0 + P.a.k1; P.T = a->dgadd ? a->gadd_rows : 0;
+    P.dgadd_ld = a->dgadd_ld > 0 ? a->dgadd_ld : a->N;
     P.n_chunks = (int)((a->B + kKC - 1) / kKC);
     gz = (P.K + kWgradKT - 1) / kWgradKT;
     gy = (a->N + 127) / 128;

@@ -65,11 +65,14 @@ class _FusedLinear(torch.autograd.Function):
     act = swish(LayerNorm(.; gamma, beta)) when gamma is given, identity otherwise."""
 
     @staticmethod
-    def forward(ctx, x0, x1, gamma, beta, w, b, z0, z1, w2, b2, add, gadd, gidx):
+    def forward(ctx, x0, x1, gamma, beta, w, b, z0, z1, w2, b2, add, gadd, gidx, table=None):
+        """`table = (column, holder)`: `gadd` is a wide [T, W] table (every block's time term, `time_table`) and this node
+        adds its columns [column, column + N); the gradient goes straight into the same columns of `holder`'s buffer."""
         lib = _lib.load()
         if not x0.is_cuda:
             raise _lib.DiffsgError("diffsg_b200 training runs on CUDA only (no CPU implementation)")
         x0, x1, z0, z1, add, gadd = (_prep(t) for t in (x0, x1, z0, z1, add, gadd))
+        col, holder = table if table is not None else (0, None)
         B, N = x0.shape[0], w.shape[0]
         K = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
         assert w.shape[1] == K and w.is_contiguous() and (b is None or b.is_contiguous())
@@ -83,12 +86,14 @@ class _FusedLinear(torch.autograd.Function):
             assert gidx.dtype == torch.int64 and gidx.numel() == B
         a = _lib.TlinFwdArgs(a=_mat(x0, x1), w=w.data_ptr(), bias=_ptr(b), gamma=_ptr(gamma), beta=_ptr(beta),
                              mean=_ptr(mean), rstd=_ptr(rstd), a2=_mat(z0, z1), w2=_ptr(w2), bias2=_ptr(b2),
-                             add=_ptr(add), gadd=_ptr(gadd), gidx=_ptr(gidx), y=y.data_ptr(), B=B, N=N)
+                             add=_ptr(add), gadd=None if gadd is None else gadd.data_ptr() + 4 * col, gidx=_ptr(gidx),
+                             y=y.data_ptr(), B=B, N=N, gadd_ld=0 if gadd is None else gadd.shape[1])
         with torch.cuda.device(x0.device):
             _lib.check(lib.diffsg_tlin_forward(C.byref(a), _lib.stream_ptr()), "diffsg_tlin_forward")
         ctx.save_for_backward(x0, x1, z0, z1, mean, rstd, gidx)
         ctx.params = (gamma, beta, w, b, w2, b2)
         ctx.gadd_rows = 0 if gadd is None else gadd.shape[0]
+        ctx.table = None if holder is None else (col, holder, gadd.shape[1], holder.claim())
         return y
 
     @staticmethod
@@ -100,7 +105,7 @@ class _FusedLinear(torch.autograd.Function):
         dy = _prep(dy)
         B, N = dy.shape
         dev = dy.device
-        out = [None] * 13
+        out = [None] * 14
 
         def target(i, p):
             if p is None or not need[i]:
@@ -113,18 +118,25 @@ class _FusedLinear(torch.autograd.Function):
         keep = []                                            # temporaries the kernels write into: alive until the launch
         # ---- wgrad of the main segment (+ bias gradient, + scatter of the gathered add)
         dw, db = target(4, w), target(5, b)
-        dgadd = None
+        dgadd, dgadd_ptr, dgadd_ld = None, None, 0
         if need[11] and ctx.gadd_rows:
-            dgadd = torch.zeros(ctx.gadd_rows, N, dtype=torch.float32, device=dev)
-            out[11] = dgadd
+            if ctx.table is not None:
+                col, holder, width, returns_it = ctx.table
+                dgadd = holder.buffer(ctx.gadd_rows, width, dev)
+                dgadd_ptr, dgadd_ld = dgadd.data_ptr() + 4 * col, width
+                out[11] = dgadd if returns_it else None      # the first consumer (last in backward) hands the table back
+            else:
+                dgadd = torch.zeros(ctx.gadd_rows, N, dtype=torch.float32, device=dev)
+                dgadd_ptr = dgadd.data_ptr()
+                out[11] = dgadd
         if dw is not None or db is not None or dgadd is not None:
             if dw is None:                                   # frozen weight: the kernel still needs a target
                 dw = torch.zeros_like(w)
                 keep.append(dw)
             wg.append(_lib.TlinWgradArgs(dy=dy.data_ptr(), a=_mat(x0, x1), gamma=_ptr(gamma), beta=_ptr(beta),
                                          mean=_ptr(mean), rstd=_ptr(rstd), gidx=_ptr(gidx) if dgadd is not None else None,
-                                         dw=dw.data_ptr(), dbias=_ptr(db), dgadd=_ptr(dgadd), B=B, N=N,
-                                         gadd_rows=ctx.gadd_rows if dgadd is not None else 0))
+                                         dw=dw.data_ptr(), dbias=_ptr(db), dgadd=dgadd_ptr, B=B, N=N,
+                                         gadd_rows=ctx.gadd_rows if dgadd is not None else 0, dgadd_ld=dgadd_ld))
         # ---- wgrad of the second (identity) segment
         if w2 is not None:
             dw2, db2 = target(8, w2), target(9, b2)
@@ -169,7 +181,62 @@ class _FusedLinear(torch.autograd.Function):
         return tuple(out)
 
 
-def fused_linear(x0, lin, x1=None, norm=None, seg2=None, add=None, gadd=None, gidx=None, weight=None, bias=None):
+class _TableGrad:
+    """Gradient of a time table: ONE zero-initialised [T, W] buffer that every consumer's wgrad adds its columns into.
+    The consumer created first runs last in the backward (each block's gradient depends on all later blocks), so it is
+    the one that returns the finished buffer to autograd; the others return None."""
+
+    def __init__(self):
+        self._buf = None
+        self._claimed = False
+
+    def claim(self):
+        first, self._claimed = not self._claimed, True
+        return first
+
+    def buffer(self, rows, width, device):
+        if self._buf is None:
+            self._buf = torch.zeros(rows, width, dtype=torch.float32, device=device)
+        return self._buf
+
+
+class _CatParams(torch.autograd.Function):
+    """torch.cat(parameters, 0) whose backward adds the slices straight into the parameters' .grad (one multi-tensor add)."""
+
+    @staticmethod
+    def forward(ctx, *ps):
+        ctx.ps = ps
+        return torch.cat(ps, 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        parts = g.split([p.shape[0] for p in ctx.ps], 0)
+        outs, tgt, src = [], [], []
+        for p, part, need in zip(ctx.ps, parts, ctx.needs_input_grad):
+            if need and p.is_leaf:
+                tgt.append(_grad_target(p)[0])
+                src.append(part)
+                outs.append(None)
+            else:
+                outs.append(part if need else None)
+        if tgt:
+            torch._foreach_add_(tgt, src)
+        return tuple(outs)
+
+
+def time_table(temb_act, blocks):
+    """Every block's `time_emb` Linear of the (hoisted) time rows as ONE node: [T, 4P] x cat(W_i)^T -> [T, sum N_i].
+    Returns (table, column offsets, gradient holder)."""
+    w = _CatParams.apply(*[b.time_emb.weight for b in blocks])
+    bias = _CatParams.apply(*[b.time_emb.bias for b in blocks])
+    cols, c = [], 0
+    for b in blocks:
+        cols.append(c)
+        c += b.time_emb.weight.shape[0]
+    return fused_linear(temb_act, None, weight=w, bias=bias), cols, _TableGrad()
+
+
+def fused_linear(x0, lin, x1=None, norm=None, seg2=None, add=None, gadd=None, gidx=None, weight=None, bias=None, table=None):
     """One fused node.  `lin` (nn.Linear) or explicit (`weight`, `bias`); `norm` (nn.LayerNorm) puts
     LayerNorm -> Swish in front; `seg2 = (z0, z1, lin2)` accumulates a second Linear of another input."""
     w = lin.weight if weight is None else weight
@@ -179,7 +246,7 @@ def fused_linear(x0, lin, x1=None, norm=None, seg2=None, add=None, gadd=None, gi
         z0, z1, l2 = seg2
         w2, b2 = l2.weight, l2.bias
     return _FusedLinear.apply(x0, x1, None if norm is None else norm.weight, None if norm is None else norm.bias,
-                              w, b, z0, z1, w2, b2, add, gadd, gidx)
+                              w, b, z0, z1, w2, b2, add, gadd, gidx, table)
 
 
 def ln_swish_linear(x, norm, lin):
@@ -187,13 +254,16 @@ def ln_swish_linear(x, norm, lin):
     return fused_linear(x, lin, norm=norm)
 
 
-def _res(blk, x0, x1, temb_act, cond_act, gidx):
-    """ResidualBlock (UNetCF.py:83-95) as three fused nodes (+ the block's time-embedding Linear on the time rows)."""
-    tb = fused_linear(temb_act, blk.time_emb)
-    if gidx is not None:
-        h = fused_linear(x0, blk.lin1, x1=x1, norm=blk.norm1, gadd=tb, gidx=gidx)
+def _res(blk, x0, x1, temb_act, cond_act, gidx, tt=None):
+    """ResidualBlock (UNetCF.py:83-95) as three fused nodes.  The time term comes from the shared time table `tt`
+    (gather mode) or from the block's own time-embedding node."""
+    if tt is not None:
+        table, cols, holder = tt
+        h = fused_linear(x0, blk.lin1, x1=x1, norm=blk.norm1, gadd=table, gidx=gidx, table=(cols[id(blk)], holder))
+    elif gidx is not None:
+        h = fused_linear(x0, blk.lin1, x1=x1, norm=blk.norm1, gadd=fused_linear(temb_act, blk.time_emb), gidx=gidx)
     else:
-        h = fused_linear(x0, blk.lin1, x1=x1, norm=blk.norm1, add=tb)
+        h = fused_linear(x0, blk.lin1, x1=x1, norm=blk.norm1, add=fused_linear(temb_act, blk.time_emb))
     h = fused_linear(h, blk.lin2, norm=blk.norm2, seg2=(cond_act, None, blk.cond_emb))
     if isinstance(blk.shortcut, torch.nn.Linear):
         return fused_linear(h, blk.lin3, norm=blk.norm3, seg2=(x0, x1, blk.shortcut))
@@ -234,20 +304,28 @@ def unet_forward_train(model, x, t, cond, cond_mask, t_index=None, n_steps=None)
         temb, gidx = torch.index_select(temb, 0, gidx), None          # long schedules: gather once, add row by row
     temb_act = F.silu(temb)
     cond_act = F.silu(cond.to(torch.float32).reshape(B, -1) * cond_mask.to(torch.float32).reshape(-1, 1))
+    tt = None
+    if gidx is not None:
+        # gather mode: all blocks' time-embedding Linears as one [T, 4P] x [4P, sum N] node, forward and backward
+        blocks = ([m.res for m in model.down if isinstance(m, DownBlock)] + [model.middle.res1, model.middle.res2]
+                  + [m.res for m in model.up if isinstance(m, UpBlock)])
+        if all(p.is_leaf for b in blocks for p in b.time_emb.parameters()):
+            table, cols, holder = time_table(temb_act, blocks)
+            tt = (table, {id(b): c for b, c in zip(blocks, cols)}, holder)
     h = fused_linear(x, model.feature_proj)
     skips = [h]
     for m in model.down:
         if isinstance(m, DownBlock):
-            h = _attn(m.attn, _res(m.res, h, None, temb_act, cond_act, gidx))
+            h = _attn(m.attn, _res(m.res, h, None, temb_act, cond_act, gidx, tt))
         else:
             h = fused_linear(h, m.lin)
         skips.append(h)
-    h = _res(model.middle.res1, h, None, temb_act, cond_act, gidx)
+    h = _res(model.middle.res1, h, None, temb_act, cond_act, gidx, tt)
     h = _attn(model.middle.attn, h)
-    h = _res(model.middle.res2, h, None, temb_act, cond_act, gidx)
+    h = _res(model.middle.res2, h, None, temb_act, cond_act, gidx, tt)
     for m in model.up:
         if isinstance(m, UpBlock):
-            h = _attn(m.attn, _res(m.res, h, skips.pop(), temb_act, cond_act, gidx))      # cat(h, skip) is never formed
+            h = _attn(m.attn, _res(m.res, h, skips.pop(), temb_act, cond_act, gidx, tt))      # cat(h, skip) is never formed
         else:
             h = fused_linear(h, m.lin)
     return fused_linear(h, model.final, norm=model.norm)

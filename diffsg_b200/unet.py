@@ -202,9 +202,8 @@ def _forward_steps(self, x, ts, n_steps, cond, cond_mask):
     needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
     if needs_grad and x.is_cuda:
         from .train import unet_forward_train
-        if x.shape[0] >= 1024:    # below that the step is launch-bound and the 2 x 27 gather / scatter kernels cost more
-            return unet_forward_train(self, x, None, cond, cond_mask, t_index=ts, n_steps=n_steps)
-        return unet_forward_train(self, x, ts / n_steps, cond, cond_mask)
+        # the gather of the row's time term is fused into the forward epilogue and its scatter into wgrad: always hoist
+        return unet_forward_train(self, x, None, cond, cond_mask, t_index=ts, n_steps=n_steps)
     if x.is_cuda:
         return self.engine().forward(x, None, cond, cond_mask, t_index=ts, n_steps=n_steps)   # cached step table, no host sync
     return unet_forward(self, x, ts / n_steps, cond, cond_mask)

@@ -328,12 +328,12 @@ typedef struct diffsg_tlin_fwd_args {
     const float* w2;              /* [N, a2.k0 + a2.k1] */
     const float* bias2;
     const float* add;             /* [B, N] or NULL */
-    const float* gadd;            /* [T, N] or NULL: row gidx[row] is added to output row `row` */
+    const float* gadd;            /* [T, N] (row stride gadd_ld) or NULL: row gidx[row] is added to output row `row` */
     const int64_t* gidx;          /* [B] */
     float* y;                     /* [B, N] */
     int64_t B;
     int32_t N;
-    int32_t reserved;
+    int32_t gadd_ld;              /* row stride of gadd in floats; 0 = N (dense).  A column slice of a wider table is allowed */
 } diffsg_tlin_fwd_args;
 int diffsg_tlin_forward(const diffsg_tlin_fwd_args* args, void* stream);
 
@@ -359,7 +359,8 @@ typedef struct diffsg_tlin_dgrad_args {
 int diffsg_tlin_dgrad(const diffsg_tlin_dgrad_args* args, void* stream);
 
 /* dw[N, K] += dy^T . act(a);  dbias[N] += column sums of dy;  dgadd[T, N] += rows of dy scattered by gidx
- * (all three from one pass over the rows; dbias / dgadd optional, gadd_rows <= 31). */
+ * (all three from one pass over the rows; dbias / dgadd optional, gadd_rows <= 31; dgadd may be a column slice of a
+ * wider [T, dgadd_ld] table). */
 typedef struct diffsg_tlin_wgrad_args {
     const float* dy;
     diffsg_mat a;
@@ -374,6 +375,8 @@ typedef struct diffsg_tlin_wgrad_args {
     int64_t B;
     int32_t N;
     int32_t gadd_rows;
+    int32_t dgadd_ld;             /* row stride of dgadd in floats; 0 = N */
+    int32_t reserved;
 } diffsg_tlin_wgrad_args;
 int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* args, void* stream);
 
