@@ -68,6 +68,24 @@ def main():
             txt = (G / name).read_text()
             txt = "\n".join(l for l in txt.splitlines() if "Host Frame" not in l)[-20000:]
             (P / name.replace("r2_", "r02_")).write_text(txt + "\n")
+    # ---- tcgen05 training kernels (tools/train_profile.sh)
+    for kind in ("fwd", "bwd"):
+        rep = G / f"t_{kind}.ncu-rep"
+        if rep.exists():
+            (P / f"r02_ncu_full_tlin_{kind}_kernel.csv").write_text(ncu_csv(rep, "--page", "raw"))
+    lc = G / "t_launches.csv"
+    if lc.exists():
+        lines = [l for l in lc.read_text().splitlines() if l.startswith('"')]
+        (P / "r02_ncu_launches_train.csv").write_text("\n".join(lines) + "\n")
+    for tool in ("memcheck", "racecheck", "synccheck"):
+        f = G / f"t_{tool}_tlin.log"
+        if f.exists():
+            txt = "\n".join(l for l in f.read_text().splitlines() if "Host Frame" not in l)[-20000:]
+            (P / f"r02_{tool}_tlin.log").write_text(txt + "\n")
+    for b in (512, 65536):
+        f = G / f"timeline_{b}.txt"
+        if f.exists():
+            (P / f"r02_train_timeline_b{b}.txt").write_text("\n".join(l for l in f.read_text().splitlines() if "grid=" in l) + "\n")
     # SASS census of the library that ships
     so = ROOT / "diffsg_b200" / "libdiffsg_b200.so"
     if so.exists():
@@ -81,11 +99,11 @@ def main():
             m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
             if m and cur:
                 cnt[cur][m.group(1)] += 1
-        keys = ["UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "MUFU", "F2FP", "HADD2", "STS", "LDS", "LDG", "STG"]
+        keys = ["UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "MUFU", "F2FP", "HADD2", "STS", "LDS", "LDG", "STG", "RED", "ACQBULK"]
         out = ["# SASS census of diffsg_b200/libdiffsg_b200.so (cuobjdump -sass), tensor-core kernels",
                "", "| kernel | instructions | " + " | ".join(keys) + " |", "|---|---|" + "---|" * len(keys)]
         for fn, c in cnt.items():
-            if "tc_unet_kernel" in fn or "tc_gemm_test" in fn:
+            if "tc_unet_kernel" in fn or "tc_gemm_test" in fn or "tlin_" in fn:
                 out.append(f"| `{fn}` | {sum(c.values())} | " + " | ".join(str(c[k]) for k in keys) + " |")
         out += ["", "UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UBLKCP = cp.async.bulk (1-D TMA), SYNCS = mbarrier ops,",
                 "FFMA2 / FADD2 / FMUL2 = packed f32x2 arithmetic, MUFU = ex2 / rcp / tanh / rsqrt."]
