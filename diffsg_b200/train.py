@@ -47,7 +47,7 @@ def _prep(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _grad_target(p, like=None):
+def _grad_target(p):
     """Where a parameter gradient is accumulated: `p.grad` itself for a leaf (allocated as zeros on first use, returned
     to autograd as None), a fresh zero tensor that is handed back to autograd otherwise."""
     if p.is_leaf:
