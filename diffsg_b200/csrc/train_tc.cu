@@ -569,11 +569,12 @@ __device__ __forceinline__ void wt_items_load(float (&v)[8][8], const DgradArgs&
         const int it = t + (first + u) * kRows;
         int k, n8;
         fd.divmod(it, n8, k);
+        // one 64-bit base per item, 32-bit steps of K per n; rows of W beyond N / columns beyond K / items beyond the chunk: 0
+        const int nb = n0 + n8 * 8;
+        const int nv = (it < total && k < k_valid) ? min(P.N - nb, 8) : 0;
+        const float* base = P.w + (size_t)nb * P.K + kb + k;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int n = n0 + n8 * 8 + q;
-            v[u][q] = (it < total && k < k_valid && n < P.N) ? __ldg(P.w + (size_t)n * P.K + kb + k) : 0.f;
-        }
+        for (int q = 0; q < 8; ++q) v[u][q] = q < nv ? __ldg(base + q * P.K) : 0.f;
     }
 }
 __device__ __forceinline__ void wt_items_store(float (&v)[8][8], uint8_t* b_hi, uint32_t b_term, int k_pad, const FastDiv& fd, int kw,
@@ -815,19 +816,19 @@ struct WgradArgs {
 __device__ __forceinline__ void tr_items_load(float (&v)[8][8], const Mat& M, int f0, int nf, const FastDiv& fd, int64_t r0, int nr8,
                                               int64_t B, int t, int first) {
     const int total = nf * nr8;
+    const int rows_left = (int)min(B - r0, (int64_t)kKC);          // valid rows of this chunk
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const int it = t + (first + u) * kRows;
         int f, r8;
         fd.divmod(it, r8, f);
         f += f0;
-        const float* src = f < M.k0 ? M.p0 + f : M.p1 + (f - M.k0);
+        // one 64-bit base per item, 32-bit steps of the row stride; rows beyond B / items beyond the chunk: 0
         const int ld = f < M.k0 ? M.k0 : M.k1;
+        const float* base = (f < M.k0 ? M.p0 + f : M.p1 + (f - M.k0)) + (r0 + r8 * 8) * ld;
+        const int nv = it < total ? rows_left - r8 * 8 : 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int64_t r = r0 + r8 * 8 + q;
-            v[u][q] = (it < total && r < B) ? __ldg(src + r * ld) : 0.f;
-        }
+        for (int q = 0; q < 8; ++q) v[u][q] = q < nv ? __ldg(base + q * ld) : 0.f;
     }
 }
 
@@ -900,8 +901,77 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw
     };
 
     int it_no = 0;
-    if (bx < P.n_chunks) chunk_load(bx, 0);
-    for (int ch = bx; ch < P.n_chunks; ch += gx, ++it_no) {
+    // Many chunks per CTA (large batches): a ROLLED staging loop shared by all 256 threads.  The unrolled, prefetching
+    // path below is ~60 KB of straight-line code per chunk; looping over it thrashes the instruction cache
+    // (stall_no_instructions was 45-50 % of the samples), and with two CTAs x 8 warps per SM thread-level parallelism
+    // covers the load latency that the register prefetch hides for small problems.
+    const bool rolled = P.n_chunks > 2 * gx;
+    if (rolled) {
+        for (int ch = bx; ch < P.n_chunks; ch += gx, ++it_no) {
+            const int64_t r0 = (int64_t)ch * kKC;
+            const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
+            const int nr8 = kw >> 3;
+            const int rows_left = (int)min(P.B - r0, (int64_t)kKC);
+            if (it_no > 0) wait_consumed(S, phase);
+            if (tid < kKC) {
+                const int64_t r = r0 + tid;
+                const bool ok = r < P.B;
+                s_mu[0][tid] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
+                s_rs[0][tid] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
+                s_gi[0][tid] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int it = tid; it < n_valid * nr8; it += kThreads) {             // A operand = dy^T
+                int nn, r8;
+                fd_n.divmod(it, r8, nn);
+                const float* base = P.dy + (r0 + r8 * 8) * P.N + n0 + nn;
+                const int nv = rows_left - r8 * 8;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * P.N) : 0.f;
+                store_split(a_hi, a_term_bytes(), op_off(nn, r8 * 8), v);
+            }
+#pragma unroll 2
+            for (int it = tid; it < kcols * nr8; it += kThreads) {               // B operand, feature columns = act(a)^T
+                int c, r8;
+                fd_k.divmod(it, r8, c);
+                const int f = kb + c;
+                const int ld = f < P.a.k0 ? P.a.k0 : P.a.k1;
+                const float* base = (f < P.a.k0 ? P.a.p0 + f : P.a.p1 + (f - P.a.k0)) + (r0 + r8 * 8) * ld;
+                const int nv = rows_left - r8 * 8;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * ld) : 0.f;
+                if (ln) {
+                    const float gm = __ldg(P.gamma + f), bt = __ldg(P.beta + f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int rr = r8 * 8 + q;
+                        const float n = fmaf((v[q] - s_mu[0][rr]) * s_rs[0][rr], gm, bt);
+                        v[q] = n * sigmoidf_(n);
+                    }
+                }
+                store_split(b_hi, b_term, op_off(c, r8 * 8), v);
+            }
+            const int nx = bcols_pad - kcols;
+            for (int it = tid; it < nx * nr8; it += kThreads) {                  // [1 | onehot(gidx)] and zero padding
+                int c, r8;
+                fd_x.divmod(it, r8, c);
+                c += kcols;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int rr = r8 * 8 + q;
+                    v[q] = (rr < rows_left && (c == one_col || (hot0 >= 0 && s_gi[0][rr] == c - hot0))) ? 1.f : 0.f;
+                }
+                store_split(b_hi, b_term, op_off(c, r8 * 8), v);
+            }
+            publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, it_no == 0);
+        }
+    }
+    if (!rolled && bx < P.n_chunks) chunk_load(bx, 0);
+    for (int ch = bx; !rolled && ch < P.n_chunks; ch += gx, ++it_no) {
         const int slot = it_no & 1;
         const int64_t r0 = (int64_t)ch * kKC;
         const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
