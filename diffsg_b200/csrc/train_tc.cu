@@ -556,7 +556,7 @@ struct DgradArgs {
     float* dgamma;
     float* dbeta;
     int64_t B;
-    int N, K, kt, kt_pad, tmem_cols, dyvec;
+    int N, K, kt, kt_pad, tmem_cols, dyvec, rolled;
 };
 
 // column side of dgrad: B operand = W^T, (mn = k, kk = n); memory is contiguous along k -> lanes along k, 8 n values per
@@ -628,10 +628,46 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
         if (side == 0) row_chunk_load<kV>(DY, rm, row0, P.B, n0, kw, buf);
         else wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 0);
     };
-    if (side == 1) chunk_load(0);        // weights only: may run ahead of the previous kernel
-    pdl_wait();
-    if (side == 0) chunk_load(0);
-    for (int i = 0; i < nchunk; ++i) {
+    // More than one wave of tiles (large batches): rolled staging loops shared by all 256 threads — a fraction of the
+    // instruction footprint of the unrolled prefetching path; the co-resident CTAs cover the load latency instead
+    const bool rolled = P.rolled != 0;
+    if (rolled) {
+        pdl_wait();
+        for (int i = 0; i < nchunk; ++i) {
+            const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
+            const int pieces = kw >> 3;
+            if (i > 0) wait_consumed(S, phase);
+#pragma unroll 2
+            for (int a = tid; a < kRows * 8; a += kThreads) {                     // A = dy rows: 8 rows x 128 B per warp load
+                const int pc = (a >> 3) & 7, rl = ((a >> 6) << 3) | (a & 7);
+                if (pc >= pieces) continue;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                if (row0 + rl < P.B) load8<kV>(DY, row0 + rl, n0 + pc * 8, v);
+                store_split(a_hi, a_term_bytes(), op_off(rl, pc * 8), v);
+            }
+            const int total = k_pad * pieces;
+#pragma unroll 2
+            for (int it = tid; it < total; it += kThreads) {                       // B = W^T
+                int k, n8;
+                fd.divmod(it, n8, k);
+                const int nb = n0 + n8 * 8;
+                const int nv = k < k_valid ? min(P.N - nb, 8) : 0;
+                const float* base = P.w + (size_t)nb * P.K + kb + k;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * P.K) : 0.f;
+                store_split(b_hi, b_term, op_off(k, n8 * 8), v);
+            }
+            publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
+        }
+    } else {
+        if (side == 1) chunk_load(0);        // weights only: may run ahead of the previous kernel
+        pdl_wait();
+        if (side == 0) chunk_load(0);
+    }
+    for (int i = 0; !rolled && i < nchunk; ++i) {
         const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
         if (i > 0) wait_consumed(S, phase);
         if (side == 0) {
@@ -905,7 +941,7 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw
     // path below is ~60 KB of straight-line code per chunk; looping over it thrashes the instruction cache
     // (stall_no_instructions was 45-50 % of the samples), and with two CTAs x 8 warps per SM thread-level parallelism
     // covers the load latency that the register prefetch hides for small problems.
-    const bool rolled = P.n_chunks > 2 * gx;
+    const bool rolled = P.n_chunks > gx;
     if (rolled) {
         for (int ch = bx; ch < P.n_chunks; ch += gx, ++it_no) {
             const int64_t r0 = (int64_t)ch * kKC;
@@ -1196,6 +1232,7 @@ static int prep_dgrad(const diffsg_tlin_dgrad_args* a, DgradArgs& P, int& n_tile
     if (tile > smem) smem = tile;
     n_tiles = (int)((a->B + kRows - 1) / kRows);
     gy = (a->K + P.kt - 1) / P.kt;
+    P.rolled = n_tiles * gy > 296;           // more than one wave of CTAs (2 per SM)
     return DIFFSG_OK;
 }
 
