@@ -28,7 +28,7 @@ constexpr int kRows = 128;              // rows per tile = UMMA M = TMEM lanes
 constexpr int kKC = 64;                 // contraction columns per staged chunk
 constexpr uint32_t kLBO = 128;          // K-adjacent core matrices are contiguous
 constexpr uint32_t kSBO = kKC * 16;     // next 8 rows
-constexpr int kThreads = 256;          // warps 0-3: row side, warps 4-7: column side (see the scaffolding notes)
+constexpr int kThreads = 256;          // 8 warps; see the scaffolding notes
 constexpr int kWgradKT = 224;           // feature columns per wgrad CTA (+ <= 32 extra columns = 256 = max UMMA N)
 constexpr int kMaxExtra = 32;
 
@@ -172,11 +172,12 @@ __device__ __forceinline__ void pdl_wait() {
 }
 
 // ------------------------------------------------------------------------------------------------ CTA scaffolding
-// 256 threads: warps 0-3 are the ROW side (thread t == row t of the tile: A operands, LayerNorm moments), warps 4-7 the
-// COLUMN side (weights / transposed operands); both stage their operand of a chunk concurrently, the loads of chunk i+1
-// are issued before the wait for the MMAs of chunk i (software prefetch into 64 registers per thread), and all eight
-// warps share the epilogue (warp w reads the TMEM lanes of sub-partition w % 4; 32-column rounds alternate between
-// the sides).
+// 256 threads (8 warps), 2 CTAs per SM.  Operand staging is done by rolled loops shared by all threads, one 8-element
+// item (8 consecutive contraction elements of one operand row) per iteration: load fp32, optional LayerNorm -> Swish,
+// split into bf16 (hi, lo), two 16-byte stores into the core-matrix chunk.  The 16 warps of an SM cover the load
+// latency; an earlier version that unrolled 8 items per thread and prefetched the next chunk into registers was 3-4x the
+// code and bound by instruction fetch.  All eight warps share the epilogues: warp w reads the TMEM
+// lanes of sub-partition w % 4, the two warps of a sub-partition ("sides") take alternating 32-column rounds.
 struct Smem {
     uint64_t bar;
     uint32_t tmem_base;
@@ -237,67 +238,15 @@ __device__ __forceinline__ void wait_consumed(Smem& S, uint32_t& phase) {
     tcgen05_fence_after();
 }
 
-// ---- row side: one <= 64-column chunk of the 128-row tile of a row-major matrix.  Lane l of warp w covers row
-// 32 w + 8 g + (l & 7) and the 8-column piece (l >> 3) + 4 h for item u = 2 g + h: one warp-wide load touches 8 rows x
-// 128 contiguous bytes (8 cache lines instead of the 32 of a thread-per-row walk), and the 8 lanes of a quarter warp
-// store one whole 128-byte core matrix (conflict-free).
+// ---- LayerNorm moments: lane l of warp w (w < 4) covers rows 32 w + 8 g + (l & 7), g = 0..3, and every fourth
+// 8-column piece starting at l >> 3: one warp-wide load touches 8 rows x 128 contiguous bytes (8 cache lines instead of
+// the 32 of a thread-per-row walk); the four lanes that share a row meet through two shuffles.
 struct RowMap {
     int r_in, pq, wbase;
     __device__ __forceinline__ explicit RowMap(int t) : r_in(t & 7), pq((t & 31) >> 3), wbase(t & ~31) {}
     __device__ __forceinline__ int row(int u) const { return wbase + 8 * (u >> 1) + r_in; }      // row inside the tile
     __device__ __forceinline__ int piece(int u) const { return pq + 4 * (u & 1); }
 };
-template <bool kV>
-__device__ __forceinline__ void row_chunk_load(const Mat& A, const RowMap& rm, int64_t row0, int64_t B, int k0, int kw, float (&v)[8][8]) {
-    const int pieces = kw >> 3, K = A.k0 + A.k1;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int64_t row = row0 + rm.row(u);
-        const int pc = rm.piece(u), c = k0 + pc * 8;
-        const bool ok = pc < pieces && row < B;
-        if (kV || A.vec) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (ok && c < K) {
-                const float4* p = reinterpret_cast<const float4*>(c < A.k0 ? A.p0 + row * A.k0 + c : A.p1 + row * A.k1 + (c - A.k0));
-                a = __ldg(p);
-                b = __ldg(p + 1);
-            }
-            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
-            if (ok) load8<kV>(A, row, c, v[u]);
-        }
-    }
-}
-// mu / rs: LayerNorm statistics of the thread's four rows (row group g = u >> 1)
-template <bool kAct>
-__device__ __forceinline__ void row_chunk_store(uint8_t* a_hi, const RowMap& rm, int k0, int kw, const float (&mu)[4], const float (&rs)[4],
-                                                const float* s_gamma, const float* s_beta, float (&v)[8][8]) {
-    const int pieces = kw >> 3;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int pc = rm.piece(u);
-        if (pc < pieces) {
-            if (kAct) {
-                const int c = k0 + pc * 8;
-                const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c), g1 = *reinterpret_cast<const float4*>(s_gamma + c + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c), b1 = *reinterpret_cast<const float4*>(s_beta + c + 4);
-                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float m = mu[u >> 1], r = rs[u >> 1];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    // columns >= K: x = gamma = beta = 0 (zero-padded tables) -> n = 0 -> swish = 0, no per-element branch
-                    const float n = fmaf((v[u][q] - m) * r, gm[q], bt[q]);
-                    v[u][q] = n * sigmoidf_(n);
-                }
-            }
-            store_split(a_hi, a_term_bytes(), op_off(rm.row(u), pc * 8), v[u]);
-        }
-    }
-}
-
 // ---- epilogue through shared memory: the accumulator rows (thread == row == TMEM lane) are parked in a padded row-major
 // tile in the operand buffers (free after the last MMA) and leave it through row-contiguous, fully coalesced accesses
 constexpr int kTilePad = 4;             // floats; row stride 4 (mod 32) words: conflict-free 16-byte accesses from 8 rows
@@ -316,46 +265,6 @@ __device__ __forceinline__ void tmem_rows_to_tile(float* tile, int ld, uint32_t 
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[u][4 * j], v[u][4 * j + 1], v[u][4 * j + 2], v[u][4 * j + 3]);
         }
-    }
-}
-
-// ---- column side, operand whose contraction dimension is contiguous in memory: src[mn][k] with row stride ld (the
-// weights [N, K] of the forward).  Items (mn, 8-column piece), mn fastest across lanes (16-byte conflict-free shared
-// stores), <= 8 items per thread.
-template <bool kV>
-__device__ __forceinline__ void w_chunk_load(float (&v)[8][8], const float* __restrict__ w, int ld, int n0, int n_valid, int n_pad,
-                                             const FastDiv& fd, int k0, int K, int kw, bool vec, int t) {
-    const int total = n_pad * (kw >> 3);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int it = t + u * kRows;
-        int n, j;
-        fd.divmod(it, j, n);
-        const int c = k0 + j * 8;
-        const bool ok = it < total && n < n_valid && c < K;
-        if (kV || vec) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (ok) {
-                const float4* p = reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * ld + c);
-                a = __ldg(p);
-                b = __ldg(p + 1);
-            }
-            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[u][q] = (ok && c + q < K) ? __ldg(w + (size_t)(n0 + n) * ld + c + q) : 0.f;
-        }
-    }
-}
-__device__ __forceinline__ void w_chunk_store(float (&v)[8][8], uint8_t* b_hi, uint32_t b_term, int n_pad, const FastDiv& fd, int kw,
-                                              int t) {
-    const int total = n_pad * (kw >> 3);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int it = t + u * kRows;
-        int n, j;
-        fd.divmod(it, j, n);
-        if (it < total) store_split(b_hi, b_term, op_off(n, j * 8), v[u]);
     }
 }
 
@@ -383,7 +292,7 @@ template <bool kV>
 __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ Smem S;
-    __shared__ float s_gamma[256], s_beta[256];
+    __shared__ float s_gamma[256], s_beta[256], s_mu[kRows], s_rs[kRows];
     uint8_t* a_hi = smem_raw;
     uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
     const uint32_t b_term = (uint32_t)P.n_pad * kKC * 2;
@@ -402,15 +311,10 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad);
 
-    float buf[8][8];
     const FastDiv fd(n_pad);
-    if (side == 1) {                     // first weight chunk: parameters only, may run ahead of the previous kernel
-        const int kw0 = min(kKC, (K0 + 15) & ~15);
-        w_chunk_load<kV>(buf, P.w, K0, n0, n_valid, n_pad, fd, 0, K0, kw0, P.wvec, t);
-    }
     pdl_wait();
 
-    // LayerNorm moments of the thread's four rows (row side; the column side is already fetching the first weight chunk):
+    // LayerNorm moments of the thread's four rows (warps 0-3):
     // shifted one-pass sums over the lane's pieces, then over the four lanes that share a row
     const RowMap rm(t);
     const int64_t row0 = (int64_t)blockIdx.x * kRows;
@@ -452,31 +356,66 @@ __global__ void __launch_bounds__(kThreads, 2) tlin_fwd_kernel(const FwdArgs P) 
             rs[g] = rsqrtf(fmaxf(sq[g] / (float)K0 - md * md, 0.f) + kLnEps);
             const int64_t r = row0 + rm.row(2 * g);
             if (blockIdx.y == 0 && rm.pq == 0 && r < P.B) { P.mean[r] = mu[g]; P.rstd[r] = rs[g]; }
+            if (rm.pq == 0) { s_mu[rm.row(2 * g)] = mu[g]; s_rs[rm.row(2 * g)] = rs[g]; }
         }
     }
 
+    // Staging: rolled loops shared by all 256 threads, one 8-element item per iteration (see dgrad_body)
     uint32_t phase = 0;
-    auto chunk_load = [&](int i) {
-        const int seg = i >= nc0;
-        const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
-        const int kw = min(kKC, (K - k0 + 15) & ~15);
-        if (side == 0) row_chunk_load<kV>(seg ? P.a2 : P.a, rm, row0, P.B, k0, kw, buf);
-        else w_chunk_load<kV>(buf, seg ? P.w2 : P.w, K, n0, n_valid, n_pad, fd, k0, K, kw, seg ? P.wvec2 : P.wvec, t);
-    };
-    if (side == 0) chunk_load(0);
-    for (int i = 0; i < nchunk; ++i) {
-        const int seg = i >= nc0;
-        const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
-        const int kw = min(kKC, (K - k0 + 15) & ~15);
-        if (i > 0) wait_consumed(S, phase);
-        if (side == 0) {
-            if (ln && seg == 0) row_chunk_store<true>(a_hi, rm, k0, kw, mu, rs, s_gamma, s_beta, buf);
-            else row_chunk_store<false>(a_hi, rm, k0, kw, mu, rs, nullptr, nullptr, buf);
-        } else {
-            w_chunk_store(buf, b_hi, b_term, n_pad, fd, kw, t);
+    {
+        __syncthreads();                                     // row statistics visible to every staging thread
+        for (int i = 0; i < nchunk; ++i) {
+            const int seg = i >= nc0;
+            const int K = seg ? K1 : K0, k0 = (seg ? i - nc0 : i) * kKC;
+            const int kw = min(kKC, (K - k0 + 15) & ~15);
+            const int pieces = kw >> 3;
+            const Mat& A = seg ? P.a2 : P.a;
+            const bool act = ln && seg == 0;
+            if (i > 0) wait_consumed(S, phase);
+#pragma unroll 2
+            for (int a = tid; a < kRows * 8; a += kThreads) {                     // A rows: 8 rows x 128 B per warp load
+                const int pc = (a >> 3) & 7, rl = ((a >> 6) << 3) | (a & 7);
+                if (pc >= pieces) continue;
+                const int c = k0 + pc * 8;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                if (row0 + rl < P.B) load8<kV>(A, row0 + rl, c, v);
+                if (act) {
+                    const float m = s_mu[rl], r = s_rs[rl];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float n = fmaf((v[q] - m) * r, s_gamma[c + q], s_beta[c + q]);
+                        v[q] = n * sigmoidf_(n);
+                    }
+                }
+                store_split(a_hi, a_term_bytes(), op_off(rl, pc * 8), v);
+            }
+            const float* W = seg ? P.w2 : P.w;
+            const bool wv = kV || (seg ? P.wvec2 : P.wvec);
+            const int total = n_pad * pieces;
+#pragma unroll 2
+            for (int it = tid; it < total; it += kThreads) {                       // weights [N, K]
+                int n, j;
+                fd.divmod(it, j, n);
+                const int c = k0 + j * 8;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                if (n < n_valid && c < K) {
+                    const float* src = W + (size_t)(n0 + n) * K + c;
+                    if (wv) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(src)), y = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = (c + q < K) ? __ldg(src + q) : 0.f;
+                    }
+                }
+                store_split(b_hi, b_term, op_off(n, j * 8), v);
+            }
+            publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
         }
-        publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
-        if (i + 1 < nchunk) chunk_load(i + 1);
     }
     wait_consumed(S, phase);
 
@@ -556,38 +495,8 @@ struct DgradArgs {
     float* dgamma;
     float* dbeta;
     int64_t B;
-    int N, K, kt, kt_pad, tmem_cols, dyvec, rolled;
+    int N, K, kt, kt_pad, tmem_cols, dyvec;
 };
-
-// column side of dgrad: B operand = W^T, (mn = k, kk = n); memory is contiguous along k -> lanes along k, 8 n values per
-// item; items [first, first + 8) of this thread
-__device__ __forceinline__ void wt_items_load(float (&v)[8][8], const DgradArgs& P, int kb, int k_valid, int k_pad, const FastDiv& fd,
-                                              int n0, int kw, int t, int first) {
-    const int total = k_pad * (kw >> 3);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int it = t + (first + u) * kRows;
-        int k, n8;
-        fd.divmod(it, n8, k);
-        // one 64-bit base per item, 32-bit steps of K per n; rows of W beyond N / columns beyond K / items beyond the chunk: 0
-        const int nb = n0 + n8 * 8;
-        const int nv = (it < total && k < k_valid) ? min(P.N - nb, 8) : 0;
-        const float* base = P.w + (size_t)nb * P.K + kb + k;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[u][q] = q < nv ? __ldg(base + q * P.K) : 0.f;
-    }
-}
-__device__ __forceinline__ void wt_items_store(float (&v)[8][8], uint8_t* b_hi, uint32_t b_term, int k_pad, const FastDiv& fd, int kw,
-                                               int t, int first) {
-    const int total = k_pad * (kw >> 3);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int it = t + (first + u) * kRows;
-        int k, n8;
-        fd.divmod(it, n8, k);
-        if (it < total) store_split(b_hi, b_term, op_off(k, n8 * 8), v[u]);
-    }
-}
 
 template <bool kV>
 __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw, Smem& S, int bx, int by) {
@@ -617,70 +526,41 @@ __device__ __forceinline__ void dgrad_body(const DgradArgs& P, uint8_t* smem_raw
     const Mat DY{P.dy, nullptr, P.N, 0, P.dyvec};
     const int nchunk = (P.N + kKC - 1) / kKC;
     const FastDiv fd(k_pad);
-    const RowMap rm(t);
     const int64_t row0 = (int64_t)bx * kRows;
-    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
 
-    float buf[8][8];
+    // Staging: rolled loops shared by all 256 threads, one 8-element item per iteration (the two CTAs x 8 warps of an SM
+    // cover the load latency; an unrolled register-prefetch version of these loops was ~4x the code and bound by
+    // instruction fetch, stall_no_instructions 45-50 %)
     uint32_t phase = 0;
-    auto chunk_load = [&](int i) {
+    pdl_wait();
+    for (int i = 0; i < nchunk; ++i) {
         const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
-        if (side == 0) row_chunk_load<kV>(DY, rm, row0, P.B, n0, kw, buf);
-        else wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 0);
-    };
-    // More than one wave of tiles (large batches): rolled staging loops shared by all 256 threads — a fraction of the
-    // instruction footprint of the unrolled prefetching path; the co-resident CTAs cover the load latency instead
-    const bool rolled = P.rolled != 0;
-    if (rolled) {
-        pdl_wait();
-        for (int i = 0; i < nchunk; ++i) {
-            const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
-            const int pieces = kw >> 3;
-            if (i > 0) wait_consumed(S, phase);
-#pragma unroll 2
-            for (int a = tid; a < kRows * 8; a += kThreads) {                     // A = dy rows: 8 rows x 128 B per warp load
-                const int pc = (a >> 3) & 7, rl = ((a >> 6) << 3) | (a & 7);
-                if (pc >= pieces) continue;
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = 0.f;
-                if (row0 + rl < P.B) load8<kV>(DY, row0 + rl, n0 + pc * 8, v);
-                store_split(a_hi, a_term_bytes(), op_off(rl, pc * 8), v);
-            }
-            const int total = k_pad * pieces;
-#pragma unroll 2
-            for (int it = tid; it < total; it += kThreads) {                       // B = W^T
-                int k, n8;
-                fd.divmod(it, n8, k);
-                const int nb = n0 + n8 * 8;
-                const int nv = k < k_valid ? min(P.N - nb, 8) : 0;
-                const float* base = P.w + (size_t)nb * P.K + kb + k;
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * P.K) : 0.f;
-                store_split(b_hi, b_term, op_off(k, n8 * 8), v);
-            }
-            publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
-        }
-    } else {
-        if (side == 1) chunk_load(0);        // weights only: may run ahead of the previous kernel
-        pdl_wait();
-        if (side == 0) chunk_load(0);
-    }
-    for (int i = 0; !rolled && i < nchunk; ++i) {
-        const int n0 = i * kKC, kw = min(kKC, (P.N - n0 + 15) & ~15);
+        const int pieces = kw >> 3;
         if (i > 0) wait_consumed(S, phase);
-        if (side == 0) {
-            row_chunk_store<false>(a_hi, rm, n0, kw, zero4, zero4, nullptr, nullptr, buf);
-        } else {
-            wt_items_store(buf, b_hi, b_term, k_pad, fd, kw, t, 0);
-            if (k_pad * (kw >> 3) > 8 * kRows) {             // wide outputs: items 8..15 of the thread
-                wt_items_load(buf, P, kb, k_valid, k_pad, fd, n0, kw, t, 8);
-                wt_items_store(buf, b_hi, b_term, k_pad, fd, kw, t, 8);
-            }
+#pragma unroll 2
+        for (int a = tid; a < kRows * 8; a += kThreads) {                     // A = dy rows: 8 rows x 128 B per warp load
+            const int pc = (a >> 3) & 7, rl = ((a >> 6) << 3) | (a & 7);
+            if (pc >= pieces) continue;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            if (row0 + rl < P.B) load8<kV>(DY, row0 + rl, n0 + pc * 8, v);
+            store_split(a_hi, a_term_bytes(), op_off(rl, pc * 8), v);
+        }
+        const int total = k_pad * pieces;
+#pragma unroll 2
+        for (int it = tid; it < total; it += kThreads) {                       // B = W^T: (mn = k, kk = n), lanes along k
+            int k, n8;
+            fd.divmod(it, n8, k);
+            const int nb = n0 + n8 * 8;
+            const int nv = k < k_valid ? min(P.N - nb, 8) : 0;                 // rows of W beyond N / columns beyond K: 0
+            const float* base = P.w + (size_t)nb * P.K + kb + k;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * P.K) : 0.f;
+            store_split(b_hi, b_term, op_off(k, n8 * 8), v);
         }
         publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, i == 0);
-        if (i + 1 < nchunk) chunk_load(i + 1);
     }
     wait_consumed(S, phase);
 
@@ -847,36 +727,15 @@ struct WgradArgs {
     int N, K, T, n_chunks, tmem_cols, bcols_pad, dwvec, dgadd_ld;
 };
 
-// transposed operand items: (mn = feature, kk = row); lanes along the feature (contiguous in memory), 8 rows per item;
-// items [first, first + 8) of the thread.  src = element (row 0, feature 0), ld = row stride.
-__device__ __forceinline__ void tr_items_load(float (&v)[8][8], const Mat& M, int f0, int nf, const FastDiv& fd, int64_t r0, int nr8,
-                                              int64_t B, int t, int first) {
-    const int total = nf * nr8;
-    const int rows_left = (int)min(B - r0, (int64_t)kKC);          // valid rows of this chunk
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int it = t + (first + u) * kRows;
-        int f, r8;
-        fd.divmod(it, r8, f);
-        f += f0;
-        // one 64-bit base per item, 32-bit steps of the row stride; rows beyond B / items beyond the chunk: 0
-        const int ld = f < M.k0 ? M.k0 : M.k1;
-        const float* base = (f < M.k0 ? M.p0 + f : M.p1 + (f - M.k0)) + (r0 + r8 * 8) * ld;
-        const int nv = it < total ? rows_left - r8 * 8 : 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[u][q] = q < nv ? __ldg(base + q * ld) : 0.f;
-    }
-}
-
 template <bool kV>
 __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw, Smem& S, int bx, int by, int bz, int gx, int gz) {
-    __shared__ float s_mu[2][kKC], s_rs[2][kKC];
-    __shared__ int s_gi[2][kKC];
+    __shared__ float s_mu[kKC], s_rs[kKC];
+    __shared__ int s_gi[kKC];
     uint8_t* a_hi = smem_raw;
     uint8_t* b_hi = smem_raw + 2 * a_term_bytes();
     const uint32_t b_term = (uint32_t)P.bcols_pad * kKC * 2;
 
-    const int tid = threadIdx.x, warp = tid >> 5, side = warp >> 2, t = tid & 127;
+    const int tid = threadIdx.x, warp = tid >> 5, side = warp >> 2;
     const int n0 = by * 128;
     const int n_valid = min(128, P.N - n0);
     const int kb = bz * kWgradKT;
@@ -888,166 +747,78 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& P, uint8_t* smem_raw
     const int bcols = kcols + n_extra;
     const int bcols_pad = (bcols + 15) & ~15;
     const bool ln = P.gamma != nullptr;
-    const Mat DY{P.dy, nullptr, P.N, 0, 0};
-
     cta_setup(S, P.tmem_cols);
     const uint32_t d_tmem = S.tmem_base;
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)bcols_pad);
 
     pdl_wait();                          // both operands are activations / gradients of earlier kernels
-    float buf[8][8];
     uint32_t phase = 0;
     const FastDiv fd_n(n_valid), fd_k(kcols), fd_x(max(bcols_pad - kcols, 1));
-    auto chunk_load = [&](int ch, int slot) {
-        const int64_t r0 = (int64_t)ch * kKC;
-        const int nr8 = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15) >> 3;
-        if (side == 0) {
-            tr_items_load(buf, DY, n0, n_valid, fd_n, r0, nr8, P.B, t, 0);
-            if (t < kKC) {                       // per-row scalars of the chunk (LayerNorm statistics, gather index)
-                const int64_t r = r0 + t;
-                const bool ok = r < P.B;
-                s_mu[slot][t] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
-                s_rs[slot][t] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
-                s_gi[slot][t] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
-            }
-        } else {
-            tr_items_load(buf, P.a, kb, kcols, fd_k, r0, nr8, P.B, t, 0);
-        }
-    };
-    // LayerNorm -> Swish of staged feature items (column side) and the store
-    auto b_items_store = [&](int slot, int nr8, int first) {
-        const int total = kcols * nr8;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int it = t + (first + u) * kRows;
-            if (it >= total) continue;
-            int c, r8;
-            fd_k.divmod(it, r8, c);
-            if (ln) {
-                const float gm = __ldg(P.gamma + kb + c), bt = __ldg(P.beta + kb + c);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int rr = r8 * 8 + q;
-                    const float n = fmaf((buf[u][q] - s_mu[slot][rr]) * s_rs[slot][rr], gm, bt);
-                    buf[u][q] = n * sigmoidf_(n);          // rows >= B: finite, and the dy operand is 0 there
-                }
-            }
-            store_split(b_hi, b_term, op_off(c, r8 * 8), buf[u]);
-        }
-    };
 
+    // Persistent over 64-row chunks; staging by rolled loops shared by all 256 threads (see dgrad_body).  Transposed
+    // operands: (mn = feature, kk = row), lanes along the feature (contiguous in memory), 8 rows per item.
     int it_no = 0;
-    // Many chunks per CTA (large batches): a ROLLED staging loop shared by all 256 threads.  The unrolled, prefetching
-    // path below is ~60 KB of straight-line code per chunk; looping over it thrashes the instruction cache
-    // (stall_no_instructions was 45-50 % of the samples), and with two CTAs x 8 warps per SM thread-level parallelism
-    // covers the load latency that the register prefetch hides for small problems.
-    const bool rolled = P.n_chunks > gx;
-    if (rolled) {
-        for (int ch = bx; ch < P.n_chunks; ch += gx, ++it_no) {
-            const int64_t r0 = (int64_t)ch * kKC;
-            const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
-            const int nr8 = kw >> 3;
-            const int rows_left = (int)min(P.B - r0, (int64_t)kKC);
-            if (it_no > 0) wait_consumed(S, phase);
-            if (tid < kKC) {
-                const int64_t r = r0 + tid;
-                const bool ok = r < P.B;
-                s_mu[0][tid] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
-                s_rs[0][tid] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
-                s_gi[0][tid] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
-            }
-            __syncthreads();
-#pragma unroll 2
-            for (int it = tid; it < n_valid * nr8; it += kThreads) {             // A operand = dy^T
-                int nn, r8;
-                fd_n.divmod(it, r8, nn);
-                const float* base = P.dy + (r0 + r8 * 8) * P.N + n0 + nn;
-                const int nv = rows_left - r8 * 8;
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * P.N) : 0.f;
-                store_split(a_hi, a_term_bytes(), op_off(nn, r8 * 8), v);
-            }
-#pragma unroll 2
-            for (int it = tid; it < kcols * nr8; it += kThreads) {               // B operand, feature columns = act(a)^T
-                int c, r8;
-                fd_k.divmod(it, r8, c);
-                const int f = kb + c;
-                const int ld = f < P.a.k0 ? P.a.k0 : P.a.k1;
-                const float* base = (f < P.a.k0 ? P.a.p0 + f : P.a.p1 + (f - P.a.k0)) + (r0 + r8 * 8) * ld;
-                const int nv = rows_left - r8 * 8;
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * ld) : 0.f;
-                if (ln) {
-                    const float gm = __ldg(P.gamma + f), bt = __ldg(P.beta + f);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int rr = r8 * 8 + q;
-                        const float n = fmaf((v[q] - s_mu[0][rr]) * s_rs[0][rr], gm, bt);
-                        v[q] = n * sigmoidf_(n);
-                    }
-                }
-                store_split(b_hi, b_term, op_off(c, r8 * 8), v);
-            }
-            const int nx = bcols_pad - kcols;
-            for (int it = tid; it < nx * nr8; it += kThreads) {                  // [1 | onehot(gidx)] and zero padding
-                int c, r8;
-                fd_x.divmod(it, r8, c);
-                c += kcols;
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int rr = r8 * 8 + q;
-                    v[q] = (rr < rows_left && (c == one_col || (hot0 >= 0 && s_gi[0][rr] == c - hot0))) ? 1.f : 0.f;
-                }
-                store_split(b_hi, b_term, op_off(c, r8 * 8), v);
-            }
-            publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, it_no == 0);
-        }
-    }
-    if (!rolled && bx < P.n_chunks) chunk_load(bx, 0);
-    for (int ch = bx; !rolled && ch < P.n_chunks; ch += gx, ++it_no) {
-        const int slot = it_no & 1;
+    for (int ch = bx; ch < P.n_chunks; ch += gx, ++it_no) {
         const int64_t r0 = (int64_t)ch * kKC;
         const int kw = (int)min((int64_t)kKC, (P.B - r0 + 15) & ~(int64_t)15);
         const int nr8 = kw >> 3;
+        const int rows_left = (int)min(P.B - r0, (int64_t)kKC);
         if (it_no > 0) wait_consumed(S, phase);
-        __syncthreads();                                     // the chunk's per-row scalars are visible to the column side
-        if (side == 0) {
-            // A operand = dy^T
-            const int total = n_valid * nr8;
+        if (tid < kKC) {                         // per-row scalars of the chunk (LayerNorm statistics, gather index)
+            const int64_t r = r0 + tid;
+            const bool ok = r < P.B;
+            s_mu[tid] = (ln && ok) ? __ldg(P.mean + r) : 0.f;
+            s_rs[tid] = (ln && ok) ? __ldg(P.rstd + r) : 0.f;
+            s_gi[tid] = (hot0 >= 0 && ok) ? (int)P.gidx[r] : -1;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int it = tid; it < n_valid * nr8; it += kThreads) {             // A operand = dy^T
+            int nn, r8;
+            fd_n.divmod(it, r8, nn);
+            const float* base = P.dy + (r0 + r8 * 8) * P.N + n0 + nn;
+            const int nv = rows_left - r8 * 8;
+            float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int it = t + u * kRows;
-                int nn, r8;
-                fd_n.divmod(it, r8, nn);
-                if (it < total) store_split(a_hi, a_term_bytes(), op_off(nn, r8 * 8), buf[u]);
-            }
-        } else {
-            // B operand = [act(a) | 1 | onehot(gidx)]^T
-            b_items_store(slot, nr8, 0);
-            if (kcols * nr8 > 8 * kRows) {
-                tr_items_load(buf, P.a, kb, kcols, fd_k, r0, nr8, P.B, t, 8);
-                b_items_store(slot, nr8, 8);
-            }
-            const int nx = bcols_pad - kcols;
-            for (int it = t; it < nx * nr8; it += kRows) {
-                int c, r8;
-                fd_x.divmod(it, r8, c);
-                c += kcols;
-                float v[8];
+            for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * P.N) : 0.f;
+            store_split(a_hi, a_term_bytes(), op_off(nn, r8 * 8), v);
+        }
+#pragma unroll 2
+        for (int it = tid; it < kcols * nr8; it += kThreads) {               // B operand, feature columns = act(a)^T
+            int c, r8;
+            fd_k.divmod(it, r8, c);
+            const int f = kb + c;
+            const int ld = f < P.a.k0 ? P.a.k0 : P.a.k1;
+            const float* base = (f < P.a.k0 ? P.a.p0 + f : P.a.p1 + (f - P.a.k0)) + (r0 + r8 * 8) * ld;
+            const int nv = rows_left - r8 * 8;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = q < nv ? __ldg(base + q * ld) : 0.f;
+            if (ln) {
+                const float gm = __ldg(P.gamma + f), bt = __ldg(P.beta + f);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int rr = r8 * 8 + q;
-                    const bool ok = r0 + rr < P.B;
-                    v[q] = (ok && (c == one_col || (hot0 >= 0 && s_gi[slot][rr] == c - hot0))) ? 1.f : 0.f;
+                    const float n = fmaf((v[q] - s_mu[rr]) * s_rs[rr], gm, bt);
+                    v[q] = n * sigmoidf_(n);              // rows >= B: finite, and the dy operand is 0 there
                 }
-                store_split(b_hi, b_term, op_off(c, r8 * 8), v);
             }
+            store_split(b_hi, b_term, op_off(c, r8 * 8), v);
+        }
+        const int nx = bcols_pad - kcols;
+        for (int it = tid; it < nx * nr8; it += kThreads) {                  // [1 | onehot(gidx)] and the zero padding
+            int c, r8;
+            fd_x.divmod(it, r8, c);
+            c += kcols;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int rr = r8 * 8 + q;
+                v[q] = (rr < rows_left && (c == one_col || (hot0 >= 0 && s_gi[rr] == c - hot0))) ? 1.f : 0.f;
+            }
+            store_split(b_hi, b_term, op_off(c, r8 * 8), v);
         }
         publish_and_issue(S, a_hi, b_hi, b_term, kw, idesc, d_tmem, it_no == 0);
-        if (ch + gx < P.n_chunks) chunk_load(ch + gx, slot ^ 1);
     }
     if (it_no > 0) wait_consumed(S, phase);
 
@@ -1195,10 +966,10 @@ int diffsg_tlin_forward(const diffsg_tlin_fwd_args* a, void* stream) {
     if (tile > smem) smem = tile;
     // fast variant: every operand 8-column / 16-byte aligned (the generic paths compiled out: half the instructions)
     const bool all_vec = P.a.vec && P.wvec && P.yvec && (!seg2 || (P.a2.vec && P.wvec2));
-    if (int rc = set_smem(all_vec ? (const void*)tlin_fwd_kernel<true> : (const void*)tlin_fwd_kernel<false>,
-                          (size_t)kRows * (128 + kTilePad) * sizeof(float), all_vec ? 0 : 1)) return rc;
+    void (*kern)(FwdArgs) = all_vec ? tlin_fwd_kernel<true> : tlin_fwd_kernel<false>;
+    if (int rc = set_smem((const void*)kern, (size_t)kRows * (128 + kTilePad) * sizeof(float), all_vec ? 0 : 1)) return rc;
     const dim3 grid((unsigned)((a->B + kRows - 1) / kRows), (unsigned)((a->N + 127) / 128));
-    DIFFSG_CUDA_OK(launch_pdl(all_vec ? tlin_fwd_kernel<true> : tlin_fwd_kernel<false>, grid, smem, (cudaStream_t)stream, P));
+    DIFFSG_CUDA_OK(launch_pdl(kern, grid, smem, (cudaStream_t)stream, P));
     count_launch();
     return DIFFSG_OK;
 }
@@ -1232,7 +1003,6 @@ static int prep_dgrad(const diffsg_tlin_dgrad_args* a, DgradArgs& P, int& n_tile
     if (tile > smem) smem = tile;
     n_tiles = (int)((a->B + kRows - 1) / kRows);
     gy = (a->K + P.kt - 1) / P.kt;
-    P.rolled = n_tiles * gy > 296;           // more than one wave of CTAs (2 per SM)
     return DIFFSG_OK;
 }
 
