@@ -415,6 +415,32 @@ def test_training_time_path_hoisting_is_exact():
         assert rel_l2(grads[1][1][k].cpu(), grads[0][1][k].cpu()) < 2e-4, k
 
 
+def test_training_long_schedule_gathers_the_time_rows_once():
+    """More time rows than the wgrad kernel's one-hot columns (T = 40 > 31): the hoisted time path is gathered once with
+    index_select and added row by row; same eps and gradients as the per-sample time path."""
+    from diffsg_b200.train import MAX_GATHER_ROWS, unet_forward_train
+    T_long = 40
+    assert T_long > MAX_GATHER_ROWS
+    ddpm, cfg = standin_model("nu_like")
+    model = ddpm.to(DEV).model
+    B = 333
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, cfg["input_dim"], generator=g).to(DEV)
+    c = torch.rand(B, cfg["cond_dim"], generator=g).to(DEV)
+    ts = torch.randint(0, T_long, (1, B), generator=g).to(DEV)
+    m = (torch.rand(B, 1, generator=g) > 0.1).float().to(DEV)
+    w = torch.randn(B, cfg["input_dim"], generator=g).to(DEV)
+    got = []
+    for hoist in (False, True):
+        model.zero_grad(set_to_none=True)
+        eps = model.forward_steps(x, ts, T_long, c, m) if hoist else unet_forward_train(model, x, ts / T_long, c, m)
+        (eps * w).sum().backward()
+        got.append((eps.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
+    assert rel_l2(got[1][0].cpu(), got[0][0].cpu()) < 1e-5
+    for k in got[0][1]:
+        assert rel_l2(got[1][1][k].cpu(), got[0][1][k].cpu()) < 3e-4, k
+
+
 def test_trainer_cuda_graph_mode():
     """cuda_graph=True: capturing must not change the model (lr-0 warm-up, optimiser state reset), and the
     replayed step trains like the eager one (different RNG streams: compare the loss level, not bits)."""

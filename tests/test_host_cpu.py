@@ -409,3 +409,20 @@ def test_baseline_mlp_plan_codes():
     assert acts == [1, 1, 1, 3] and head == 0
     lin, acts, head = B._mlp_plan(list(B.PPOAgent(6, 5).actor))
     assert acts == [2, 2, 2, 0] and head == 0
+
+
+def test_cat_params_backward_adds_slices_into_the_parameter_grads():
+    """diffsg_b200.train._CatParams (the weight of the shared time table): forward = torch.cat, backward adds every
+    slice of the incoming gradient straight into the leaf's .grad (allocating it when absent) and returns nothing."""
+    from diffsg_b200.train import _CatParams, _TableGrad
+    ps = [torch.nn.Parameter(torch.randn(n, 4)) for n in (3, 1, 5)]
+    ps[1].grad = torch.ones_like(ps[1])
+    cat = _CatParams.apply(*ps)
+    assert torch.equal(cat, torch.cat([p.detach() for p in ps], 0))
+    g = torch.arange(cat.numel(), dtype=torch.float32).reshape(cat.shape)
+    cat.backward(g)
+    assert torch.equal(ps[0].grad, g[:3]) and torch.equal(ps[1].grad, g[3:4] + 1.0) and torch.equal(ps[2].grad, g[4:])
+    holder = _TableGrad()
+    assert holder.claim() and not holder.claim()            # only the first consumer hands the table gradient back
+    buf = holder.buffer(2, 3, "cpu")
+    assert buf is holder.buffer(2, 3, "cpu") and float(buf.abs().sum()) == 0.0
