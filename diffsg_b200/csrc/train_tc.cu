@@ -1,18 +1,20 @@
 // Training GEMMs on the 5th-generation tensor cores (sm_100a): the Linear layers of the eps-MSE training step
 // (reference ddpm_opt/UNetCF.py:83-95 ResidualBlock, :318-356 UNet1D.forward; loss classifier_free_MSR.py:100-112)
-// as three hand-written tcgen05 kernels with the LayerNorm -> Swish pairs fused in:
+// as hand-written tcgen05 kernels with the LayerNorm -> Swish pairs fused in:
 //
-//   tlin_fwd_kernel    y  = [swish(LN(a)) | a] . W^T (+ a2 . W2^T) + bias (+ bias2) (+ add) (+ gadd[gidx])
-//   tlin_dgrad_kernel  dx = dy . W, optionally pushed through the LayerNorm -> Swish backward in the epilogue
-//                      (dgamma / dbeta column sums by a shuffle butterfly), plus an optional addend
-//   tlin_wgrad_kernel  dW += dy^T . act(a), db += column sums of dy, d(gadd) += scatter of dy by gidx — the last
-//                      two on the tensor cores as well (a ones column and T one-hot columns appended to act(a))
+//   tlin_fwd_kernel           y  = [swish(LN(a)) | a] . W^T (+ a2 . W2^T) + bias (+ bias2) (+ add) (+ gadd[gidx])
+//   tlin_bwd_kernel, dgrad    dx = dy . W, optionally pushed through the LayerNorm -> Swish backward in the epilogue
+//                             (dgamma / dbeta column sums by a shuffle butterfly), plus an optional addend
+//   tlin_bwd_kernel, wgrad    dW += dy^T . act(a), db += column sums of dy, d(gadd) += scatter of dy by gidx — the last
+//                             two on the tensor cores as well (a ones column and T one-hot columns appended to act(a))
+//   (one backward launch runs up to two dgrad and two wgrad problems of a node; CTAs pick their role by block index)
 //
 // Arithmetic: operands are fp32 in HBM; every operand element is split into bf16 (hi, lo) while it is staged into
 // shared memory and each product runs as three kind::f16 (bf16) MMAs (hi.hi + lo.hi + hi.lo) with fp32 accumulation
 // in TMEM: 16 significant operand bits, fp32 range (gradients of 1e-8 do not underflow) — "bf16x3".
-// One CTA = 128 threads = one 128-row tile (thread == row == TMEM lane in every prologue / epilogue); operands are
-// UMMA K-major no-swizzle core-matrix chunks of 64 contraction columns (the sampler engine's layout, unet_tc.cuh).
+// One CTA = 256 threads = one 128-row tile (UMMA M = 128 = TMEM lanes; in the epilogues a thread owns one accumulator
+// row); operands are UMMA K-major no-swizzle core-matrix chunks of 64 contraction columns (the sampler engine's
+// layout, unet_tc.cuh).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -28,7 +30,7 @@ constexpr int kRows = 128;              // rows per tile = UMMA M = TMEM lanes
 constexpr int kKC = 64;                 // contraction columns per staged chunk
 constexpr uint32_t kLBO = 128;          // K-adjacent core matrices are contiguous
 constexpr uint32_t kSBO = kKC * 16;     // next 8 rows
-constexpr int kThreads = 256;          // 8 warps; see the scaffolding notes
+constexpr int kThreads = 256;           // 8 warps; see the scaffolding notes
 constexpr int kWgradKT = 224;           // feature columns per wgrad CTA (+ <= 32 extra columns = 256 = max UMMA N)
 constexpr int kMaxExtra = 32;
 
