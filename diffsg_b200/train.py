@@ -125,6 +125,8 @@ class _FusedLinear(torch.autograd.Function):
                 dgadd = holder.buffer(ctx.gadd_rows, width, dev)
                 dgadd_ptr, dgadd_ld = dgadd.data_ptr() + 4 * col, width
                 out[11] = dgadd if returns_it else None      # the first consumer (last in backward) hands the table back
+                if returns_it:
+                    holder.release()
             else:
                 dgadd = torch.zeros(ctx.gadd_rows, N, dtype=torch.float32, device=dev)
                 dgadd_ptr = dgadd.data_ptr()
@@ -198,6 +200,12 @@ class _TableGrad:
         if self._buf is None:
             self._buf = torch.zeros(rows, width, dtype=torch.float32, device=device)
         return self._buf
+
+    def release(self):
+        """Called by the consumer that hands the finished buffer to autograd: a second backward through the same graph
+        (retain_graph) starts from a fresh one."""
+        buf, self._buf = self._buf, None
+        return buf
 
 
 class _CatParams(torch.autograd.Function):

@@ -114,3 +114,36 @@ def test_empty_batch_launches_nothing():
     before = _lib.launch_count()
     y = fused_linear(torch.zeros(0, 8, device=device), lin)
     assert y.shape == (0, 8) and _lib.launch_count() == before
+
+
+@pytest.mark.parametrize("ln", [False, True])
+def test_dgrad_addend_through_the_c_abi(ln):
+    """diffsg_tlin_dgrad with `dres` (an addend on dx, e.g. the gradient arriving over a residual connection) and a cat
+    output split, called through the C-ABI directly."""
+    import ctypes as C
+    from diffsg_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    B, N, k0, k1 = 200, 48, 64, 32
+    K = k0 + k1
+    r = lambda *s_: torch.randn(*s_, generator=g).to(device)      # noqa: E731
+    dy, w, x, res = r(B, N), r(N, K) * K ** -0.5, r(B, K), r(B, K)
+    gamma, beta = r(K), r(K) * 0.3
+    xd = x.double().requires_grad_(True)
+    a = F.silu(F.layer_norm(xd, (K,), gamma.double(), beta.double(), 1e-5)) if ln else xd
+    (F.linear(a, w.double()) * dy.double()).sum().backward()
+    want = xd.grad + res.double()
+    mean = x.mean(1).contiguous()
+    rstd = (x.var(1, unbiased=False) + 1e-5).rsqrt().contiguous()
+    dx0, dx1 = torch.empty(B, k0, device=device), torch.empty(B, k1, device=device)
+    r0, r1 = res[:, :k0].contiguous(), res[:, k0:].contiguous()
+    x0, x1 = x[:, :k0].contiguous(), x[:, k0:].contiguous()
+    dg, db = torch.zeros(K, device=device), torch.zeros(K, device=device)
+    args = _lib.TlinDgradArgs(dy=dy.data_ptr(), w=w.data_ptr(), x=_lib.Mat(x0.data_ptr(), x1.data_ptr(), k0, k1) if ln else _lib.Mat(None, None, 0, 0),
+                              gamma=gamma.data_ptr() if ln else None, beta=beta.data_ptr() if ln else None,
+                              mean=mean.data_ptr() if ln else None, rstd=rstd.data_ptr() if ln else None,
+                              dres=_lib.Mat(r0.data_ptr(), r1.data_ptr(), k0, k1), dx=_lib.Mat(dx0.data_ptr(), dx1.data_ptr(), k0, k1),
+                              dgamma=dg.data_ptr() if ln else None, dbeta=db.data_ptr() if ln else None, B=B, N=N, K=K)
+    _lib.check(lib.diffsg_tlin_dgrad(C.byref(args), _lib.stream_ptr()), "diffsg_tlin_dgrad")
+    torch.cuda.synchronize()
+    assert rel_l2(torch.cat((dx0, dx1), 1), want) < 5e-5
