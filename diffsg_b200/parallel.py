@@ -120,11 +120,11 @@ class DataParallelTrainer:
     """eps-MSE training step of `DDPM.forward` with flat-buffer gradient all-reduce, fused Adam and
     fused EMA (reference loop: ddpm_opt/classifier_free_MSR.py:220-232).
 
-    `cuda_graph=True` captures the step once per batch shape and replays it: the ~1 300 kernels of one
-    forward + backward (cuBLAS GEMMs, fused LayerNorm-Swish, elementwise glue, the RNG draws of
-    `DDPM.forward`) become ONE graph launch, the fused Adam a second one; the NCCL all-reduce of the flat
-    gradient stays an ordinary stream-ordered call between the two.  The step is launch-bound at the
-    reference's batch sizes, so this is where the time goes."""
+    `cuda_graph=True` captures the step once per batch shape and replays it: the ~280 kernels of one
+    forward + backward (this library's tcgen05 forward / backward nodes, `diffsg_b200.train`, the elementwise
+    glue and the RNG draws of `DDPM.forward`) become ONE graph launch, the fused Adam a second one; the NCCL
+    all-reduce of the flat gradient stays an ordinary stream-ordered call between the two.  wgrad accumulates
+    straight into the flat gradient buffer (the parameters' `.grad` are views of it).  DESIGN.md §5.4."""
 
     def __init__(self, ddpm, lr=0.005, ema_device_update=True, cuda_graph=False):
         self.ddpm = ddpm
@@ -164,7 +164,7 @@ class DataParallelTrainer:
         return loss.detach()
 
     def _capture(self, y, cond):
-        """Warm up on a side stream (lazy cuBLAS / optimiser state) WITHOUT changing the model: lr = 0 during
+        """Warm up on a side stream (lazy library / optimiser state) WITHOUT changing the model: lr = 0 during
         the warm-up steps, Adam's moments and step counter reset afterwards; then capture the two graphs."""
         sy, sc = y.clone(), cond.clone()
         lr = self.opt.lr
