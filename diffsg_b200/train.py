@@ -1,11 +1,13 @@
 """Differentiable UNet1D forward for training (eps-MSE step of DDPM.forward).
 
 Every Linear of the training graph — forward, dgrad and wgrad — runs on this library's tcgen05 kernels
-(`csrc/train_tc.cu`, C-ABI diffsg_tlin_forward / _dgrad / _wgrad: bf16 hi+lo operands, fp32 TMEM accumulators), with
+(`csrc/train_tc.cu`, C-ABI diffsg_tlin_forward / diffsg_tlin_backward: bf16 hi+lo operands, fp32 TMEM accumulators), with
 the LayerNorm -> Swish in front of a Linear fused into its operand prologue (forward, wgrad) and into the dgrad
 epilogue (backward), the bias / time-embedding / condition-embedding / residual adds fused into the forward epilogue,
 and the bias gradient and the scatter of the gathered time term computed on the tensor cores inside wgrad.
-PyTorch autograd is only the glue between the fused nodes: a ResidualBlock is three nodes, the 80-channel net ~95.
+PyTorch autograd is only the glue between the fused nodes: a ResidualBlock is three nodes (forward: one launch each,
+backward: ONE launch each for its dgrad + wgrad problems), all blocks' time-embedding Linears are one node on the T
+time rows (`time_table`), the 80-channel net is 94 forward + 94 backward launches.
 Parameter gradients are accumulated IN PLACE into `p.grad` by the wgrad / dgrad kernels (`red.global.add`), so
 autograd launches no accumulation kernels for the ~400 parameter tensors.
 
