@@ -1067,15 +1067,6 @@ int diffsg_tlin_backward(const diffsg_tlin_dgrad_args* dgrads, int32_t n_dgrad, 
         ++P.nd;
     }
     if (total == 0) return DIFFSG_OK;
-    // Several waves of CTAs: the roles gain nothing from sharing a launch and each runs better alone (one role's
-    // instruction stream per launch; the kernel is far larger than the instruction cache)
-    if (total > 4 * 296 && P.nw + P.nd > 1) {
-        for (int j = 0; j < n_wgrad; ++j)
-            if (int rc = diffsg_tlin_backward(nullptr, 0, &wgrads[j], 1, stream)) return rc;
-        for (int j = 0; j < n_dgrad; ++j)
-            if (int rc = diffsg_tlin_backward(&dgrads[j], 1, nullptr, 0, stream)) return rc;
-        return DIFFSG_OK;
-    }
     bool all_vec = true;
     for (int j = 0; j < P.nw; ++j) all_vec = all_vec && P.w[j].dwvec && P.w[j].a.vec && (P.w[j].N % 8 == 0) && aligned16(P.w[j].dy);
     for (int j = 0; j < P.nd; ++j)
