@@ -426,3 +426,37 @@ def test_cat_params_backward_adds_slices_into_the_parameter_grads():
     assert holder.claim() and not holder.claim()            # only the first consumer hands the table gradient back
     buf = holder.buffer(2, 3, "cpu")
     assert buf is holder.buffer(2, 3, "cpu") and float(buf.abs().sum()) == 0.0
+
+
+def test_training_kernel_index_arithmetic_restated():
+    """Host restatement of three pieces of index arithmetic in csrc/train_tc.cu that the GPU tests only exercise on a few
+    shapes: (1) FastDiv — q = (x * ceil(2^20 / d)) >> 20 equals x // d for every item counter the staging loops form
+    (x < 4096, d <= 256) and the product fits 32 bits; (2) op_off — the UMMA K-major no-swizzle core-matrix layout
+    [mn / 8][k / 8][mn % 8][k % 8] is a bijection of a 128 x 64 chunk onto 16 KB of bf16; (3) colsum16 — the
+    recursive-halving shuffle butterfly leaves the sum of column 8 b4 + 4 b3 + 2 b2 + b1 in every lane."""
+    x = np.arange(4096, dtype=np.uint64)
+    for d in range(1, 257):
+        m = ((1 << 20) + d - 1) // d
+        assert int(x[-1]) * m < 1 << 32
+        assert np.array_equal((x * np.uint64(m)) >> np.uint64(20), x // np.uint64(d)), d
+    mn, k = np.meshgrid(np.arange(128), np.arange(64), indexing="ij")
+    off = (mn >> 3) * (64 * 16) + (k >> 3) * 128 + (mn & 7) * 16 + (k & 7) * 2
+    assert off.min() == 0 and off.max() == 128 * 64 * 2 - 2 and len(np.unique(off)) == 128 * 64 and np.all(off % 2 == 0)
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((32, 16))                      # [lane][value]
+    lanes = np.arange(32)
+
+    def halve(vals, bit, xor):                             # one butterfly step: keep one half, receive the partner's other half
+        n = vals.shape[1] // 2
+        up = (lanes & bit) != 0
+        send = np.where(up[:, None], vals[:, :n], vals[:, n:])
+        keep = np.where(up[:, None], vals[:, n:], vals[:, :n])
+        return keep + send[lanes ^ xor]
+
+    a = halve(v, 16, 16)
+    b = halve(a, 8, 8)
+    c = halve(b, 4, 4)
+    d1 = halve(c, 2, 2)[:, 0]
+    d1 = d1 + d1[lanes ^ 1]
+    col = ((lanes >> 4) & 1) * 8 + ((lanes >> 3) & 1) * 4 + ((lanes >> 2) & 1) * 2 + ((lanes >> 1) & 1)
+    assert np.allclose(d1, v.sum(0)[col])
