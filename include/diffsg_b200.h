@@ -380,6 +380,12 @@ typedef struct diffsg_tlin_wgrad_args {
 } diffsg_tlin_wgrad_args;
 int diffsg_tlin_wgrad(const diffsg_tlin_wgrad_args* args, void* stream);
 
+#ifdef __cplusplus
+static_assert(sizeof(diffsg_mat) == 24 && sizeof(diffsg_tlin_fwd_args) == 160 && sizeof(diffsg_tlin_dgrad_args) == 152 &&
+                  sizeof(diffsg_tlin_wgrad_args) == 120,
+              "diffsg_b200 ABI struct layout changed: bump DIFFSG_ABI_VERSION and the bindings");
+#endif
+
 /* The whole backward of one fused node in ONE launch: up to two dgrad and two wgrad problems (main segment + second
  * segment) that only share inputs run side by side; CTAs pick their role from the block index. */
 int diffsg_tlin_backward(const diffsg_tlin_dgrad_args* dgrads, int32_t n_dgrad, const diffsg_tlin_wgrad_args* wgrads,

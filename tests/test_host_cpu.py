@@ -217,6 +217,8 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert _lib.load().diffsg_abi_version() == _lib.ABI_VERSION
     assert ctypes.sizeof(_lib.Op) == 48 and ctypes.sizeof(_lib.Cfg) == 64 and ctypes.sizeof(_lib.SampleArgs) == 96
+    assert (ctypes.sizeof(_lib.Mat), ctypes.sizeof(_lib.TlinFwdArgs), ctypes.sizeof(_lib.TlinDgradArgs),
+            ctypes.sizeof(_lib.TlinWgradArgs)) == (24, 160, 152, 120)        # static_assert'ed in include/diffsg_b200.h
 
 
 @pytest.mark.parametrize("name", ["nu_like", "msr3c", "msr80c", "co", "attn"])
